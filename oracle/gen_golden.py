@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REFERENCE's own CPU code on seeded inputs.
+
+Needs a PETSc build of /root/reference (PETSC_DIR / PETSC_ARCH, default /tmp/petsc-probe + arch-probe: the survey's
+configure of an unmodified copy of the reference, --with-mpi=0 --with-cuda=0 --with-debugging=0 COPTFLAGS=-O2, OpenBLAS
+0.3.15 for BLAS).  It only runs in the build container; the fixtures it writes are committed and are what the tests
+read.  ref_driver.c (this directory) is the program that calls the reference's public API.
+
+Every case records inputs (or the generator parameters) together with the reference's outputs:
+  ref_mult / ref_multadd / ref_diag  -- MatMult_SeqAIJ, MatMultAdd_SeqAIJ, MatGetDiagonal_SeqAIJ (bit-exact pins)
+  ref_mdot (with -vec_mdot_use_gemv 0 = in-tree loop dvec2.c:83) / ref_mdot_gemv (default BLAS dgemv path)
+  ref_maxpy                           -- VecMAXPY_Seq (bit-exact pin)
+  ref_ilusolve / ref_jacobi           -- PCApply_ILU (ILU(0) factor + MatSolve_SeqAIJ_NaturalOrdering), PCApply_Jacobi
+  ref_dotnorm                         -- VecDot, VecNorm (BLAS; tolerance pins)
+  KSP cases: residual history, iteration count, reason, solution
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import oracle_py as O  # noqa: E402
+
+PETSC_DIR = os.environ.get("PETSC_DIR", "/tmp/petsc-probe")
+PETSC_ARCH = os.environ.get("PETSC_ARCH", "arch-probe")
+BLASDIR = "/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def build_driver():
+    exe = os.path.join(HERE, "_ref", "ref_driver")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    cmd = ["/usr/bin/gcc", "-O2", "-o", exe, os.path.join(HERE, "ref_driver.c"),
+           "-I%s/include" % PETSC_DIR, "-I%s/%s/include" % (PETSC_DIR, PETSC_ARCH),
+           "-L%s/%s/lib" % (PETSC_DIR, PETSC_ARCH), "-Wl,-rpath,%s/%s/lib" % (PETSC_DIR, PETSC_ARCH), "-lpetsc", "-lm",
+           "-Wl,-rpath,%s" % BLASDIR, "-Wl,-rpath-link,%s" % BLASDIR, "-Wl,--allow-shlib-undefined"]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def run_case(exe, ai, aj, aa, x, y, V, alpha, opts):
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = "%s/%s/lib:%s:%s" % (PETSC_DIR, PETSC_ARCH, BLASDIR, env.get("LD_LIBRARY_PATH", ""))
+    with tempfile.TemporaryDirectory() as d:
+        m, nv = len(ai) - 1, V.shape[0]
+        for name, arr in (("ai.i32", ai), ("aj.i32", aj), ("aa.f64", aa), ("x.f64", x), ("y.f64", y), ("V.f64", V),
+                          ("alpha.f64", alpha)):
+            np.ascontiguousarray(arr).tofile(os.path.join(d, name))
+        open(os.path.join(d, "meta.txt"), "w").write("%d %d %d\n" % (m, len(aj), nv))
+        subprocess.check_call([exe, d] + opts, env=env)
+        out = {}
+        for f in os.listdir(d):
+            if f.startswith("ref_") and f.endswith(".f64"):
+                out[f[:-4]] = np.fromfile(os.path.join(d, f), dtype=np.float64)
+        if os.path.exists(os.path.join(d, "ref_ksp.txt")):
+            its, reason, rnorm, nh = open(os.path.join(d, "ref_ksp.txt")).read().split()
+            out["ref_its"] = np.int64(its); out["ref_reason"] = np.int64(reason); out["ref_rnorm"] = np.float64(rnorm)
+        return out
+
+
+def main():
+    exe = build_driver()
+    os.makedirs(OUT, exist_ok=True)
+    rng = np.random.default_rng(20260923)
+
+    def vecs(m, nv):
+        return (rng.uniform(-1, 1, m), rng.uniform(-1, 1, m), rng.uniform(-1, 1, (nv, m)), rng.uniform(-1, 1, nv))
+
+    # ---- operator-level cases (small, inputs stored) ----
+    ops = {
+        "ops_lap5_21x17": (O.lap5(21, 17), 7, {"gen": "lap5", "args": [21, 17]}),
+        "ops_lap7_9x8x7": (O.lap7(9, 8, 7), 30, {"gen": "lap7", "args": [9, 8, 7]}),
+        "ops_lap27_7": (O.lap27(7), 5, {"gen": "lap27", "args": [7]}),
+        "ops_rand_402x9": (O.random_csr(402, 9, 20260923 + 9), 6, {"gen": "stored"}),
+    }
+    for name, ((ai, aj, aa), nv, meta) in ops.items():
+        if meta["gen"] == "stored":
+            # make the random matrix diagonally dominant so ILU(0) is well defined
+            d, pos = O.getdiagonal(ai, aj, aa)
+            aa = aa.copy(); aa[pos] = 12.0
+        x, y, V, alpha = vecs(len(ai) - 1, nv)
+        out = run_case(exe, ai, aj, aa, x, y, V, alpha, ["-vec_mdot_use_gemv", "0"])
+        out2 = run_case(exe, ai, aj, aa, x, y, V, alpha, [])
+        out["ref_mdot_gemv"] = out2["ref_mdot"]
+        rec = dict(x=x, y=y, V=V, alpha=alpha, gen=meta["gen"], args=np.array(meta.get("args", []), dtype=np.int64), **out)
+        if meta["gen"] == "stored":
+            rec.update(ai=ai, aj=aj, aa=aa)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print(name, "ok")
+
+    # ---- KSP cases: matrix by generator, b = A*1, reference options recorded ----
+    ksp = {
+        # ex2_1.out: -m 5 -n 5 -ksp_gmres_cgs_refinement_type refine_always, default PC (ILU), ex2.c rtol = 1e-2/((m+1)(n+1))
+        "ksp_ex2_1": ("lap5", [5, 5], ["-ksp_type", "gmres", "-pc_type", "ilu", "-ksp_gmres_cgs_refinement_type", "refine_always",
+                                         "-ksp_rtol", repr(1e-2 / 36)]),
+        # BASELINE config 1: ex2 100x100 GMRES(30)+Jacobi, rtol = 1e-2/(101*101)
+        "ksp_ex2_100_gmres_jacobi": ("lap5", [100, 100], ["-ksp_type", "gmres", "-pc_type", "jacobi", "-ksp_rtol", repr(1e-2 / 10201)]),
+        "ksp_lap5_30_gmres_none": ("lap5", [30, 30], ["-ksp_type", "gmres", "-pc_type", "none"]),
+        "ksp_lap5_30_gmres_ilu": ("lap5", [30, 30], ["-ksp_type", "gmres", "-pc_type", "ilu", "-ksp_rtol", "1e-10"]),
+        "ksp_lap5_30_gmres_ifneeded": ("lap5", [30, 30], ["-ksp_type", "gmres", "-pc_type", "jacobi", "-ksp_gmres_cgs_refinement_type", "refine_ifneeded", "-ksp_rtol", "1e-8"]),
+        "ksp_lap5_30_cg_jacobi": ("lap5", [30, 30], ["-ksp_type", "cg", "-pc_type", "jacobi", "-ksp_rtol", "1e-8"]),
+        "ksp_lap7_12_gmres_jacobi": ("lap7", [12, 12, 12], ["-ksp_type", "gmres", "-pc_type", "jacobi", "-ksp_rtol", "1e-8"]),
+        "ksp_lap7_12_gmres5_jacobi": ("lap7", [12, 11, 10], ["-ksp_type", "gmres", "-ksp_gmres_restart", "5", "-pc_type", "jacobi", "-ksp_rtol", "1e-8"]),
+        # BASELINE config 3 shape: 27-pt, CG + ILU(0)
+        "ksp_lap27_10_cg_ilu": ("lap27", [10], ["-ksp_type", "cg", "-pc_type", "ilu", "-ksp_rtol", "1e-8"]),
+        "ksp_lap27_10_gmres_ilu": ("lap27", [10], ["-ksp_type", "gmres", "-pc_type", "ilu", "-ksp_rtol", "1e-8"]),
+    }
+    for name, (gen, args, opts) in ksp.items():
+        ai, aj, aa = getattr(O, gen)(*args)
+        m = len(ai) - 1
+        z = np.zeros(m)
+        out = run_case(exe, ai, aj, aa, z + 1, z, np.zeros((1, m)), np.zeros(1), ["-solve"] + opts)
+        keep = {k: v for k, v in out.items() if k in ("ref_hist", "ref_sol", "ref_its", "ref_reason", "ref_rnorm")}
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), gen=gen, args=np.array(args, dtype=np.int64), opts=np.array(opts), **keep)
+        print(name, "its", int(out["ref_its"]), "reason", int(out["ref_reason"]), "rnorm %.12e" % float(out["ref_rnorm"]))
+
+
+if __name__ == "__main__":
+    main()

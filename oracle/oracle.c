@@ -1,0 +1,735 @@
+/*
+ * oracle.c -- CPU restatement of the reference's Krylov hot path (see oracle.h).
+ * TEST INFRASTRUCTURE ONLY: never linked into or called from the product library.
+ *
+ * Compiled with -O2 -ffp-contract=off and WITHOUT -march=native: the reference's -O2 x86-64 build
+ * has no FMA contraction and uses the generic (non-AVX512) PetscSparseDensePlusDot branch
+ * (aij.h:609-614), so the arithmetic below is bit-for-bit what MatMult_SeqAIJ etc. perform.
+ */
+#include "oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int ora_max_threads(void)
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------ generators */
+int64_t ora_lap5_nnz(int m, int n)
+{
+  return (int64_t)5 * m * n - 2 * (int64_t)m - 2 * (int64_t)n;
+}
+
+/* ex2.c:70-92: Ii = i*n + j, i in [0,m), j in [0,n); neighbours Ii-n (i>0), Ii+n (i<m-1), Ii-1 (j>0), Ii+1 (j<n-1).
+   Columns emitted sorted (MatAssemblyEnd_SeqAIJ keeps rows sorted). */
+void ora_lap5(int m, int n, int *ai, int *aj, double *aa)
+{
+  int64_t k = 0;
+  ai[0] = 0;
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++) {
+      int Ii = i * n + j;
+      if (i > 0) { aj[k] = Ii - n; aa[k++] = -1.0; }
+      if (j > 0) { aj[k] = Ii - 1; aa[k++] = -1.0; }
+      aj[k] = Ii; aa[k++] = 4.0;
+      if (j < n - 1) { aj[k] = Ii + 1; aa[k++] = -1.0; }
+      if (i < m - 1) { aj[k] = Ii + n; aa[k++] = -1.0; }
+      ai[Ii + 1] = (int)k;
+    }
+}
+
+int64_t ora_lap7_rows_nnz(int nx, int ny, int nz, int64_t r0, int64_t r1)
+{
+  int64_t k = 0, nxy = (int64_t)nx * ny;
+  for (int64_t r = r0; r < r1; r++) {
+    int x = (int)(r % nx), y = (int)((r / nx) % ny), z = (int)(r / nxy);
+    k += 1 + (x > 0) + (x < nx - 1) + (y > 0) + (y < ny - 1) + (z > 0) + (z < nz - 1);
+  }
+  return k;
+}
+
+int64_t ora_lap7_nnz(int nx, int ny, int nz)
+{
+  int64_t N = (int64_t)nx * ny * nz;
+  return 7 * N - 2 * ((int64_t)nx * ny + (int64_t)ny * nz + (int64_t)nx * nz);
+}
+
+void ora_lap7_rows(int nx, int ny, int nz, int64_t r0, int64_t r1, int *ai, int *aj, double *aa)
+{
+  int64_t k = 0, nxy = (int64_t)nx * ny;
+  ai[0] = 0;
+  for (int64_t r = r0; r < r1; r++) {
+    int x = (int)(r % nx), y = (int)((r / nx) % ny), z = (int)(r / nxy);
+    if (z > 0) { aj[k] = (int)(r - nxy); aa[k++] = -1.0; }
+    if (y > 0) { aj[k] = (int)(r - nx); aa[k++] = -1.0; }
+    if (x > 0) { aj[k] = (int)(r - 1); aa[k++] = -1.0; }
+    aj[k] = (int)r; aa[k++] = 6.0;
+    if (x < nx - 1) { aj[k] = (int)(r + 1); aa[k++] = -1.0; }
+    if (y < ny - 1) { aj[k] = (int)(r + nx); aa[k++] = -1.0; }
+    if (z < nz - 1) { aj[k] = (int)(r + nxy); aa[k++] = -1.0; }
+    ai[r - r0 + 1] = (int)k;
+  }
+}
+
+void ora_lap7(int nx, int ny, int nz, int *ai, int *aj, double *aa)
+{
+  ora_lap7_rows(nx, ny, nz, 0, (int64_t)nx * ny * nz, ai, aj, aa);
+}
+
+int64_t ora_lap27_nnz(int n)
+{
+  /* sum over rows of prod_d (1 + (c_d>0) + (c_d<n-1)) = (3n-2)^3 */
+  int64_t t = 3 * (int64_t)n - 2;
+  return t * t * t;
+}
+
+/* bench_kspsolve.c:115-303: weights by stencil class; emitted in sorted column order */
+void ora_lap27(int n, int *ai, int *aj, double *aa)
+{
+  const double h = 1.0 / (n - 1);
+  const double w[4] = {44.0 / 13 * h, -3.0 / 13 * h, -3.0 / 26 * h, -1.0 / 13 * h};
+  int64_t      k = 0, n2 = (int64_t)n * n;
+  ai[0] = 0;
+  for (int z = 0; z < n; z++)
+    for (int y = 0; y < n; y++)
+      for (int x = 0; x < n; x++) {
+        int64_t r = x + (int64_t)n * y + n2 * z;
+        for (int dz = -1; dz <= 1; dz++) {
+          if (z + dz < 0 || z + dz >= n) continue;
+          for (int dy = -1; dy <= 1; dy++) {
+            if (y + dy < 0 || y + dy >= n) continue;
+            for (int dx = -1; dx <= 1; dx++) {
+              if (x + dx < 0 || x + dx >= n) continue;
+              aj[k]   = (int)(r + dx + (int64_t)n * dy + n2 * dz);
+              aa[k++] = w[(dx != 0) + (dy != 0) + (dz != 0)];
+            }
+          }
+        }
+        ai[r + 1] = (int)k;
+      }
+}
+
+/* ------------------------------------------------------------------ Mat */
+void ora_matmult_seqaij(int m, const int *ai, const int *aj, const double *aa, const double *x, double *y)
+{
+  for (int i = 0; i < m; i++) {
+    double sum = 0.0;
+    for (int k = ai[i]; k < ai[i + 1]; k++) sum += aa[k] * x[aj[k]];
+    y[i] = sum;
+  }
+}
+
+void ora_matmult_seqaij_omp(int m, const int *ai, const int *aj, const double *aa, const double *x, double *y)
+{
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < m; i++) {
+    double sum = 0.0;
+    for (int k = ai[i]; k < ai[i + 1]; k++) sum += aa[k] * x[aj[k]];
+    y[i] = sum;
+  }
+}
+
+void ora_matmultadd_seqaij(int m, const int *ai, const int *aj, const double *aa, const double *x, const double *y, double *z)
+{
+  for (int i = 0; i < m; i++) {
+    double sum = y[i];
+    for (int k = ai[i]; k < ai[i + 1]; k++) sum += aa[k] * x[aj[k]];
+    z[i] = sum;
+  }
+}
+
+void ora_getdiagonal_seqaij(int m, const int *ai, const int *aj, const double *aa, double *d, int *diagpos)
+{
+  for (int i = 0; i < m; i++) {
+    int pos = -1;
+    for (int k = ai[i]; k < ai[i + 1]; k++)
+      if (aj[k] == i) { pos = k; break; }
+    if (diagpos) diagpos[i] = pos;
+    d[i] = pos >= 0 ? aa[pos] : 0.0;
+  }
+}
+
+/* ------------------------------------------------------------------ Vec */
+double ora_vecdot(int64_t n, const double *x, const double *y)
+{
+  double s = 0.0;
+  for (int64_t i = 0; i < n; i++) s += x[i] * y[i];
+  return s;
+}
+double ora_vecdot_omp(int64_t n, const double *x, const double *y)
+{
+  double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+  for (int64_t i = 0; i < n; i++) s += x[i] * y[i];
+  return s;
+}
+double ora_vecnorm2(int64_t n, const double *x) { return sqrt(ora_vecdot(n, x, x)); }
+void   ora_vecaxpy(int64_t n, double a, const double *x, double *y)
+{
+  for (int64_t i = 0; i < n; i++) y[i] += a * x[i];
+}
+void ora_vecaypx(int64_t n, double a, const double *x, double *y)
+{
+  for (int64_t i = 0; i < n; i++) y[i] = x[i] + a * y[i];
+}
+void ora_vecaxpby(int64_t n, double a, double b, const double *x, double *y)
+{
+  for (int64_t i = 0; i < n; i++) y[i] = a * x[i] + b * y[i];
+}
+void ora_vecwaxpy(int64_t n, double a, const double *x, const double *y, double *w)
+{
+  for (int64_t i = 0; i < n; i++) w[i] = a * x[i] + y[i];
+}
+void ora_vecscale(int64_t n, double a, double *x)
+{
+  for (int64_t i = 0; i < n; i++) x[i] *= a;
+}
+void ora_vecpointwisemult(int64_t n, const double *x, const double *y, double *w)
+{
+  for (int64_t i = 0; i < n; i++) w[i] = x[i] * y[i];
+}
+void ora_vecreciprocal(int64_t n, double *x)
+{
+  for (int64_t i = 0; i < n; i++)
+    if (x[i] != 0.0) x[i] = 1.0 / x[i];
+}
+
+/* one group of g (1..4) vectors of dvec2.c:83-303: head remainder n&3 handled element by element (highest index first,
+   as the fall-through switch does), then quads with the 4-term inner sum added to the accumulator in one step */
+static void mdot_group(int64_t n, int g, const double *x, const double *const *y, double *z)
+{
+  double  s[4] = {0, 0, 0, 0};
+  int64_t rem  = n & 3;
+  for (int64_t e = rem - 1; e >= 0; e--)
+    for (int v = 0; v < g; v++) s[v] += x[e] * y[v][e];
+  for (int64_t j = rem; j < n; j += 4) {
+    const double x0 = x[j], x1 = x[j + 1], x2 = x[j + 2], x3 = x[j + 3];
+    for (int v = 0; v < g; v++) {
+      const double *p = y[v] + j;
+      s[v] += x0 * p[0] + x1 * p[1] + x2 * p[2] + x3 * p[3];
+    }
+  }
+  for (int v = 0; v < g; v++) z[v] = s[v];
+}
+
+void ora_vecmdot(int64_t n, int nv, const double *x, const double *const *y, double *z)
+{
+  int g = nv & 3;
+  if (n == 0) {
+    for (int v = 0; v < nv; v++) z[v] = 0.0;
+    return;
+  }
+  if (g) mdot_group(n, g, x, y, z);
+  for (int v = g; v < nv; v += 4) mdot_group(n, 4, x, y + v, z + v);
+}
+
+void ora_vecmdot_omp(int64_t n, int nv, const double *x, const double *const *y, double *z)
+{
+  int     nt = ora_max_threads();
+  double *part = (double *)calloc((size_t)nt * nv, sizeof(double));
+#pragma omp parallel num_threads(nt)
+  {
+#ifdef _OPENMP
+    int t = omp_get_thread_num();
+#else
+    int t = 0;
+#endif
+    int64_t chunk = ((n + nt - 1) / nt + 3) & ~(int64_t)3, lo = t * chunk, hi = lo + chunk;
+    if (hi > n) hi = n;
+    if (lo < hi) {
+      const double *yy[64];
+      for (int v = 0; v < nv; v++) yy[v] = y[v] + lo;
+      ora_vecmdot(hi - lo, nv, x + lo, yy, part + (size_t)t * nv);
+    }
+  }
+  for (int v = 0; v < nv; v++) {
+    double s = 0;
+    for (int t = 0; t < nt; t++) s += part[(size_t)t * nv + v];
+    z[v] = s;
+  }
+  free(part);
+}
+
+static void maxpy_range(int64_t lo, int64_t hi, int nv, const double *alpha, const double *const *y, double *x)
+{
+  int g = nv & 3;
+  if (g == 3) {
+    const double a1 = alpha[0], a2 = alpha[1], a3 = alpha[2];
+    for (int64_t i = lo; i < hi; i++) x[i] += a1 * y[0][i] + a2 * y[1][i] + a3 * y[2][i];
+  } else if (g == 2) {
+    const double a1 = alpha[0], a2 = alpha[1];
+    for (int64_t i = lo; i < hi; i++) x[i] += a1 * y[0][i] + a2 * y[1][i];
+  } else if (g == 1) {
+    const double a1 = alpha[0];
+    for (int64_t i = lo; i < hi; i++) x[i] += a1 * y[0][i];
+  }
+  for (int v = g; v < nv; v += 4) {
+    const double  a1 = alpha[v], a2 = alpha[v + 1], a3 = alpha[v + 2], a4 = alpha[v + 3];
+    const double *p1 = y[v], *p2 = y[v + 1], *p3 = y[v + 2], *p4 = y[v + 3];
+    for (int64_t i = lo; i < hi; i++) x[i] += a1 * p1[i] + a2 * p2[i] + a3 * p3[i] + a4 * p4[i];
+  }
+}
+
+void ora_vecmaxpy(int64_t n, int nv, const double *alpha, const double *const *y, double *x)
+{
+  maxpy_range(0, n, nv, alpha, y, x);
+}
+
+void ora_vecmaxpy_omp(int64_t n, int nv, const double *alpha, const double *const *y, double *x)
+{
+  int nt = ora_max_threads();
+#pragma omp parallel num_threads(nt)
+  {
+#ifdef _OPENMP
+    int t = omp_get_thread_num();
+#else
+    int t = 0;
+#endif
+    int64_t chunk = (n + nt - 1) / nt, lo = t * chunk, hi = lo + chunk;
+    if (hi > n) hi = n;
+    if (lo < hi) maxpy_range(lo, hi, nv, alpha, y, x);
+  }
+}
+
+/* ------------------------------------------------------------------ ILU(0) */
+int ora_ilu0_symbolic(int n, const int *ai, const int *aj, int *bi, int *bj, int *bdiag)
+{
+  int64_t k = 0;
+  int    *adiag = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  for (int i = 0; i < n; i++) {
+    adiag[i] = -1;
+    for (int p = ai[i]; p < ai[i + 1]; p++)
+      if (aj[p] == i) { adiag[i] = p; break; }
+    if (adiag[i] < 0) { free(adiag); return -(i + 1); } /* MatGetDiagonalMarkers: missing diagonal is an error for ILU */
+  }
+  bi[0] = 0;
+  for (int i = 0; i < n; i++) { /* L part: entries left of the diagonal */
+    int nz    = adiag[i] - ai[i];
+    bi[i + 1] = bi[i] + nz;
+    for (int j = 0; j < nz; j++) bj[k++] = aj[ai[i] + j];
+  }
+  bdiag[n] = bi[n] - 1;
+  for (int i = n - 1; i >= 0; i--) { /* U part, rows stored n-1 .. 0, diagonal last */
+    int nz = ai[i + 1] - adiag[i] - 1;
+    for (int j = 0; j < nz; j++) bj[k++] = aj[adiag[i] + 1 + j];
+    bj[k++]  = i;
+    bdiag[i] = bdiag[i + 1] + nz + 1;
+  }
+  free(adiag);
+  return 0;
+}
+
+int ora_lu_numeric(int n, const int *ai, const int *aj, const double *aa, const int *bi, const int *bj, const int *bdiag,
+                   double *ba, double zeropivot, double shiftamount)
+{
+  double *rtmp   = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+  double  shift  = 0.0;
+  int     nshift = 0, newshift;
+  do {
+    newshift = 0;
+    for (int i = 0; i < n; i++) {
+      int nzL = bi[i + 1] - bi[i];
+      int nzU = bdiag[i] - bdiag[i + 1]; /* includes diagonal */
+      for (int j = 0; j < nzL; j++) rtmp[bj[bi[i] + j]] = 0.0;
+      for (int j = 0; j < nzU; j++) rtmp[bj[bdiag[i + 1] + 1 + j]] = 0.0;
+      for (int p = ai[i]; p < ai[i + 1]; p++) rtmp[aj[p]] = aa[p];
+      rtmp[i] += shift;
+      for (int k = 0; k < nzL; k++) {
+        int     row = bj[bi[i] + k];
+        double *pc  = rtmp + row;
+        if (*pc != 0.0) {
+          double        mult = *pc * ba[bdiag[row]];
+          const int    *pj   = bj + bdiag[row + 1] + 1;
+          const double *pv   = ba + bdiag[row + 1] + 1;
+          int           nz   = bdiag[row] - bdiag[row + 1] - 1;
+          *pc = mult;
+          for (int j = 0; j < nz; j++) rtmp[pj[j]] -= mult * pv[j];
+        }
+      }
+      double rs = 0.0;
+      for (int j = 0; j < nzL; j++) {
+        double v      = rtmp[bj[bi[i] + j]];
+        ba[bi[i] + j] = v;
+        rs += fabs(v);
+      }
+      for (int j = 0; j < nzU - 1; j++) {
+        double v                 = rtmp[bj[bdiag[i + 1] + 1 + j]];
+        ba[bdiag[i + 1] + 1 + j] = v;
+        rs += fabs(v);
+      }
+      /* MatPivotCheck_nz, matimpl.h:795-811 */
+      if (fabs(rtmp[i]) <= zeropivot * rs && !isnan(rtmp[i])) {
+        shift    = nshift ? shift * 2.0 : shiftamount;
+        newshift = 1;
+        nshift++;
+        if (nshift > 60) { free(rtmp); return -1; }
+        break;
+      }
+      ba[bdiag[i]] = 1.0 / rtmp[i];
+    }
+  } while (newshift);
+  free(rtmp);
+  return nshift;
+}
+
+void ora_matsolve_natural(int n, const int *bi, const int *bj, const int *bdiag, const double *ba, const double *b, double *x)
+{
+  if (!n) return;
+  x[0] = b[0];
+  for (int i = 1; i < n; i++) {
+    double sum = b[i];
+    for (int p = bi[i]; p < bi[i + 1]; p++) sum -= ba[p] * x[bj[p]];
+    x[i] = sum;
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    double sum = x[i];
+    for (int p = bdiag[i + 1] + 1; p < bdiag[i]; p++) sum -= ba[p] * x[bj[p]];
+    x[i] = sum * ba[bdiag[i]];
+  }
+}
+
+/* ------------------------------------------------------------------ MPIAIJ setup */
+void ora_split_ownership(int64_t N, int size, int64_t *rstart)
+{
+  rstart[0] = 0;
+  for (int r = 0; r < size; r++) rstart[r + 1] = rstart[r] + N / size + ((N % size) > r);
+}
+
+static int cmp_i64(const void *a, const void *b)
+{
+  int64_t x = *(const int64_t *)a, y = *(const int64_t *)b;
+  return (x > y) - (x < y);
+}
+
+int ora_mpiaij_split(int mloc, int64_t cstart, int64_t cend, const int *ai, const int64_t *ajg, const double *aa, int *Ai,
+                     int *Aj, double *Aa, int *Bi, int *Bj, double *Ba, int64_t *garray)
+{
+  int64_t nzB = 0, ka = 0, kb = 0;
+  int     ec  = 0;
+  /* mmaij.c:25-51: collect distinct off-process columns, sort ascending */
+  for (int i = 0; i < mloc; i++)
+    for (int p = ai[i]; p < ai[i + 1]; p++)
+      if (ajg[p] < cstart || ajg[p] >= cend) garray[nzB++] = ajg[p];
+  if (nzB) {
+    qsort(garray, (size_t)nzB, sizeof(int64_t), cmp_i64);
+    ec = 1;
+    for (int64_t k = 1; k < nzB; k++)
+      if (garray[k] != garray[ec - 1]) garray[ec++] = garray[k];
+  }
+  Ai[0] = Bi[0] = 0;
+  for (int i = 0; i < mloc; i++) {
+    for (int p = ai[i]; p < ai[i + 1]; p++) {
+      int64_t c = ajg[p];
+      if (c >= cstart && c < cend) {
+        Aj[ka]   = (int)(c - cstart);
+        Aa[ka++] = aa[p];
+      } else { /* mmaij.c:55-61: renumber into position within garray */
+        int lo = 0, hi = ec - 1;
+        while (lo < hi) {
+          int mid = (lo + hi) / 2;
+          if (garray[mid] < c) lo = mid + 1;
+          else hi = mid;
+        }
+        Bj[kb]   = lo;
+        Ba[kb++] = aa[p];
+      }
+    }
+    Ai[i + 1] = (int)ka;
+    Bi[i + 1] = (int)kb;
+  }
+  return ec;
+}
+
+/* ------------------------------------------------------------------ KSP */
+void ora_ksp_default_opts(ora_ksp_opts *o)
+{
+  o->pc_type    = ORA_PC_ILU0;
+  o->restart    = 30;
+  o->cgs_refine = ORA_CGS_REFINE_NEVER;
+  o->max_it     = 10000;
+  o->rtol       = 1e-5;
+  o->abstol     = 1e-50;
+  o->dtol       = 1e4;
+  o->nblocks    = 1;
+  o->use_omp    = 0;
+}
+
+typedef struct {
+  int           n, type, use_omp;
+  const int    *ai, *aj;
+  const double *aa;
+  double       *dinv;                 /* jacobi: 1/diag */
+  int           nblk;                 /* ilu / bjacobi */
+  int64_t      *rstart;
+  int         **bi, **bj, **bdiag;
+  double      **ba;
+} ora_pc;
+
+static int pc_setup(ora_pc *pc, int n, const int *ai, const int *aj, const double *aa, const ora_ksp_opts *o)
+{
+  memset(pc, 0, sizeof(*pc));
+  pc->n = n; pc->ai = ai; pc->aj = aj; pc->aa = aa; pc->type = o->pc_type; pc->use_omp = o->use_omp;
+  if (o->pc_type == ORA_PC_JACOBI) {
+    /* jacobi.c:172-270: diag -> reciprocal; zero diagonal entries become 1.0 */
+    pc->dinv = (double *)malloc(sizeof(double) * (size_t)n);
+    ora_getdiagonal_seqaij(n, ai, aj, aa, pc->dinv, NULL);
+    for (int i = 0; i < n; i++) pc->dinv[i] = pc->dinv[i] != 0.0 ? 1.0 / pc->dinv[i] : 1.0;
+  } else if (o->pc_type == ORA_PC_ILU0 || o->pc_type == ORA_PC_BJACOBI_ILU0) {
+    int nb     = o->pc_type == ORA_PC_ILU0 ? 1 : o->nblocks;
+    pc->nblk   = nb;
+    pc->rstart = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nb + 1));
+    ora_split_ownership(n, nb, pc->rstart);
+    pc->bi = (int **)calloc((size_t)nb, sizeof(int *)); pc->bj = (int **)calloc((size_t)nb, sizeof(int *));
+    pc->bdiag = (int **)calloc((size_t)nb, sizeof(int *)); pc->ba = (double **)calloc((size_t)nb, sizeof(double *));
+    for (int b = 0; b < nb; b++) {
+      /* bjacobi.c:117-123: the block is the diagonal block a->A of the row-partitioned matrix */
+      int     r0 = (int)pc->rstart[b], r1 = (int)pc->rstart[b + 1], ml = r1 - r0;
+      int64_t cap = ai[r1] - ai[r0];
+      int    *li = (int *)malloc(sizeof(int) * (size_t)(ml + 1)), *lj = (int *)malloc(sizeof(int) * (size_t)(cap + 1));
+      double *la = (double *)malloc(sizeof(double) * (size_t)(cap + 1));
+      int64_t k = 0;
+      li[0] = 0;
+      for (int i = r0; i < r1; i++) {
+        for (int p = ai[i]; p < ai[i + 1]; p++)
+          if (aj[p] >= r0 && aj[p] < r1) { lj[k] = aj[p] - r0; la[k++] = aa[p]; }
+        li[i - r0 + 1] = (int)k;
+      }
+      pc->bi[b] = (int *)malloc(sizeof(int) * (size_t)(ml + 1)); pc->bdiag[b] = (int *)malloc(sizeof(int) * (size_t)(ml + 1));
+      pc->bj[b] = (int *)malloc(sizeof(int) * (size_t)(k + 1)); pc->ba[b] = (double *)calloc((size_t)(k + 1), sizeof(double));
+      if (ora_ilu0_symbolic(ml, li, lj, pc->bi[b], pc->bj[b], pc->bdiag[b])) return -1;
+      /* ilu.c PCCreate_ILU defaults: shifttype NONZERO, shiftamount 100 eps, zeropivot 100 eps */
+      if (ora_lu_numeric(ml, li, lj, la, pc->bi[b], pc->bj[b], pc->bdiag[b], pc->ba[b], 100.0 * 2.220446049250313e-16, 100.0 * 2.220446049250313e-16) < 0) return -2;
+      free(li); free(lj); free(la);
+    }
+  }
+  return 0;
+}
+
+static void pc_apply(const ora_pc *pc, const double *x, double *y)
+{
+  if (pc->type == ORA_PC_NONE) memcpy(y, x, sizeof(double) * (size_t)pc->n);
+  else if (pc->type == ORA_PC_JACOBI) ora_vecpointwisemult(pc->n, x, pc->dinv, y); /* jacobi.c:354-362 */
+  else
+    for (int b = 0; b < pc->nblk; b++) {
+      int r0 = (int)pc->rstart[b], ml = (int)(pc->rstart[b + 1] - pc->rstart[b]);
+      ora_matsolve_natural(ml, pc->bi[b], pc->bj[b], pc->bdiag[b], pc->ba[b], x + r0, y + r0);
+    }
+}
+
+static void pc_destroy(ora_pc *pc)
+{
+  free(pc->dinv);
+  for (int b = 0; b < pc->nblk; b++) { free(pc->bi[b]); free(pc->bj[b]); free(pc->bdiag[b]); free(pc->ba[b]); }
+  free(pc->bi); free(pc->bj); free(pc->bdiag); free(pc->ba); free(pc->rstart);
+}
+
+static void k_matmult(const ora_pc *pc, const double *x, double *y)
+{
+  if (pc->use_omp) ora_matmult_seqaij_omp(pc->n, pc->ai, pc->aj, pc->aa, x, y);
+  else ora_matmult_seqaij(pc->n, pc->ai, pc->aj, pc->aa, x, y);
+}
+
+/* KSPConvergedDefault, iterativ.c:1490-1581 (zero initial guess: rnorm0 = first residual) */
+typedef struct { double rnorm0, ttol, rtol, abstol, dtol; } conv_ctx;
+static int converged_default(conv_ctx *c, int it, double rnorm)
+{
+  if (!it) { c->rnorm0 = rnorm; c->ttol = fmax(c->rtol * rnorm, c->abstol); }
+  if (isnan(rnorm) || isinf(rnorm)) return -9;
+  if (rnorm <= c->ttol) return rnorm < c->abstol ? 3 : 2;
+  if (rnorm >= c->dtol * c->rnorm0) return -4;
+  return 0;
+}
+
+#define HH(a, b)  (hh + (b) * (max_k + 2) + (a))
+#define HES(a, b) (hes + (b) * (max_k + 1) + (a))
+
+int ora_ksp_gmres(int n, const int *ai, const int *aj, const double *aa, const double *b, double *x, const ora_ksp_opts *o,
+                  ora_ksp_result *res, double *hist, int histcap)
+{
+  const int max_k = o->restart;
+  ora_pc    pc;
+  int       rc = pc_setup(&pc, n, ai, aj, aa, o);
+  if (rc) return rc;
+  double **vv = (double **)malloc(sizeof(double *) * (size_t)(max_k + 1));
+  for (int i = 0; i <= max_k; i++) vv[i] = (double *)malloc(sizeof(double) * (size_t)n);
+  double *temp = (double *)malloc(sizeof(double) * (size_t)n), *tmat = (double *)malloc(sizeof(double) * (size_t)n);
+  double *hh = (double *)calloc((size_t)(max_k + 2) * (max_k + 1), sizeof(double));
+  double *hes = (double *)calloc((size_t)(max_k + 1) * (max_k + 1), sizeof(double));
+  double *grs = (double *)calloc((size_t)max_k + 2, sizeof(double)), *cc = (double *)calloc((size_t)max_k + 2, sizeof(double));
+  double *ss = (double *)calloc((size_t)max_k + 2, sizeof(double)), *nrs = (double *)calloc((size_t)max_k + 2, sizeof(double));
+  double *lhh = (double *)calloc((size_t)max_k + 2, sizeof(double));
+  conv_ctx cv = {0, 0, o->rtol, o->abstol, o->dtol};
+  int      its = 0, reason = 0, nh = 0, guess_zero = 1, itcount = 0;
+  double   rnorm = -1.0;
+  memset(x, 0, sizeof(double) * (size_t)n);
+
+#define LOGRES(r) do { if (hist && nh < histcap) hist[nh] = (r); nh++; } while (0)
+  while (!reason) {
+    /* KSPInitialResidual, itres.c:35-73, left PC */
+    if (!guess_zero) {
+      k_matmult(&pc, x, temp);
+      memcpy(tmat, b, sizeof(double) * (size_t)n);
+      ora_vecaxpy(n, -1.0, temp, tmat);
+      pc_apply(&pc, tmat, vv[0]);
+    } else {
+      memcpy(tmat, b, sizeof(double) * (size_t)n);
+      pc_apply(&pc, b, vv[0]);
+    }
+    /* KSPGMRESCycle, gmres.c:88-193 */
+    int    it = 0, hapend = 0;
+    double resn = ora_vecnorm2(n, vv[0]), tt;
+    if (resn != 0.0) ora_vecscale(n, 1.0 / resn, vv[0]);
+    grs[0] = resn;
+    rnorm  = resn;
+    LOGRES(resn);
+    if (!resn) { reason = 3; break; }
+    reason = converged_default(&cv, its, resn);
+    while (!reason && it < max_k && its < o->max_it) {
+      if (it) LOGRES(resn);
+      /* KSP_PCApplyBAorAB, left: MatMult then PCApply (precon.c:853-854) */
+      k_matmult(&pc, vv[it], tmat);
+      pc_apply(&pc, tmat, vv[it + 1]);
+      /* borthog2.c:33-114 classical Gram-Schmidt */
+      {
+        double *h = HH(0, it), *he = HES(0, it);
+        int     nref = (o->cgs_refine == ORA_CGS_REFINE_ALWAYS) ? 2 : 1;
+        for (int j = 0; j <= it; j++) h[j] = he[j] = 0.0;
+        for (int pass = 0; pass < nref; pass++) {
+          if (pc.use_omp) ora_vecmdot_omp(n, it + 1, vv[it + 1], (const double *const *)vv, lhh);
+          else ora_vecmdot(n, it + 1, vv[it + 1], (const double *const *)vv, lhh);
+          for (int j = 0; j <= it; j++) lhh[j] = -lhh[j];
+          if (pc.use_omp) ora_vecmaxpy_omp(n, it + 1, lhh, (const double *const *)vv, vv[it + 1]);
+          else ora_vecmaxpy(n, it + 1, lhh, (const double *const *)vv, vv[it + 1]);
+          for (int j = 0; j <= it; j++) { h[j] -= lhh[j]; he[j] -= lhh[j]; }
+          if (pass == 0 && o->cgs_refine == ORA_CGS_REFINE_IFNEEDED) {
+            double hnrm = 0.0, wnrm;
+            for (int j = 0; j <= it; j++) hnrm += lhh[j] * lhh[j];
+            hnrm = sqrt(hnrm);
+            wnrm = ora_vecnorm2(n, vv[it + 1]);
+            if (wnrm < hnrm) nref = 2;
+          }
+        }
+      }
+      tt = pc.use_omp ? sqrt(ora_vecdot_omp(n, vv[it + 1], vv[it + 1])) : ora_vecnorm2(n, vv[it + 1]);
+      if (tt != 0.0) ora_vecscale(n, 1.0 / tt, vv[it + 1]);
+      *HH(it + 1, it)  = tt;
+      *HES(it + 1, it) = tt;
+      {
+        double hapbnd = fabs(tt / grs[it]);
+        if (hapbnd > 1.0e-30) hapbnd = 1.0e-30; /* gmres.c:905 haptol */
+        if (tt < hapbnd) hapend = 1;
+      }
+      /* KSPGMRESUpdateHessenberg, gmres.c:346-397 */
+      {
+        double *h = HH(0, it), t2;
+        for (int j = 1; j <= it; j++) {
+          t2   = *h;
+          *h   = cc[j - 1] * t2 + ss[j - 1] * *(h + 1);
+          h++;
+          *h = cc[j - 1] * *h - (ss[j - 1] * t2);
+        }
+        if (!hapend) {
+          t2 = sqrt(*h * *h + *(h + 1) * *(h + 1));
+          if (t2 == 0.0) { reason = -2; break; }
+          cc[it]      = *h / t2;
+          ss[it]      = *(h + 1) / t2;
+          grs[it + 1] = -(ss[it] * grs[it]);
+          grs[it]     = cc[it] * grs[it];
+          *h          = cc[it] * *h + ss[it] * *(h + 1);
+          resn        = fabs(grs[it + 1]);
+        } else resn = 0.0;
+      }
+      it++;
+      its++;
+      rnorm  = resn;
+      reason = converged_default(&cv, its, resn);
+      if (hapend && !reason) { reason = -5; break; }
+    }
+    /* KSPGMRESBuildSoln, gmres.c:298-341 */
+    if (it > 0) {
+      int k = it - 1;
+      if (*HH(k, k) != 0.0) {
+        nrs[k] = grs[k] / *HH(k, k);
+        for (int ii = 1; ii <= k; ii++) {
+          int    kk = k - ii;
+          double t3 = grs[kk];
+          for (int j = kk + 1; j <= k; j++) t3 = t3 - *HH(kk, j) * nrs[j];
+          if (*HH(kk, kk) == 0.0) { reason = -5; break; }
+          nrs[kk] = t3 / *HH(kk, kk);
+        }
+        memset(temp, 0, sizeof(double) * (size_t)n);
+        ora_vecmaxpy(n, it, nrs, (const double *const *)vv, temp);
+        ora_vecaxpy(n, 1.0, temp, x);
+      } else reason = -5;
+    }
+    if (!reason && its >= o->max_it) reason = -3;
+    if (it && reason) LOGRES(resn);
+    itcount += it;
+    if (itcount >= o->max_it) { if (!reason) reason = -3; break; }
+    guess_zero = 0;
+  }
+  res->its = its; res->reason = reason; res->rnorm = rnorm; res->nhist = nh;
+  for (int i = 0; i <= max_k; i++) free(vv[i]);
+  free(vv); free(temp); free(tmat); free(hh); free(hes); free(grs); free(cc); free(ss); free(nrs); free(lhh);
+  pc_destroy(&pc);
+  return 0;
+}
+
+int ora_ksp_cg(int n, const int *ai, const int *aj, const double *aa, const double *b, double *x, const ora_ksp_opts *o,
+               ora_ksp_result *res, double *hist, int histcap)
+{
+  ora_pc pc;
+  int    rc = pc_setup(&pc, n, ai, aj, aa, o);
+  if (rc) return rc;
+  double  *R = (double *)malloc(sizeof(double) * (size_t)n), *Z = (double *)malloc(sizeof(double) * (size_t)n);
+  double  *P = (double *)malloc(sizeof(double) * (size_t)n), *W = Z;
+  conv_ctx cv = {0, 0, o->rtol, o->abstol, o->dtol};
+  double   dp, beta, betaold = 1.0, bb = 0.0, a, dpi = 0.0, dpiold;
+  int      i = 0, reason = 0, nh = 0, its = 0;
+  memset(x, 0, sizeof(double) * (size_t)n);
+  memcpy(R, b, sizeof(double) * (size_t)n);      /* r <- b (x = 0), cg.c:163 */
+  pc_apply(&pc, R, Z);                             /* z <- Br */
+  dp = ora_vecnorm2(n, Z);                         /* KSP_NORM_PRECONDITIONED */
+  LOGRES(dp);
+  reason = converged_default(&cv, 0, dp);
+  if (!reason) {
+    beta = ora_vecdot(n, Z, R);
+    do {
+      its = i + 1;
+      if (beta == 0.0) { reason = 3; break; }
+      else if (i > 0 && beta * betaold < 0.0) { reason = -8; break; }
+      if (!i) { memcpy(P, Z, sizeof(double) * (size_t)n); bb = 0.0; }
+      else { bb = beta / betaold; ora_vecaypx(n, bb, Z, P); } /* p <- z + b p */
+      dpiold = dpi;
+      k_matmult(&pc, P, W);                         /* w <- Ap */
+      dpi     = ora_vecdot(n, P, W);
+      betaold = beta;
+      if (dpi == 0.0 || (i > 0 && ((dpi > 0) - (dpi < 0)) * ((dpiold > 0) - (dpiold < 0)) < 0)) { reason = -10; break; }
+      a = beta / dpi;
+      ora_vecaxpy(n, a, P, x);
+      ora_vecaxpy(n, -a, W, R);
+      pc_apply(&pc, R, Z);
+      dp = ora_vecnorm2(n, Z);
+      LOGRES(dp);
+      reason = converged_default(&cv, i + 1, dp);
+      if (reason) break;
+      beta = ora_vecdot(n, Z, R);
+      i++;
+    } while (i < o->max_it);
+    if (i >= o->max_it && !reason) reason = -3;
+  }
+  (void)bb;
+  res->its = its; res->reason = reason; res->rnorm = dp; res->nhist = nh;
+  free(R); free(Z); free(P);
+  pc_destroy(&pc);
+  return 0;
+}

@@ -1,0 +1,167 @@
+/*
+ * ref_driver.c -- fixture generator: runs the REFERENCE's own MATSEQAIJ/VECSEQ/KSP/PC CPU code (public PETSc API only)
+ * on inputs written by oracle/gen_golden.py and dumps the outputs as raw little-endian arrays.
+ *
+ * Test infrastructure only.  It is compiled against a PETSc build of /root/reference when one exists in the build
+ * container (PETSC_DIR/PETSC_ARCH; see gen_golden.py) and is never shipped or used at run time: the committed
+ * tests/golden/ fixtures are what the tests read.
+ *
+ * usage: ref_driver <dir> [petsc options...]
+ *   reads  <dir>/ai.i32 aj.i32 aa.f64 x.f64 y.f64 V.f64 alpha.f64 meta.txt("m nnz nv")
+ *   writes <dir>/ref_mult.f64 ref_multadd.f64 ref_diag.f64 ref_mdot.f64 ref_maxpy.f64 ref_ilusolve.f64
+ *          ref_jacobi.f64 ref_dotnorm.f64 ref_hist.f64 ref_sol.f64 ref_ksp.txt
+ */
+#include <petscksp.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+static void *rd(const char *dir, const char *name, size_t bytes)
+{
+  char  p[4096];
+  void *buf = malloc(bytes ? bytes : 1);
+  FILE *f;
+  snprintf(p, sizeof p, "%s/%s", dir, name);
+  f = fopen(p, "rb");
+  if (!f || fread(buf, 1, bytes, f) != bytes) { fprintf(stderr, "cannot read %s\n", p); exit(2); }
+  fclose(f);
+  return buf;
+}
+static void wr(const char *dir, const char *name, const void *buf, size_t bytes)
+{
+  char  p[4096];
+  FILE *f;
+  snprintf(p, sizeof p, "%s/%s", dir, name);
+  f = fopen(p, "wb");
+  fwrite(buf, 1, bytes, f);
+  fclose(f);
+}
+
+int main(int argc, char **argv)
+{
+  const char *dir;
+  int         m, nv;
+  long        nnz;
+  PetscInt   *ai, *aj;
+  PetscScalar *aa, *x, *y, *V, *alpha;
+  Mat          A;
+  Vec          vx, vy, vz, vd, *vv, vb, vu, vsol;
+  PC           pc;
+  KSP          ksp;
+  PetscBool    dosolve = PETSC_FALSE;
+
+  if (argc < 2) return 1;
+  dir = argv[1];
+  PetscCall(PetscInitialize(&argc, &argv, NULL, NULL));
+  {
+    char  p[4096];
+    FILE *f;
+    snprintf(p, sizeof p, "%s/meta.txt", dir);
+    f = fopen(p, "r");
+    if (!f || fscanf(f, "%d %ld %d", &m, &nnz, &nv) != 3) return 2;
+    fclose(f);
+  }
+  ai    = (PetscInt *)rd(dir, "ai.i32", sizeof(PetscInt) * (size_t)(m + 1));
+  aj    = (PetscInt *)rd(dir, "aj.i32", sizeof(PetscInt) * (size_t)nnz);
+  aa    = (PetscScalar *)rd(dir, "aa.f64", sizeof(PetscScalar) * (size_t)nnz);
+  x     = (PetscScalar *)rd(dir, "x.f64", sizeof(PetscScalar) * (size_t)m);
+  y     = (PetscScalar *)rd(dir, "y.f64", sizeof(PetscScalar) * (size_t)m);
+  V     = (PetscScalar *)rd(dir, "V.f64", sizeof(PetscScalar) * (size_t)m * nv);
+  alpha = (PetscScalar *)rd(dir, "alpha.f64", sizeof(PetscScalar) * (size_t)nv);
+
+  PetscCall(MatCreateSeqAIJWithArrays(PETSC_COMM_SELF, m, m, ai, aj, aa, &A));
+  PetscCall(VecCreateSeqWithArray(PETSC_COMM_SELF, 1, m, x, &vx));
+  PetscCall(VecCreateSeqWithArray(PETSC_COMM_SELF, 1, m, y, &vy));
+  PetscCall(VecDuplicate(vx, &vz));
+  PetscCall(VecDuplicate(vx, &vd));
+  {
+    const PetscScalar *z;
+    /* MatMult / MatMultAdd / MatGetDiagonal */
+    PetscCall(MatMult(A, vx, vz));
+    PetscCall(VecGetArrayRead(vz, &z)); wr(dir, "ref_mult.f64", z, sizeof(PetscScalar) * m); PetscCall(VecRestoreArrayRead(vz, &z));
+    PetscCall(MatMultAdd(A, vx, vy, vz));
+    PetscCall(VecGetArrayRead(vz, &z)); wr(dir, "ref_multadd.f64", z, sizeof(PetscScalar) * m); PetscCall(VecRestoreArrayRead(vz, &z));
+    PetscCall(MatGetDiagonal(A, vd));
+    PetscCall(VecGetArrayRead(vd, &z)); wr(dir, "ref_diag.f64", z, sizeof(PetscScalar) * m); PetscCall(VecRestoreArrayRead(vd, &z));
+  }
+  /* VecMDot / VecMAXPY / VecDot / VecNorm */
+  PetscCall(PetscMalloc1(nv, &vv));
+  for (int j = 0; j < nv; j++) PetscCall(VecCreateSeqWithArray(PETSC_COMM_SELF, 1, m, V + (size_t)j * m, &vv[j]));
+  {
+    PetscScalar *dots, dn[3];
+    PetscReal    nrm;
+    const PetscScalar *z;
+    PetscCall(PetscMalloc1(nv, &dots));
+    PetscCall(VecMDot(vx, nv, vv, dots));
+    wr(dir, "ref_mdot.f64", dots, sizeof(PetscScalar) * nv);
+    PetscCall(VecCopy(vy, vz));
+    PetscCall(VecMAXPY(vz, nv, alpha, vv));
+    PetscCall(VecGetArrayRead(vz, &z)); wr(dir, "ref_maxpy.f64", z, sizeof(PetscScalar) * m); PetscCall(VecRestoreArrayRead(vz, &z));
+    PetscCall(VecDot(vx, vy, &dn[0]));
+    PetscCall(VecNorm(vx, NORM_2, &nrm));
+    dn[1] = nrm;
+    PetscCall(VecNorm(vy, NORM_2, &nrm));
+    dn[2] = nrm;
+    wr(dir, "ref_dotnorm.f64", dn, sizeof dn);
+    PetscCall(PetscFree(dots));
+  }
+  /* PCILU(0) apply = MatSolve ; PCJACOBI apply */
+  {
+    const PetscScalar *z;
+    PetscCall(PCCreate(PETSC_COMM_SELF, &pc));
+    PetscCall(PCSetType(pc, PCILU));
+    PetscCall(PCSetOperators(pc, A, A));
+    PetscCall(PCSetUp(pc));
+    PetscCall(PCApply(pc, vx, vz));
+    PetscCall(VecGetArrayRead(vz, &z)); wr(dir, "ref_ilusolve.f64", z, sizeof(PetscScalar) * m); PetscCall(VecRestoreArrayRead(vz, &z));
+    PetscCall(PCDestroy(&pc));
+    PetscCall(PCCreate(PETSC_COMM_SELF, &pc));
+    PetscCall(PCSetType(pc, PCJACOBI));
+    PetscCall(PCSetOperators(pc, A, A));
+    PetscCall(PCSetUp(pc));
+    PetscCall(PCApply(pc, vx, vz));
+    PetscCall(VecGetArrayRead(vz, &z)); wr(dir, "ref_jacobi.f64", z, sizeof(PetscScalar) * m); PetscCall(VecRestoreArrayRead(vz, &z));
+    PetscCall(PCDestroy(&pc));
+  }
+  /* KSPSolve with b = A*1 (ex2.c / bench_kspsolve.c convention), options from the command line */
+  PetscCall(PetscOptionsGetBool(NULL, NULL, "-solve", &dosolve, NULL));
+  if (dosolve) {
+    PetscReal         *hist;
+    PetscInt           nh = 0, its, cap = 200000;
+    const PetscReal   *h;
+    const PetscScalar *z;
+    KSPConvergedReason reason;
+    PetscReal          rnorm;
+    char               p[4096];
+    FILE              *f;
+    PetscCall(VecDuplicate(vx, &vb));
+    PetscCall(VecDuplicate(vx, &vu));
+    PetscCall(VecDuplicate(vx, &vsol));
+    PetscCall(VecSet(vu, 1.0));
+    PetscCall(MatMult(A, vu, vb));
+    PetscCall(KSPCreate(PETSC_COMM_SELF, &ksp));
+    PetscCall(KSPSetOperators(ksp, A, A));
+    PetscCall(PetscMalloc1(cap, &hist));
+    PetscCall(KSPSetResidualHistory(ksp, hist, cap, PETSC_TRUE));
+    PetscCall(KSPSetFromOptions(ksp));
+    PetscCall(KSPSolve(ksp, vb, vsol));
+    PetscCall(KSPGetResidualHistory(ksp, &h, &nh));
+    PetscCall(KSPGetIterationNumber(ksp, &its));
+    PetscCall(KSPGetConvergedReason(ksp, &reason));
+    PetscCall(KSPGetResidualNorm(ksp, &rnorm));
+    wr(dir, "ref_hist.f64", h, sizeof(PetscReal) * (size_t)nh);
+    PetscCall(VecGetArrayRead(vsol, &z)); wr(dir, "ref_sol.f64", z, sizeof(PetscScalar) * m); PetscCall(VecRestoreArrayRead(vsol, &z));
+    snprintf(p, sizeof p, "%s/ref_ksp.txt", dir);
+    f = fopen(p, "w");
+    fprintf(f, "%d %d %.17g %d\n", (int)its, (int)reason, (double)rnorm, (int)nh);
+    fclose(f);
+    PetscCall(KSPDestroy(&ksp));
+    PetscCall(VecDestroy(&vb)); PetscCall(VecDestroy(&vu)); PetscCall(VecDestroy(&vsol));
+    PetscCall(PetscFree(hist));
+  }
+  for (int j = 0; j < nv; j++) PetscCall(VecDestroy(&vv[j]));
+  PetscCall(PetscFree(vv));
+  PetscCall(VecDestroy(&vx)); PetscCall(VecDestroy(&vy)); PetscCall(VecDestroy(&vz)); PetscCall(VecDestroy(&vd));
+  PetscCall(MatDestroy(&A));
+  PetscCall(PetscFinalize());
+  return 0;
+}
