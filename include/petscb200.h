@@ -1,0 +1,187 @@
+/*
+ * petscb200.h -- C ABI of libpetscb200.so: hand-written sm_100a kernels for PETSc's Krylov inner loop.
+ *
+ * This is the drop-in boundary.  The reference's device back-ends reach their kernels through a C
+ * library handle obtained from PETSc's device layer -- PetscCUBLASGetHandle() / PetscGetCurrentCUDAStream()
+ * (include/petscdevice_cuda.h:180-183) -- and then call cusparseSpMV / cublasXdot / ... with raw device pointers.
+ * Every entry point below replaces one such call site (cited per function); arguments are plain pointers and sizes,
+ * no PETSc, torch or C++ types.  Host code above this ABI stays in C: either the PETSc type plugin
+ * (petsc_plugin/, -mat_type aijb200 -vec_type b200) or the stand-alone host mirror (include/petscb200_host.h).
+ *
+ * Conventions
+ *  - PetscScalar = double, PetscInt = int32 (the reference's default configuration).
+ *  - Every function returns 0 (PETSC_SUCCESS) or a PetscErrorCode value (B200_ERR_*), never throws or exits;
+ *    b200GetLastErrorString() gives the message PetscCallCUDA would have printed.
+ *  - Pointers named d_* are device pointers; they must come from b200Malloc (256-byte aligned, padded by 256 bytes:
+ *    the SpMV kernel issues 16-byte-granular TMA bulk copies that may over-read a CSR array by < 16 bytes).
+ *  - All work is enqueued on the handle's stream (default: a non-blocking stream created with the handle; a PETSc
+ *    plugin passes PetscDefaultCudaStream via b200SetStream).  Functions returning scalars to host memory synchronise
+ *    that stream, exactly as cublasDdot with CUBLAS_POINTER_MODE_HOST does.
+ */
+#ifndef PETSCB200_H
+#define PETSCB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* PetscErrorCode values (include/petscsystypes.h:45-91) */
+enum {
+  B200_SUCCESS              = 0,
+  B200_ERR_MEM              = 55,
+  B200_ERR_SUP              = 56,
+  B200_ERR_ORDER            = 58,
+  B200_ERR_ARG_SIZ          = 60,
+  B200_ERR_ARG_WRONG        = 62,
+  B200_ERR_ARG_OUTOFRANGE   = 63,
+  B200_ERR_MAT_LU_ZRPVT     = 71,
+  B200_ERR_ARG_WRONGSTATE   = 73,
+  B200_ERR_LIB              = 76,
+  B200_ERR_ARG_NULL         = 85,
+  B200_ERR_GPU_RESOURCE     = 96,
+  B200_ERR_GPU              = 97
+};
+
+typedef struct b200Handle_s *b200Handle;
+
+/* ---- handle / stream (replaces PetscCUBLASGetHandle + PetscGetCurrentCUDAStream, petscdevice_cuda.h:180-183) ---- */
+int         b200Create(b200Handle *h, int device);          /* device < 0: current device */
+int         b200Destroy(b200Handle h);
+int         b200SetStream(b200Handle h, void *cudaStream);  /* cudaStream_t; NULL restores the handle's own stream */
+int         b200GetStream(b200Handle h, void **cudaStream);
+int         b200Synchronize(b200Handle h);
+int         b200GetDevice(b200Handle h, int *device);
+int         b200DeviceCount(int *n);
+const char *b200GetLastErrorString(void);
+const char *b200Version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
+long long   b200KernelLaunchCount(void);
+
+/* timing on the handle's stream (cudaEvent pair; bench.py measures kernels with these, not with host clocks) */
+typedef struct b200Event_s *b200Event;
+int b200EventCreate(b200Event *ev);
+int b200EventDestroy(b200Event ev);
+int b200EventRecord(b200Handle h, b200Event ev);
+int b200EventElapsedMs(b200Event start, b200Event stop, double *ms); /* synchronises on stop */
+
+/* ---- memory (replaces cudaMalloc/cudaMemcpy in aijcusparse.cu:1477-1590, veccupmimpl.h:391-440) ---- */
+int b200Malloc(b200Handle h, void **d_ptr, size_t bytes);   /* padded + aligned as the kernels require */
+int b200Free(b200Handle h, void *d_ptr);
+int b200MallocHost(void **h_ptr, size_t bytes);              /* pinned */
+int b200FreeHost(void *h_ptr);
+int b200MemcpyHtoD(b200Handle h, void *d_dst, const void *h_src, size_t bytes); /* stream-ordered, returns after completion */
+int b200MemcpyDtoH(b200Handle h, void *h_dst, const void *d_src, size_t bytes);
+int b200MemcpyDtoD(b200Handle h, void *d_dst, const void *d_src, size_t bytes); /* asynchronous */
+int b200MemcpyHtoDAsync(b200Handle h, void *d_dst, const void *h_src, size_t bytes);
+int b200MemcpyDtoHAsync(b200Handle h, void *h_dst, const void *d_src, size_t bytes);
+int b200Memset(b200Handle h, void *d_ptr, int byte, size_t bytes);
+int b200MemGetInfo(size_t *free_bytes, size_t *total_bytes);
+
+/* ---- CSR SpMV: MatMult_SeqAIJ (aij.c:1444) / cusparseSpMV CSR_ALG1 call site aijcusparse.cu:2528 ---- */
+typedef struct b200CsrPlan_s *b200CsrPlan;
+/* analysis (the cusparseSpMV_preprocess analogue, aijcusparse.cu:2517): row-length statistics, row-tile size and
+   lanes-per-row selection.  d_rowptr[m+1], d_colidx[nnz] are kept by reference (not copied). */
+int b200CsrPlanCreate(b200Handle h, int m, int n, int64_t nnz, const int *d_rowptr, const int *d_colidx, b200CsrPlan *plan);
+int b200CsrPlanDestroy(b200CsrPlan plan);
+/* tuning / introspection: lanes_per_row in {0=auto,1,2,4,8,16,32}; lanes_per_row == 1 reproduces MatMult_SeqAIJ's
+   strict left-to-right, FMA-free row sums bit for bit.  rows_per_tile 0 = auto. */
+int b200CsrPlanSetLayout(b200CsrPlan plan, int lanes_per_row, int rows_per_tile, int stages, int ctas_per_sm);
+int b200CsrPlanGetLayout(b200CsrPlan plan, int *lanes_per_row, int *rows_per_tile, int *stages, int *grid, int *smem_bytes, int *max_row_nnz);
+/* y = A x                                             (MatMult_SeqAIJ, aij.c:1444-1499) */
+int b200CsrSpMV(b200Handle h, b200CsrPlan plan, const double *d_val, const double *d_x, double *d_y);
+/* z = y + A x  (z may alias y)                        (MatMultAdd_SeqAIJ, aij.c:1606-1655) */
+int b200CsrSpMVAdd(b200Handle h, b200CsrPlan plan, const double *d_val, const double *d_x, const double *d_y, double *d_z);
+/* w = dinv .* (A x), and y = A x too when d_y != NULL  (MatMult + PCApply_Jacobi fused: precon.c:853-854 + jacobi.c:354) */
+int b200CsrSpMVJacobi(b200Handle h, b200CsrPlan plan, const double *d_val, const double *d_x, const double *d_dinv, double *d_w, double *d_y);
+/* compressed-row z = y + A x for a block whose rows are mostly empty (off-diagonal block B of MATMPIAIJ):
+   only the nrows_c rows listed in d_rindex are read/written   (MatMultAdd_SeqAIJ compressed branch, aij.c:1626-1640) */
+int b200CsrSpMVAddCompressed(b200Handle h, int nrows_c, const int *d_cr_i, const int *d_rindex, const int *d_colidx, const double *d_val, const double *d_x, const double *d_y, double *d_z);
+int b200CsrCountNonemptyRows(b200Handle h, int m, const int *d_rowptr, int *count_host);   /* MatCheckCompressedRow input */
+/* d[r] = a[diag(r)] or 0 ; d_diagpos (nullable) gets the position or -1   (MatGetDiagonal_SeqAIJ aij.c:1347, GetDiagonal_CSR aijcupm.hpp:115) */
+int b200CsrGetDiagonal(b200Handle h, int m, const int *d_rowptr, const int *d_colidx, const double *d_val, double *d_diag, int *d_diagpos);
+/* dinv[r] = 1/d[r], zero diagonal -> 1.0             (PCSetUp_Jacobi, jacobi.c:172-270) ; *nzero_host counts the zeros */
+int b200JacobiInvertDiagonal(b200Handle h, int64_t n, const double *d_diag, double *d_dinv, int *nzero_host);
+
+/* ---- BLAS-1: VECSEQ ops / cuBLAS + MDot_kernel/MAXPY_kernel call sites in vecseqcupm_impl.hpp ---- */
+int b200VecSet(b200Handle h, int64_t n, double alpha, double *d_x);                                   /* VecSet */
+int b200VecCopy(b200Handle h, int64_t n, const double *d_x, double *d_y);                             /* VecCopy */
+int b200VecScale(b200Handle h, int64_t n, double alpha, double *d_x);                                 /* bvec1.c:51 / :1473 cublasXscal */
+int b200VecAXPY(b200Handle h, int64_t n, double alpha, const double *d_x, double *d_y);               /* bvec1.c:70 / :519 cublasXaxpy */
+int b200VecAYPX(b200Handle h, int64_t n, double alpha, const double *d_x, double *d_y);               /* dvec2.c:753  y = x + a y */
+int b200VecAXPBY(b200Handle h, int64_t n, double alpha, double beta, const double *d_x, double *d_y); /* bvec1.c:91   y = a x + b y */
+int b200VecWAXPY(b200Handle h, int64_t n, double alpha, const double *d_x, const double *d_y, double *d_w); /* dvec2.c:791 w = a x + y */
+int b200VecPointwiseMult(b200Handle h, int64_t n, const double *d_x, const double *d_y, double *d_w); /* bvec2.c:72 */
+int b200VecPointwiseDivide(b200Handle h, int64_t n, const double *d_x, const double *d_y, double *d_w);
+int b200VecReciprocal(b200Handle h, int64_t n, double *d_x);
+int b200VecShift(b200Handle h, int64_t n, double shift, double *d_x);
+/* reductions: result in host memory, stream synchronised on return */
+int b200VecDot(b200Handle h, int64_t n, const double *d_x, const double *d_y, double *result);        /* bvec1.c:33 / :1125 cublasXdot */
+int b200VecNorm2(b200Handle h, int64_t n, const double *d_x, double *result);                         /* bvec2.c:201 / :1749 cublasXnrm2 */
+int b200VecNorm(b200Handle h, int64_t n, const double *d_x, int type /*0:1-norm 1:2-norm 3:inf*/, double *result);
+int b200VecSum(b200Handle h, int64_t n, const double *d_x, double *result);
+int b200VecMax(b200Handle h, int64_t n, const double *d_x, int64_t *idx, double *result);
+int b200VecMin(b200Handle h, int64_t n, const double *d_x, int64_t *idx, double *result);
+/* z[j] = x . y_j, j < nv : ONE kernel, x read once       (VecMDot_Seq dvec2.c:83 / MDot_kernel vecseqcupm_impl.hpp:1148-1360)
+   y = host array of nv device pointers */
+int b200VecMDot(b200Handle h, int64_t n, int nv, const double *d_x, const double *const *y, double *result);
+/* x += sum_j alpha_j y_j : ONE pass, association identical to VecMAXPY_Seq (dvec2.c:658, petscaxpy.h:125): the
+   nv&3 remainder group first, then groups of 4, FMA-free -> bit-identical to the CPU reference.
+   norm2_out (nullable): 2-norm of the UPDATED x from the same pass (fused MAXPY+norm; host value, synchronises) */
+int b200VecMAXPY(b200Handle h, int64_t n, int nv, const double *alpha, const double *const *y, double *d_x, double *norm2_out);
+/* y += alpha x and dot = y_new . z in one pass (fused AXPY+dot; z may be y for the squared norm) */
+int b200VecAXPYDot(b200Handle h, int64_t n, double alpha, const double *d_x, double *d_y, const double *d_z, double *result);
+/* device-result variants (no host sync): results land in d_result[nv]; used by the MPI vector type, which all-reduces
+   them before the single device->host copy (pvecimpl.h:97-172) */
+int b200VecMDotAsync(b200Handle h, int64_t n, int nv, const double *d_x, const double *const *y, double *d_result);
+int b200VecMAXPYAsync(b200Handle h, int64_t n, int nv, const double *alpha, const double *const *y, double *d_x, double *d_sumsq /*nullable*/);
+
+/* ---- ILU(0): MatILUFactorSymbolic_SeqAIJ_ilu0 / MatLUFactorNumeric_SeqAIJ / MatSolve_SeqAIJ_NaturalOrdering
+        (aijfact.c:1471, 216, 2413) ; cusparseXcsrilu02 + cusparseSpSV call sites aijcusparse.cu:766-827, 643-693 ---- */
+typedef struct b200IluPlan_s *b200IluPlan;
+/* symbolic: factor layout bi/bj/bdiag exactly as aijfact.c:1454-1469, plus dependency analysis for the device solves.
+   Host CSR pattern in, everything else on device. */
+int b200Ilu0Symbolic(b200Handle h, int n, const int *h_ai, const int *h_aj, b200IluPlan *plan);
+int b200Ilu0Destroy(b200IluPlan plan);
+/* numeric factorisation on device from A's device values (same row/element operation order as aijfact.c:216-389,
+   FMA-free => factor bit-identical to the CPU reference); shifttype NONZERO semantics (matimpl.h:795-811) */
+int b200Ilu0Numeric(b200Handle h, b200IluPlan plan, const double *d_aval, double zeropivot, double shiftamount, int *nshift);
+/* x = U^{-1} L^{-1} b (aijfact.c:2413-2457), rows summed left to right without FMA: bit-identical */
+int b200Ilu0Solve(b200Handle h, b200IluPlan plan, const double *d_b, double *d_x);
+int b200Ilu0GetFactor(b200Handle h, b200IluPlan plan, int *h_bi, int *h_bj, int *h_bdiag, double *h_ba); /* tests: copies out */
+int b200Ilu0GetInfo(b200IluPlan plan, int *nlevels_lower, int *nlevels_upper, int64_t *nnz);
+
+/* ---- multi-GPU: NCCL replaces MPI in VecScatter/PetscSF (sfbasic.c:352-381, sfmpi.c:6-47) and MPIU_Allreduce
+        (pvecimpl.h:101-171) ---- */
+#define B200_UNIQUE_ID_BYTES 128
+int b200CommGetUniqueId(void *id128);                                    /* rank 0, then broadcast out-of-band */
+int b200CommInitRank(b200Handle h, int nranks, int rank, const void *id128);
+int b200CommDestroy(b200Handle h);
+int b200CommRank(b200Handle h, int *rank, int *nranks);                  /* 0,1 when no communicator */
+int b200CommAllreduceSum(b200Handle h, double *d_buf, int count);        /* in place, on the handle's stream */
+int b200CommAllreduceMax(b200Handle h, double *d_buf, int count);
+int b200CommBarrier(b200Handle h);
+/* setup-time exchange of 32-bit index lists: segment p of d_send (sendcounts[p] ints, rank order) goes to rank p */
+int b200CommAlltoallvInt(b200Handle h, const int *sendcounts, const int *d_send, const int *recvcounts, int *d_recv);
+/* Halo plan = the Mvctx scatter of MatSetUpMultiply_MPIAIJ (mmaij.c:108-117): for each peer, which of MY entries it
+   needs (send lists, local indices) and how many consecutive lvec slots I receive from it (garray is sorted, so the
+   entries owned by one rank are contiguous in lvec: no unpack kernel). */
+typedef struct b200Halo_s *b200Halo;
+int b200HaloCreate(b200Handle h, int npeers, const int *peers, const int *send_counts, const int *h_send_idx /*concatenated*/,
+                   const int *recv_counts, const int *recv_offsets, b200Halo *halo);
+int b200HaloDestroy(b200Halo halo);
+/* pack x[send_idx] and ncclSend/ncclRecv on the handle's halo stream (ordered after work already on the main stream) */
+int b200HaloBegin(b200Handle h, b200Halo halo, const double *d_x, double *d_lvec);
+/* make the main stream wait for the exchange */
+int b200HaloEnd(b200Handle h, b200Halo halo);
+
+/* ---- device-side generators of the benchmark operators (bench/test utility; SURVEY 8d inputs) ---- */
+/* rows [r0,r1) of the 7-point nx*ny*nz Laplacian, local row pointer, GLOBAL 32-bit columns */
+int b200GenLaplace7(b200Handle h, int nx, int ny, int nz, int64_t r0, int64_t r1, int *d_rowptr, int *d_colidx, double *d_val);
+int b200GenLaplace7Nnz(int nx, int ny, int nz, int64_t r0, int64_t r1, int64_t *nnz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,657 @@
+/*
+ * blas1.cu -- BLAS-1 kernels of the Krylov loop for sm_100a (HBM-bound streaming kernels, no tensor cores).
+ *
+ * Replaces, per SURVEY.md 2.1: cuBLAS axpy/dot/nrm2/scal (vecseqcupm_impl.hpp:519,1125,1749,1473), MDot_kernel<N<=8> +
+ * sum_kernel (:1148-1240), MAXPY_kernel<N<=8> (:959-988), thrust pointwise ops (:202-251).
+ *
+ * Design
+ *  - 128-bit (double2) loads/stores on the 16-byte-aligned fast path, grid-stride, all loads of an iteration issued
+ *    before the first use (memory-level parallelism), grid = SMs x resident CTAs.
+ *  - VecMDot: ONE kernel for any nv <= 32, x is read once, the nv dot products accumulate in registers; the
+ *    cross-CTA stage is atomic-free and deterministic: per-CTA partials + a ticket counter, the last CTA to arrive
+ *    sums the partials in fixed order with warp shuffles and writes the results to device memory AND to mapped pinned
+ *    host memory (so the host needs one stream sync, no extra memcpy).
+ *  - VecMAXPY: ONE pass (x read and written once) with the association of VecMAXPY_Seq (dvec2.c:658-693,
+ *    petscaxpy.h:125-150) and __dmul_rn/__dadd_rn (no FMA contraction): bit-identical to the CPU reference.
+ *    Optionally accumulates ||x_new||^2 in the same pass (fused MAXPY+norm for VecNormalize in KSPGMRESCycle).
+ */
+#include "b200_internal.h"
+
+#define TPB 256
+
+struct PtrPack {
+  const double *p[B200_MAX_NV];
+};
+struct AlphaPack {
+  double a[B200_MAX_NV];
+};
+
+static inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
+
+static int ew_grid(b200Handle h, int64_t nwork)
+{
+  int64_t blocks = (nwork + TPB - 1) / TPB;
+  int64_t cap    = (int64_t)h->num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+/* ------------------------------------------------------------------ elementwise */
+enum { OP_SET, OP_COPY, OP_SCALE, OP_AXPY, OP_AYPX, OP_AXPBY, OP_WAXPY, OP_PMULT, OP_PDIV, OP_RECIP, OP_SHIFT };
+
+template <int OP>
+__device__ __forceinline__ double ew_apply(double a, double b, double x, double y)
+{
+  /* x = first input, y = second input (or old output for in-place ops) */
+  if (OP == OP_SET) return a;
+  if (OP == OP_COPY) return x;
+  if (OP == OP_SCALE) return a * x;
+  if (OP == OP_AXPY) return y + a * x;   /* y += a x */
+  if (OP == OP_AYPX) return x + a * y;   /* y = x + a y */
+  if (OP == OP_AXPBY) return a * x + b * y;
+  if (OP == OP_WAXPY) return a * x + y;
+  if (OP == OP_PMULT) return __dmul_rn(x, y);
+  if (OP == OP_PDIV) return y != 0.0 ? x / y : 0.0;
+  if (OP == OP_RECIP) return x != 0.0 ? 1.0 / x : 0.0;
+  if (OP == OP_SHIFT) return x + a;
+  return 0.0;
+}
+
+template <int OP> struct ew_traits {
+  static constexpr int nin = (OP == OP_SET) ? 0 : (OP == OP_COPY || OP == OP_SCALE || OP == OP_RECIP || OP == OP_SHIFT) ? 1 : 2;
+};
+
+/* in0 = x, in1 = y (second operand; for in-place ops in1 == out) */
+template <int OP, int UNR>
+__global__ void __launch_bounds__(TPB) ew_kernel_v2(int64_t n, double a, double b, const double *__restrict__ in0, const double *in1, double *out)
+{
+  constexpr int nin    = ew_traits<OP>::nin;
+  const int64_t nvec   = n >> 1;
+  const int64_t stride = (int64_t)gridDim.x * TPB;
+  int64_t       i      = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  const double2 *x2 = reinterpret_cast<const double2 *>(in0);
+  const double2 *y2 = reinterpret_cast<const double2 *>(in1);
+  double2       *o2 = reinterpret_cast<double2 *>(out);
+  for (; i < nvec; i += stride * UNR) {
+    double2 xv[UNR], yv[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      int64_t k = i + u * stride;
+      if (k < nvec) {
+        if (nin >= 1) xv[u] = x2[k];
+        if (nin >= 2) yv[u] = y2[k];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      int64_t k = i + u * stride;
+      if (k < nvec) {
+        double2 r;
+        r.x = ew_apply<OP>(a, b, xv[u].x, yv[u].x);
+        r.y = ew_apply<OP>(a, b, xv[u].y, yv[u].y);
+        o2[k] = r;
+      }
+    }
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    int64_t k = n - 1;
+    out[k]    = ew_apply<OP>(a, b, nin >= 1 ? in0[k] : 0.0, nin >= 2 ? in1[k] : 0.0);
+  }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(TPB) ew_kernel_s(int64_t n, double a, double b, const double *in0, const double *in1, double *out)
+{
+  constexpr int nin    = ew_traits<OP>::nin;
+  const int64_t stride = (int64_t)gridDim.x * TPB;
+  for (int64_t k = (int64_t)blockIdx.x * TPB + threadIdx.x; k < n; k += stride) out[k] = ew_apply<OP>(a, b, nin >= 1 ? in0[k] : 0.0, nin >= 2 ? in1[k] : 0.0);
+}
+
+template <int OP>
+static int ew_launch(b200Handle h, int64_t n, double a, double b, const double *in0, const double *in1, double *out)
+{
+  B200_CHECK(h, B200_ERR_ARG_NULL, "null handle");
+  B200_CHECK(n >= 0, B200_ERR_ARG_OUTOFRANGE, "negative length");
+  if (!n) return 0;
+  constexpr int nin = ew_traits<OP>::nin;
+  B200_CHECK(out && (nin < 1 || in0) && (nin < 2 || in1), B200_ERR_ARG_NULL, "null vector pointer");
+  bool al = aligned16(out) && (nin < 1 || aligned16(in0)) && (nin < 2 || aligned16(in1));
+  if (al) {
+    constexpr int UNR = 4;
+    int           g   = ew_grid(h, ((n >> 1) + UNR - 1) / UNR);
+    ew_kernel_v2<OP, UNR><<<g, TPB, 0, h->stream>>>(n, a, b, in0, in1, out);
+  } else {
+    ew_kernel_s<OP><<<ew_grid(h, n), TPB, 0, h->stream>>>(n, a, b, in0, in1, out);
+  }
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  return 0;
+}
+
+extern "C" int b200VecSet(b200Handle h, int64_t n, double alpha, double *x) { return ew_launch<OP_SET>(h, n, alpha, 0, NULL, NULL, x); }
+extern "C" int b200VecCopy(b200Handle h, int64_t n, const double *x, double *y)
+{
+  if (x == y) return 0;
+  return ew_launch<OP_COPY>(h, n, 0, 0, x, NULL, y);
+}
+extern "C" int b200VecScale(b200Handle h, int64_t n, double alpha, double *x) { return ew_launch<OP_SCALE>(h, n, alpha, 0, x, NULL, x); }
+extern "C" int b200VecAXPY(b200Handle h, int64_t n, double alpha, const double *x, double *y) { return ew_launch<OP_AXPY>(h, n, alpha, 0, x, y, y); }
+extern "C" int b200VecAYPX(b200Handle h, int64_t n, double alpha, const double *x, double *y) { return ew_launch<OP_AYPX>(h, n, alpha, 0, x, y, y); }
+extern "C" int b200VecAXPBY(b200Handle h, int64_t n, double alpha, double beta, const double *x, double *y) { return ew_launch<OP_AXPBY>(h, n, alpha, beta, x, y, y); }
+extern "C" int b200VecWAXPY(b200Handle h, int64_t n, double alpha, const double *x, const double *y, double *w) { return ew_launch<OP_WAXPY>(h, n, alpha, 0, x, y, w); }
+extern "C" int b200VecPointwiseMult(b200Handle h, int64_t n, const double *x, const double *y, double *w) { return ew_launch<OP_PMULT>(h, n, 0, 0, x, y, w); }
+extern "C" int b200VecPointwiseDivide(b200Handle h, int64_t n, const double *x, const double *y, double *w) { return ew_launch<OP_PDIV>(h, n, 0, 0, x, y, w); }
+extern "C" int b200VecReciprocal(b200Handle h, int64_t n, double *x) { return ew_launch<OP_RECIP>(h, n, 0, 0, x, NULL, x); }
+extern "C" int b200VecShift(b200Handle h, int64_t n, double s, double *x) { return ew_launch<OP_SHIFT>(h, n, s, 0, x, NULL, x); }
+
+/* ------------------------------------------------------------------ reductions: shared final stage */
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+/* Block-level + grid-level reduction of NV per-thread accumulators.  RED: 0 = sum, 1 = max.
+   partials layout [NV][gridDim.x]; the last CTA (ticket counter) reduces them in a fixed order. */
+template <int NV, int RED>
+__device__ __forceinline__ void grid_reduce(double (&acc)[NV], double *partials, unsigned int *counter, double *d_result, double *h_result)
+{
+  __shared__ double   s_part[NV][TPB / 32];
+  __shared__ unsigned s_last;
+  const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    double v = RED ? warp_max(acc[j]) : warp_sum(acc[j]);
+    if (lane == 0) s_part[j][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double v = s_part[threadIdx.x][0];
+#pragma unroll
+    for (int w = 1; w < TPB / 32; w++) v = RED ? fmax(v, s_part[threadIdx.x][w]) : v + s_part[threadIdx.x][w];
+    partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int j = warp; j < NV; j += TPB / 32) {
+      double v = RED ? -INFINITY : 0.0;
+      for (unsigned b = lane; b < gridDim.x; b += 32) {
+        double p = __ldcg(&partials[(size_t)j * gridDim.x + b]);
+        v        = RED ? fmax(v, p) : v + p;
+      }
+      v = RED ? warp_max(v) : warp_sum(v);
+      if (lane == 0) {
+        d_result[j] = v;
+        if (h_result) h_result[j] = v;
+      }
+    }
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+/* ------------------------------------------------------------------ MDot */
+template <int NV, int UNR, bool VEC2>
+__global__ void __launch_bounds__(TPB) mdot_kernel(int64_t n, const double *__restrict__ x, PtrPack y, double *partials, unsigned int *counter, double *d_result, double *h_result)
+{
+  double acc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; j++) acc[j] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * TPB;
+  int64_t       i      = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (VEC2) {
+    const int64_t  nvec = n >> 1;
+    const double2 *x2   = reinterpret_cast<const double2 *>(x);
+    for (; i < nvec; i += stride * UNR) {
+      double2 xv[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        int64_t k = i + u * stride;
+        xv[u]     = k < nvec ? x2[k] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int j = 0; j < NV; j++) {
+        const double2 *y2 = reinterpret_cast<const double2 *>(y.p[j]);
+        double2        yv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+          int64_t k = i + u * stride;
+          yv[u]     = k < nvec ? __ldg(&y2[k]) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+          acc[j] = fma(xv[u].x, yv[u].x, acc[j]);
+          acc[j] = fma(xv[u].y, yv[u].y, acc[j]);
+        }
+      }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+      for (int j = 0; j < NV; j++) acc[j] = fma(x[n - 1], y.p[j][n - 1], acc[j]);
+    }
+  } else {
+    for (; i < n; i += stride) {
+      double xv = x[i];
+#pragma unroll
+      for (int j = 0; j < NV; j++) acc[j] = fma(xv, y.p[j][i], acc[j]);
+    }
+  }
+  grid_reduce<NV, 0>(acc, partials, counter, d_result, h_result);
+}
+
+template <int NV>
+static int mdot_launch_nv(b200Handle h, int64_t n, const double *x, const PtrPack &y, bool vec2, double *d_result, double *h_result)
+{
+  constexpr int UNR = NV <= 2 ? 4 : (NV <= 6 ? 2 : 1);
+  static int    occ[2] = {0, 0};
+  void (*kern)(int64_t, const double *, PtrPack, double *, unsigned int *, double *, double *) = vec2 ? mdot_kernel<NV, UNR, true> : mdot_kernel<NV, 1, false>;
+  if (!occ[vec2]) {
+    int o = 1;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, TPB, 0));
+    occ[vec2] = o < 1 ? 1 : (o > 8 ? 8 : o);
+  }
+  int64_t work   = vec2 ? ((n >> 1) + UNR - 1) / UNR : n;
+  int64_t blocks = (work + TPB - 1) / TPB;
+  int64_t cap    = (int64_t)h->num_sms * occ[vec2];
+  if (cap > B200_RED_MAXGRID) cap = B200_RED_MAXGRID;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  kern<<<(int)blocks, TPB, 0, h->stream>>>(n, x, y, h->d_partials, h->d_counter, d_result, h_result);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  return 0;
+}
+
+static int mdot_dispatch(b200Handle h, int64_t n, int nv, const double *x, const double *const *yp, double *d_result, double *h_result)
+{
+  PtrPack y;
+  bool    vec2 = aligned16(x);
+  for (int j = 0; j < nv; j++) {
+    y.p[j] = yp[j];
+    vec2   = vec2 && aligned16(yp[j]);
+  }
+  for (int j = nv; j < B200_MAX_NV; j++) y.p[j] = yp[0];
+  switch (nv) {
+#define C_(N) \
+  case N: return mdot_launch_nv<N>(h, n, x, y, vec2, d_result, h_result);
+    C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14) C_(15) C_(16)
+    C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26) C_(27) C_(28) C_(29) C_(30) C_(31) C_(32)
+#undef C_
+  }
+  B200_CHECK(0, B200_ERR_ARG_OUTOFRANGE, "nv=%d out of range", nv);
+}
+
+/* device-result variant; chunks nv > 32 */
+extern "C" int b200VecMDotAsync(b200Handle h, int64_t n, int nv, const double *x, const double *const *y, double *d_result)
+{
+  B200_CHECK(h, B200_ERR_ARG_NULL, "null handle");
+  B200_CHECK(nv >= 0 && n >= 0, B200_ERR_ARG_OUTOFRANGE, "negative size");
+  if (!nv) return 0;
+  B200_CHECK(x && y && d_result, B200_ERR_ARG_NULL, "null pointer");
+  if (n == 0) {
+    B200_CUDA(cudaMemsetAsync(d_result, 0, sizeof(double) * nv, h->stream));
+    return 0;
+  }
+  for (int j0 = 0; j0 < nv; j0 += B200_MAX_NV) {
+    int c  = nv - j0 < B200_MAX_NV ? nv - j0 : B200_MAX_NV;
+    int rc = mdot_dispatch(h, n, c, x, y + j0, d_result + j0, NULL);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int b200VecMDot(b200Handle h, int64_t n, int nv, const double *x, const double *const *y, double *result)
+{
+  B200_CHECK(h, B200_ERR_ARG_NULL, "null handle");
+  B200_CHECK(nv >= 0 && n >= 0, B200_ERR_ARG_OUTOFRANGE, "negative size");
+  if (!nv) return 0;
+  B200_CHECK(x && y && result, B200_ERR_ARG_NULL, "null pointer");
+  if (n == 0) {
+    for (int j = 0; j < nv; j++) result[j] = 0.0;
+    return 0;
+  }
+  for (int j0 = 0; j0 < nv; j0 += B200_MAX_NV) {
+    int c  = nv - j0 < B200_MAX_NV ? nv - j0 : B200_MAX_NV;
+    int rc = mdot_dispatch(h, n, c, x, y + j0, h->d_result, h->h_result_dev);
+    if (rc) return rc;
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    for (int j = 0; j < c; j++) result[j0 + j] = h->h_result[j];
+  }
+  return 0;
+}
+
+extern "C" int b200VecDot(b200Handle h, int64_t n, const double *x, const double *y, double *result)
+{
+  /* VecDot(x,y) = y^H x ; real scalars: symmetric */
+  return b200VecMDot(h, n, 1, x, &y, result);
+}
+
+/* ------------------------------------------------------------------ generic single reductions (norms, sum, max, min) */
+enum { R_SUMSQ, R_SUMABS, R_SUM, R_MAXABS, R_MAX, R_MIN };
+
+template <int R>
+__global__ void __launch_bounds__(TPB) reduce_kernel(int64_t n, const double *__restrict__ x, double *partials, unsigned int *counter, double *d_result, double *h_result)
+{
+  constexpr bool ismax = (R == R_MAXABS || R == R_MAX || R == R_MIN);
+  double         acc[1];
+  acc[0] = ismax ? -INFINITY : 0.0;
+  const int64_t stride = (int64_t)gridDim.x * TPB;
+  for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
+    double v = x[i];
+    if (R == R_SUMSQ) acc[0] = fma(v, v, acc[0]);
+    else if (R == R_SUMABS) acc[0] += fabs(v);
+    else if (R == R_SUM) acc[0] += v;
+    else if (R == R_MAXABS) acc[0] = fmax(acc[0], fabs(v));
+    else if (R == R_MAX) acc[0] = fmax(acc[0], v);
+    else acc[0] = fmax(acc[0], -v);
+  }
+  grid_reduce<1, ismax ? 1 : 0>(acc, partials, counter, d_result, h_result);
+}
+
+template <int R>
+static int reduce_launch(b200Handle h, int64_t n, const double *x, double *result)
+{
+  B200_CHECK(h && result, B200_ERR_ARG_NULL, "null argument");
+  B200_CHECK(n >= 0, B200_ERR_ARG_OUTOFRANGE, "negative length");
+  if (!n) {
+    *result = (R == R_MAX || R == R_MIN) ? -INFINITY : 0.0;
+    return 0;
+  }
+  B200_CHECK(x, B200_ERR_ARG_NULL, "null vector");
+  int g = ew_grid(h, (n + 3) / 4);
+  if (g > B200_RED_MAXGRID) g = B200_RED_MAXGRID;
+  reduce_kernel<R><<<g, TPB, 0, h->stream>>>(n, x, h->d_partials, h->d_counter, h->d_result, h->h_result_dev);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  *result = h->h_result[0];
+  return 0;
+}
+
+extern "C" int b200VecNorm2(b200Handle h, int64_t n, const double *x, double *result)
+{
+  /* VecNorm_Seq NORM_2 = sqrt(ddot(x,x)) (bvec2.c:201-205): same kernel as the dot product */
+  int rc = b200VecMDot(h, n, 1, x, &x, result);
+  if (!rc) *result = sqrt(*result);
+  return rc;
+}
+
+extern "C" int b200VecNorm(b200Handle h, int64_t n, const double *x, int type, double *result)
+{
+  if (type == 1) return b200VecNorm2(h, n, x, result);
+  if (type == 0) return reduce_launch<R_SUMABS>(h, n, x, result);
+  if (type == 3) {
+    int rc = reduce_launch<R_MAXABS>(h, n, x, result);
+    if (!rc && n == 0) *result = 0.0;
+    return rc;
+  }
+  B200_CHECK(0, B200_ERR_ARG_OUTOFRANGE, "unknown norm type %d", type);
+}
+extern "C" int b200VecSum(b200Handle h, int64_t n, const double *x, double *result) { return reduce_launch<R_SUM>(h, n, x, result); }
+
+__global__ void first_index_kernel(int64_t n, const double *__restrict__ x, double val, long long *idx)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    if (x[i] == val) atomicMin(idx, (long long)i);
+}
+
+static int maxmin(b200Handle h, int64_t n, const double *x, int64_t *idx, double *result, bool ismax)
+{
+  int rc = ismax ? reduce_launch<R_MAX>(h, n, x, result) : reduce_launch<R_MIN>(h, n, x, result);
+  if (rc) return rc;
+  if (!ismax) *result = -*result;
+  if (!n) {
+    *result = ismax ? -1.7976931348623157e308 : 1.7976931348623157e308; /* PETSC_MIN_REAL / PETSC_MAX_REAL */
+    if (idx) *idx = -1;
+    return 0;
+  }
+  if (idx) {
+    long long big = 0x7fffffffffffffffLL;
+    B200_CUDA(cudaMemcpyAsync(h->d_idx, &big, sizeof big, cudaMemcpyHostToDevice, h->stream));
+    first_index_kernel<<<ew_grid(h, n), TPB, 0, h->stream>>>(n, x, *result, h->d_idx);
+    B200_LAUNCHED(1);
+    B200_KERNEL_CHECK();
+    B200_CUDA(cudaMemcpyAsync(h->h_flag, h->d_idx, sizeof big, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    *idx = *(long long *)h->h_flag;
+  }
+  return 0;
+}
+extern "C" int b200VecMax(b200Handle h, int64_t n, const double *x, int64_t *idx, double *r) { return maxmin(h, n, x, idx, r, true); }
+extern "C" int b200VecMin(b200Handle h, int64_t n, const double *x, int64_t *idx, double *r) { return maxmin(h, n, x, idx, r, false); }
+
+/* ------------------------------------------------------------------ MAXPY (+ fused norm) */
+template <int NV>
+__device__ __forceinline__ double maxpy_elem(double xv, const double (&yv)[NV], const AlphaPack &al)
+{
+  /* VecMAXPY_Seq: remainder group of NV&3 vectors first, then groups of 4; within a group the products are summed left
+     to right and the group total is added to x (petscaxpy.h:125-150).  No FMA contraction. */
+  constexpr int g = NV & 3;
+  if (g == 1) xv = __dadd_rn(xv, __dmul_rn(al.a[0], yv[0]));
+  if (g == 2) xv = __dadd_rn(xv, __dadd_rn(__dmul_rn(al.a[0], yv[0]), __dmul_rn(al.a[1], yv[1])));
+  if (g == 3) xv = __dadd_rn(xv, __dadd_rn(__dadd_rn(__dmul_rn(al.a[0], yv[0]), __dmul_rn(al.a[1], yv[1])), __dmul_rn(al.a[2], yv[2])));
+#pragma unroll
+  for (int j = g; j < NV; j += 4) {
+    double t = __dadd_rn(__dmul_rn(al.a[j], yv[j]), __dmul_rn(al.a[j + 1], yv[j + 1]));
+    t        = __dadd_rn(t, __dmul_rn(al.a[j + 2], yv[j + 2]));
+    t        = __dadd_rn(t, __dmul_rn(al.a[j + 3], yv[j + 3]));
+    xv       = __dadd_rn(xv, t);
+  }
+  return xv;
+}
+
+template <int NV, bool NORM, bool VEC2>
+__global__ void __launch_bounds__(TPB) maxpy_kernel(int64_t n, double *x, PtrPack y, AlphaPack al, double *partials, unsigned int *counter, double *d_result, double *h_result)
+{
+  double        acc[1] = {0.0};
+  const int64_t stride = (int64_t)gridDim.x * TPB;
+  int64_t       i      = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (VEC2) {
+    const int64_t nvec = n >> 1;
+    double2      *x2   = reinterpret_cast<double2 *>(x);
+    for (; i < nvec; i += stride) {
+      double2 xv = x2[i];
+      double  y0[NV], y1[NV];
+#pragma unroll
+      for (int j = 0; j < NV; j++) {
+        double2 t = __ldg(reinterpret_cast<const double2 *>(y.p[j]) + i);
+        y0[j]     = t.x;
+        y1[j]     = t.y;
+      }
+      xv.x  = maxpy_elem<NV>(xv.x, y0, al);
+      xv.y  = maxpy_elem<NV>(xv.y, y1, al);
+      x2[i] = xv;
+      if (NORM) {
+        acc[0] = fma(xv.x, xv.x, acc[0]);
+        acc[0] = fma(xv.y, xv.y, acc[0]);
+      }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+      double y0[NV];
+#pragma unroll
+      for (int j = 0; j < NV; j++) y0[j] = y.p[j][n - 1];
+      double xv = maxpy_elem<NV>(x[n - 1], y0, al);
+      x[n - 1]  = xv;
+      if (NORM) acc[0] = fma(xv, xv, acc[0]);
+    }
+  } else {
+    for (; i < n; i += stride) {
+      double y0[NV];
+#pragma unroll
+      for (int j = 0; j < NV; j++) y0[j] = y.p[j][i];
+      double xv = maxpy_elem<NV>(x[i], y0, al);
+      x[i]      = xv;
+      if (NORM) acc[0] = fma(xv, xv, acc[0]);
+    }
+  }
+  if (NORM) grid_reduce<1, 0>(acc, partials, counter, d_result, h_result);
+}
+
+template <int NV>
+static int maxpy_launch_nv(b200Handle h, int64_t n, double *x, const PtrPack &y, const AlphaPack &al, bool vec2, bool norm, double *d_result, double *h_result)
+{
+  typedef void (*kern_t)(int64_t, double *, PtrPack, AlphaPack, double *, unsigned int *, double *, double *);
+  static int occ[4] = {0, 0, 0, 0};
+  int        v      = (vec2 ? 1 : 0) + (norm ? 2 : 0);
+  kern_t     kern   = vec2 ? (norm ? (kern_t)maxpy_kernel<NV, true, true> : (kern_t)maxpy_kernel<NV, false, true>) : (norm ? (kern_t)maxpy_kernel<NV, true, false> : (kern_t)maxpy_kernel<NV, false, false>);
+  if (!occ[v]) {
+    int o = 1;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, TPB, 0));
+    occ[v] = o < 1 ? 1 : (o > 8 ? 8 : o);
+  }
+  int64_t work   = vec2 ? (n >> 1) : n;
+  int64_t blocks = (work + TPB - 1) / TPB;
+  int64_t cap    = (int64_t)h->num_sms * occ[v];
+  if (cap > B200_RED_MAXGRID) cap = B200_RED_MAXGRID;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  kern<<<(int)blocks, TPB, 0, h->stream>>>(n, x, y, al, h->d_partials, h->d_counter, d_result, h_result);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  return 0;
+}
+
+static int maxpy_dispatch(b200Handle h, int64_t n, int nv, const double *alpha, const double *const *yp, double *x, bool norm, double *d_result, double *h_result)
+{
+  PtrPack   y;
+  AlphaPack al;
+  bool      vec2 = aligned16(x);
+  for (int j = 0; j < nv; j++) {
+    y.p[j]  = yp[j];
+    al.a[j] = alpha[j];
+    vec2    = vec2 && aligned16(yp[j]);
+  }
+  for (int j = nv; j < B200_MAX_NV; j++) {
+    y.p[j]  = yp[0];
+    al.a[j] = 0.0;
+  }
+  switch (nv) {
+#define C_(N) \
+  case N: return maxpy_launch_nv<N>(h, n, x, y, al, vec2, norm, d_result, h_result);
+    C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14) C_(15) C_(16)
+    C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26) C_(27) C_(28) C_(29) C_(30) C_(31) C_(32)
+#undef C_
+  }
+  B200_CHECK(0, B200_ERR_ARG_OUTOFRANGE, "nv=%d out of range", nv);
+}
+
+/* chunking for nv > 32 must respect the reference grouping: the remainder group (nv & 3) comes first, so the first
+   chunk takes (nv & 3) + a multiple of 4 vectors and all later chunks are multiples of 4 */
+static int maxpy_any(b200Handle h, int64_t n, int nv, const double *alpha, const double *const *y, double *x, bool norm, double *d_result, double *h_result)
+{
+  int j0 = 0;
+  while (j0 < nv) {
+    int left = nv - j0, c;
+    if (left <= B200_MAX_NV) c = left;
+    else c = (j0 == 0) ? ((nv & 3) + ((B200_MAX_NV - (nv & 3)) & ~3)) : B200_MAX_NV;
+    bool last = (j0 + c == nv);
+    int  rc   = maxpy_dispatch(h, n, c, alpha + j0, y + j0, x, norm && last, d_result, h_result);
+    if (rc) return rc;
+    j0 += c;
+  }
+  return 0;
+}
+
+extern "C" int b200VecMAXPYAsync(b200Handle h, int64_t n, int nv, const double *alpha, const double *const *y, double *x, double *d_sumsq)
+{
+  B200_CHECK(h, B200_ERR_ARG_NULL, "null handle");
+  B200_CHECK(nv >= 0 && n >= 0, B200_ERR_ARG_OUTOFRANGE, "negative size");
+  if (n == 0 || nv == 0) {
+    if (d_sumsq && n == 0) B200_CUDA(cudaMemsetAsync(d_sumsq, 0, sizeof(double), h->stream));
+    if (d_sumsq && n > 0) { /* no update: plain sum of squares */
+      const double *xp = x;
+      return b200VecMDotAsync(h, n, 1, x, &xp, d_sumsq);
+    }
+    return 0;
+  }
+  B200_CHECK(x && y && alpha, B200_ERR_ARG_NULL, "null pointer");
+  return maxpy_any(h, n, nv, alpha, y, x, d_sumsq != NULL, d_sumsq, NULL);
+}
+
+extern "C" int b200VecMAXPY(b200Handle h, int64_t n, int nv, const double *alpha, const double *const *y, double *x, double *norm2_out)
+{
+  B200_CHECK(h, B200_ERR_ARG_NULL, "null handle");
+  B200_CHECK(nv >= 0 && n >= 0, B200_ERR_ARG_OUTOFRANGE, "negative size");
+  if (n == 0 || nv == 0) {
+    if (norm2_out) return b200VecNorm2(h, n, x, norm2_out);
+    return 0;
+  }
+  B200_CHECK(x && y && alpha, B200_ERR_ARG_NULL, "null pointer");
+  int rc = maxpy_any(h, n, nv, alpha, y, x, norm2_out != NULL, h->d_result, h->h_result_dev);
+  if (rc) return rc;
+  if (norm2_out) {
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    *norm2_out = sqrt(h->h_result[0]);
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------ fused AXPY + dot */
+template <bool VEC2>
+__global__ void __launch_bounds__(TPB) axpy_dot_kernel(int64_t n, double a, const double *__restrict__ x, double *y, const double *z, double *partials, unsigned int *counter, double *d_result, double *h_result)
+{
+  double        acc[1] = {0.0};
+  const int64_t stride = (int64_t)gridDim.x * TPB;
+  int64_t       i      = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  const bool    self   = (z == y);
+  if (VEC2) {
+    const int64_t  nvec = n >> 1;
+    const double2 *x2 = reinterpret_cast<const double2 *>(x), *z2 = reinterpret_cast<const double2 *>(z);
+    double2       *y2 = reinterpret_cast<double2 *>(y);
+    for (; i < nvec; i += stride) {
+      double2 xv = x2[i], yv = y2[i], zv;
+      if (!self) zv = z2[i];
+      yv.x = yv.x + a * xv.x;
+      yv.y = yv.y + a * xv.y;
+      if (self) zv = yv;
+      y2[i]  = yv;
+      acc[0] = fma(yv.x, zv.x, acc[0]);
+      acc[0] = fma(yv.y, zv.y, acc[0]);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+      double yv = y[n - 1] + a * x[n - 1];
+      y[n - 1]  = yv;
+      acc[0]    = fma(yv, self ? yv : z[n - 1], acc[0]);
+    }
+  } else {
+    for (; i < n; i += stride) {
+      double yv = y[i] + a * x[i];
+      y[i]      = yv;
+      acc[0]    = fma(yv, self ? yv : z[i], acc[0]);
+    }
+  }
+  grid_reduce<1, 0>(acc, partials, counter, d_result, h_result);
+}
+
+extern "C" int b200VecAXPYDot(b200Handle h, int64_t n, double alpha, const double *x, double *y, const double *z, double *result)
+{
+  B200_CHECK(h && result, B200_ERR_ARG_NULL, "null argument");
+  B200_CHECK(n >= 0, B200_ERR_ARG_OUTOFRANGE, "negative length");
+  if (!n) {
+    *result = 0.0;
+    return 0;
+  }
+  B200_CHECK(x && y && z, B200_ERR_ARG_NULL, "null vector");
+  bool vec2 = aligned16(x) && aligned16(y) && aligned16(z);
+  int  g    = ew_grid(h, vec2 ? (n >> 1) : n);
+  if (g > B200_RED_MAXGRID) g = B200_RED_MAXGRID;
+  if (vec2) axpy_dot_kernel<true><<<g, TPB, 0, h->stream>>>(n, alpha, x, y, z, h->d_partials, h->d_counter, h->d_result, h->h_result_dev);
+  else axpy_dot_kernel<false><<<g, TPB, 0, h->stream>>>(n, alpha, x, y, z, h->d_partials, h->d_counter, h->d_result, h->h_result_dev);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  *result = h->h_result[0];
+  return 0;
+}

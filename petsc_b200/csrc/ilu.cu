@@ -1,0 +1,419 @@
+/*
+ * ilu.cu -- ILU(0) for MATSEQAIJ on sm_100a: symbolic layout, numeric factorisation and the two triangular sweeps.
+ *
+ * Reference: MatILUFactorSymbolic_SeqAIJ_ilu0 (aijfact.c:1471-1534), MatLUFactorNumeric_SeqAIJ (aijfact.c:216-389),
+ * MatSolve_SeqAIJ_NaturalOrdering (aijfact.c:2413-2457); the reference's GPU path is cusparseXcsrilu02 + cusparseSpSV
+ * (aijcusparse.cu:766-827, 643-693).
+ *
+ * Factor layout = the reference's (aijfact.c:1454-1469): bj/ba hold L(0,:)..L(n-1,:) then U(n-1,:)..U(0,:); bi[i] = start
+ * of L(i,:); bdiag[i] = position of U's diagonal (stored INVERTED), U(i,:) = (strict upper ..., diagonal).
+ *
+ * Parallel schedule: dependency levels are computed once (level(i) = 1 + max level over the row's L entries; mirrored
+ * for U), rows are laid out in level order with every level padded to a whole warp, and ONE kernel per sweep walks that
+ * order.  CTAs take their slice through an atomic ticket (so they start in dependency order) and a row whose inputs
+ * are not final yet spins on per-row ready flags written with release semantics by the producer (no grid-wide barrier,
+ * no kernel launch per level: the critical path costs one L2 round trip per level instead of one launch).
+ *
+ * Arithmetic: G lanes cooperate on a row (they fetch the factor entries and the gathered x values in parallel), but the
+ * row sum is accumulated strictly left to right with __dmul_rn/__dsub_rn, exactly PetscSparseDenseMinusDot
+ * (aij.h:531-536) in the reference's FMA-free -O2 build.  The numeric factorisation applies the eliminations of a row
+ * in the reference's order (L entries ascending; each target entry updated once per pivot row).  Both the factor and
+ * the solve are therefore bit-identical to the CPU reference.
+ */
+#include "b200_internal.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct b200IluPlan_s {
+  int     n;
+  int64_t nnz;
+  int    *d_ai, *d_adiag;            /* A pattern: row start and diagonal position */
+  int    *d_bi, *d_bj, *d_bdiag;     /* factor layout */
+  double *d_ba;
+  int    *d_orderL, *d_orderU;       /* rows in level order, -1 padded to warp multiples */
+  int     nslotL, nslotU;
+  int    *d_flag;                    /* per-row ready epoch */
+  int    *d_ticket;                  /* [4] tickets + status */
+  int     epoch;
+  int     nlevL, nlevU;
+  int     G;                         /* lanes per row in the sweeps */
+  int    *h_bi, *h_bj, *h_bdiag;     /* host copy of the layout (kept for GetFactor) */
+  int     factored;
+};
+
+#define ILU_TPB 256
+
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void wait_ready(const int *flag, int row, int epoch)
+{
+  while (ld_acquire(flag + row) != epoch) { }
+}
+
+/* Dynamic CTA index: CTAs are numbered in the order they actually start, so a CTA only ever waits on rows owned by
+   CTAs that are already running or finished. */
+__device__ __forceinline__ int take_ticket(int *ticket)
+{
+  __shared__ int s_t;
+  if (threadIdx.x == 0) s_t = atomicAdd(ticket, 1);
+  __syncthreads();
+  return s_t;
+}
+
+/* ------------------------------------------------------------------ triangular sweeps */
+/* lower: x[i] = b[i] - sum_{k in L(i,:)} ba[k] x[bj[k]]            (aijfact.c:2431-2440)
+   upper: x[i] = (x[i] - sum_{k in U(i,:) strict} ba[k] x[bj[k]]) * ba[bdiag[i]]   (aijfact.c:2443-2451) */
+template <int G, bool UPPER>
+__global__ void __launch_bounds__(ILU_TPB) ilu_sweep_kernel(int nslot, const int *__restrict__ order, const int *__restrict__ bi, const int *__restrict__ bdiag, const int *__restrict__ bj, const double *__restrict__ ba, const double *b, double *x, int *flag, int epoch, int *ticket)
+{
+  const int      cta  = take_ticket(ticket);
+  const int      slot = cta * (ILU_TPB / G) + threadIdx.x / G;
+  const int      gl   = threadIdx.x % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  if (slot >= nslot) return;
+  const int i = order[slot];
+  if (i < 0) return; /* padding: whole groups drop out together */
+  int    ks, ke;
+  double sum, dinv = 0.0;
+  if (!UPPER) {
+    ks  = bi[i];
+    ke  = bi[i + 1];
+    sum = b[i];
+  } else {
+    ks   = bdiag[i + 1] + 1;
+    ke   = bdiag[i];
+    sum  = __ldcg(x + i);
+    dinv = ba[ke];
+  }
+  for (int k0 = ks; k0 < ke; k0 += G) {
+    const int k = k0 + gl;
+    double    p = 0.0;
+    if (k < ke) {
+      const int c = bj[k];
+      wait_ready(flag, c, epoch);
+      p = __dmul_rn(ba[k], __ldcg(x + c));
+    }
+    const int cnt = min(G, ke - k0);
+#pragma unroll
+    for (int l = 0; l < G; l++) {
+      const double pl = __shfl_sync(gmask, p, l, G);
+      if (l < cnt) sum = __dsub_rn(sum, pl); /* strict left-to-right, FMA-free */
+    }
+  }
+  if (gl == 0) {
+    if (UPPER) sum = __dmul_rn(sum, dinv);
+    x[i] = sum;
+    __threadfence();
+    st_release(flag + i, epoch);
+  }
+}
+
+/* ------------------------------------------------------------------ numeric factorisation */
+/* position of column c inside a sorted segment bj[lo,hi), or -1 */
+__device__ __forceinline__ int find_col(const int *__restrict__ bj, int lo, int hi, int c)
+{
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    int v   = bj[mid];
+    if (v == c) return mid;
+    if (v < c) lo = mid + 1;
+    else hi = mid;
+  }
+  return -1;
+}
+
+template <int G>
+__global__ void __launch_bounds__(ILU_TPB) ilu_numeric_kernel(int nslot, const int *__restrict__ order, const int *__restrict__ ai, const int *__restrict__ adiag, const double *__restrict__ aval, const int *__restrict__ bi, const int *__restrict__ bdiag, const int *__restrict__ bj, double *ba, double shift, double zeropivot, int *flag, int epoch, int *ticket, int *status)
+{
+  const int      cta   = take_ticket(ticket);
+  const int      slot  = cta * (ILU_TPB / G) + threadIdx.x / G;
+  const int      gl    = threadIdx.x % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  if (slot >= nslot) return;
+  const int i = order[slot];
+  if (i < 0) return;
+  const int l0 = bi[i], l1 = bi[i + 1];             /* L(i,:) */
+  const int u0 = bdiag[i + 1] + 1, u1 = bdiag[i];    /* U(i,:) strict part, diagonal at u1 */
+  const int a0 = ai[i], ad = adiag[i], a1 = ai[i + 1];
+  /* load the unfactored row into the factor storage (aijfact.c:282-286) */
+  for (int k = gl; k < l1 - l0; k += G) ba[l0 + k] = aval[a0 + k];
+  for (int k = gl; k < u1 - u0; k += G) ba[u0 + k] = aval[ad + 1 + k];
+  if (gl == 0) ba[u1] = aval[ad] + shift;
+  (void)a1;
+  __syncwarp(gmask);
+  /* elimination (aijfact.c:289-306): pivot rows in ascending column order */
+  for (int kl = l0; kl < l1; kl++) {
+    const int row = bj[kl];
+    wait_ready(flag, row, epoch);
+    const double pc = __ldcg(ba + kl);
+    if (pc != 0.0) {
+      const double mult = __dmul_rn(pc, __ldcg(ba + bdiag[row]));
+      const int    r0 = bdiag[row + 1] + 1, r1 = bdiag[row]; /* U(row,:) without its diagonal */
+      for (int t = r0 + gl; t < r1; t += G) {
+        const int c = bj[t];
+        int       pos;
+        if (c < i) pos = find_col(bj, kl + 1, l1, c);
+        else if (c == i) pos = u1;
+        else pos = find_col(bj, u0, u1, c);
+        if (pos >= 0) ba[pos] = __dsub_rn(__ldcg(ba + pos), __dmul_rn(mult, __ldcg(ba + t)));
+      }
+      __syncwarp(gmask);
+      if (gl == 0) ba[kl] = mult;
+    }
+    __syncwarp(gmask);
+  }
+  /* pivot check (MatPivotCheck_nz, matimpl.h:795-811) and inversion of the diagonal (aijfact.c:332-334) */
+  double rs = 0.0;
+  for (int k = l0 + gl; k < l1; k += G) rs += fabs(__ldcg(ba + k));
+  for (int k = u0 + gl; k < u1; k += G) rs += fabs(__ldcg(ba + k));
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) rs += __shfl_xor_sync(gmask, rs, o, G);
+  if (gl == 0) {
+    const double pv = __ldcg(ba + u1);
+    if (fabs(pv) <= zeropivot * rs && !isnan(pv)) atomicMax(status, 1);
+    ba[u1] = 1.0 / pv;
+    __threadfence();
+    st_release(flag + i, epoch);
+  }
+}
+
+/* ------------------------------------------------------------------ host: symbolic + level schedule */
+static int *levels_to_order(int n, const int *lev, int nlev, int rpw, int *nslot_out)
+{
+  /* counting sort by level, each level padded to a multiple of rpw (rows per warp) with -1 */
+  int64_t *cnt = (int64_t *)calloc((size_t)nlev + 1, sizeof(int64_t));
+  for (int i = 0; i < n; i++) cnt[lev[i] + 1]++;
+  int64_t tot = 0;
+  int64_t *start = (int64_t *)malloc(sizeof(int64_t) * ((size_t)nlev + 1));
+  for (int l = 0; l < nlev; l++) {
+    start[l] = tot;
+    tot += (cnt[l + 1] + rpw - 1) / rpw * rpw;
+  }
+  if (tot > 2147483000LL) {
+    free(cnt);
+    free(start);
+    return NULL;
+  }
+  int *order = (int *)malloc(sizeof(int) * (size_t)(tot + 1));
+  for (int64_t k = 0; k < tot; k++) order[k] = -1;
+  for (int i = 0; i < n; i++) order[start[lev[i]]++] = i;
+  *nslot_out = (int)tot;
+  free(cnt);
+  free(start);
+  return order;
+}
+
+extern "C" int b200Ilu0Destroy(b200IluPlan p)
+{
+  if (!p) return 0;
+  cudaFree(p->d_ai); cudaFree(p->d_adiag); cudaFree(p->d_bi); cudaFree(p->d_bj); cudaFree(p->d_bdiag); cudaFree(p->d_ba);
+  cudaFree(p->d_orderL); cudaFree(p->d_orderU); cudaFree(p->d_flag); cudaFree(p->d_ticket);
+  free(p->h_bi); free(p->h_bj); free(p->h_bdiag);
+  free(p);
+  return 0;
+}
+
+extern "C" int b200Ilu0Symbolic(b200Handle h, int n, const int *ai, const int *aj, b200IluPlan *plan)
+{
+  B200_CHECK(h && plan, B200_ERR_ARG_NULL, "null argument");
+  B200_CHECK(n >= 0, B200_ERR_ARG_OUTOFRANGE, "negative size");
+  B200_CHECK(n == 0 || (ai && aj), B200_ERR_ARG_NULL, "null pattern");
+  b200IluPlan p = (b200IluPlan)calloc(1, sizeof(*p));
+  B200_CHECK(p, B200_ERR_MEM, "out of host memory");
+  p->n   = n;
+  p->nnz = n ? ai[n] : 0;
+  const int64_t nnz = p->nnz;
+  int *adiag = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+  int *bi = (int *)malloc(sizeof(int) * (size_t)(n + 1)), *bdiag = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+  int *bj = (int *)malloc(sizeof(int) * (size_t)(nnz + 1));
+  int *levL = (int *)malloc(sizeof(int) * (size_t)(n + 1)), *levU = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+  B200_CHECK(adiag && bi && bdiag && bj && levL && levU, B200_ERR_MEM, "out of host memory");
+  /* diagonal markers (MatGetDiagonalMarkers_SeqAIJ): ILU needs every diagonal entry present */
+  for (int i = 0; i < n; i++) {
+    int lo = ai[i], hi = ai[i + 1], pos = -1;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (aj[mid] == i) { pos = mid; break; }
+      if (aj[mid] < i) lo = mid + 1;
+      else hi = mid;
+    }
+    if (pos < 0) {
+      free(adiag); free(bi); free(bdiag); free(bj); free(levL); free(levU); free(p);
+      B200_CHECK(0, B200_ERR_ARG_WRONGSTATE, "Matrix is missing diagonal entry %d", i); /* aij.c MatMissingDiagonal */
+    }
+    adiag[i] = pos;
+  }
+  /* aijfact.c:1503-1521 */
+  int64_t k = 0;
+  bi[0]     = 0;
+  for (int i = 0; i < n; i++) {
+    int nz    = adiag[i] - ai[i];
+    bi[i + 1] = bi[i] + nz;
+    memcpy(bj + k, aj + ai[i], sizeof(int) * (size_t)nz);
+    k += nz;
+  }
+  bdiag[n] = bi[n] - 1;
+  for (int i = n - 1; i >= 0; i--) {
+    int nz = ai[i + 1] - adiag[i] - 1;
+    memcpy(bj + k, aj + adiag[i] + 1, sizeof(int) * (size_t)nz);
+    k += nz;
+    bj[k++]  = i;
+    bdiag[i] = bdiag[i + 1] + nz + 1;
+  }
+  /* dependency levels */
+  int nlevL = 0, nlevU = 0;
+  for (int i = 0; i < n; i++) {
+    int l = 0;
+    for (int q = ai[i]; q < adiag[i]; q++) l = levL[aj[q]] + 1 > l ? levL[aj[q]] + 1 : l;
+    levL[i] = l;
+    if (l + 1 > nlevL) nlevL = l + 1;
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    int l = 0;
+    for (int q = adiag[i] + 1; q < ai[i + 1]; q++) l = levU[aj[q]] + 1 > l ? levU[aj[q]] + 1 : l;
+    levU[i] = l;
+    if (l + 1 > nlevU) nlevU = l + 1;
+  }
+  p->nlevL = nlevL;
+  p->nlevU = nlevU;
+  /* lanes per row for the sweeps: about the mean number of off-diagonal entries per triangular row */
+  {
+    double avg = n ? (double)(nnz - n) / (2.0 * n) : 0.0;
+    int    G   = 2;
+    while (G < 32 && G < avg) G <<= 1;
+    p->G = G;
+  }
+  /* the numeric kernel uses 8 lanes per row; pad levels for the larger of the two groupings */
+  const int rpw = 32 / (p->G < 8 ? p->G : 8); /* a multiple of the sweeps' rows-per-warp (32/G) as well */
+  int *orderL = levels_to_order(n, levL, nlevL, rpw, &p->nslotL);
+  int *orderU = levels_to_order(n, levU, nlevU, rpw, &p->nslotU);
+  free(levL); free(levU);
+  if (!orderL || !orderU) {
+    free(orderL); free(orderU); free(adiag); free(bi); free(bdiag); free(bj); free(p);
+    B200_CHECK(0, B200_ERR_SUP, "level schedule exceeds 32-bit indexing");
+  }
+#define UP(dst, src, cnt, T) \
+  do { \
+    B200_CUDA(cudaMalloc(&p->dst, sizeof(T) * ((size_t)(cnt) + 64))); \
+    B200_CUDA(cudaMemcpyAsync(p->dst, src, sizeof(T) * (size_t)(cnt), cudaMemcpyHostToDevice, h->stream)); \
+  } while (0)
+  UP(d_ai, ai, n + 1, int);
+  UP(d_adiag, adiag, n, int);
+  UP(d_bi, bi, n + 1, int);
+  UP(d_bdiag, bdiag, n + 1, int);
+  UP(d_bj, bj, nnz, int);
+  UP(d_orderL, orderL, p->nslotL, int);
+  UP(d_orderU, orderU, p->nslotU, int);
+#undef UP
+  B200_CUDA(cudaMalloc(&p->d_ba, sizeof(double) * ((size_t)nnz + 64)));
+  B200_CUDA(cudaMalloc(&p->d_flag, sizeof(int) * ((size_t)n + 64)));
+  B200_CUDA(cudaMemsetAsync(p->d_flag, 0, sizeof(int) * ((size_t)n + 64), h->stream));
+  B200_CUDA(cudaMalloc(&p->d_ticket, 64));
+  B200_CUDA(cudaMemsetAsync(p->d_ticket, 0, 64, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  free(orderL); free(orderU); free(adiag);
+  p->h_bi = bi; p->h_bj = bj; p->h_bdiag = bdiag;
+  p->epoch = 0;
+  *plan    = p;
+  return 0;
+}
+
+template <int G>
+static int numeric_launch(b200Handle h, b200IluPlan p, const double *aval, double shift, double zeropivot)
+{
+  const int rows_per_cta = ILU_TPB / G;
+  const int grid         = (p->nslotL + rows_per_cta - 1) / rows_per_cta;
+  ilu_numeric_kernel<G><<<grid, ILU_TPB, 0, h->stream>>>(p->nslotL, p->d_orderL, p->d_ai, p->d_adiag, aval, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, shift, zeropivot, p->d_flag, p->epoch, p->d_ticket, p->d_ticket + 8);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  return 0;
+}
+
+extern "C" int b200Ilu0Numeric(b200Handle h, b200IluPlan p, const double *d_aval, double zeropivot, double shiftamount, int *nshift_out)
+{
+  B200_CHECK(h && p, B200_ERR_ARG_NULL, "null argument");
+  if (nshift_out) *nshift_out = 0;
+  if (p->n == 0) {
+    p->factored = 1;
+    return 0;
+  }
+  B200_CHECK(d_aval, B200_ERR_ARG_NULL, "null values");
+  double shift  = 0.0;
+  int    nshift = 0;
+  for (;;) {
+    p->epoch++;
+    B200_CUDA(cudaMemsetAsync(p->d_ticket, 0, 64, h->stream));
+    int rc = (p->G >= 8) ? numeric_launch<8>(h, p, d_aval, shift, zeropivot) : (p->G == 4 ? numeric_launch<4>(h, p, d_aval, shift, zeropivot) : numeric_launch<2>(h, p, d_aval, shift, zeropivot));
+    if (rc) return rc;
+    int status = 0;
+    B200_CUDA(cudaMemcpyAsync(&status, p->d_ticket + 8, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    if (!status) break;
+    /* MatPivotCheck_nz: first shift = shiftamount, then doubled; refactor from scratch (aijfact.c:264 do-while) */
+    shift = nshift ? shift * 2.0 : shiftamount;
+    nshift++;
+    B200_CHECK(nshift <= 60 && shift > 0.0, B200_ERR_MAT_LU_ZRPVT, "Zero pivot in ILU(0) factorisation; shift could not repair it");
+  }
+  if (nshift_out) *nshift_out = nshift;
+  p->factored = 1;
+  return 0;
+}
+
+template <int G>
+static int sweeps_launch(b200Handle h, b200IluPlan p, const double *b, double *x)
+{
+  const int rows_per_cta = ILU_TPB / G;
+  p->epoch++;
+  B200_CUDA(cudaMemsetAsync(p->d_ticket, 0, 64, h->stream));
+  ilu_sweep_kernel<G, false><<<(p->nslotL + rows_per_cta - 1) / rows_per_cta, ILU_TPB, 0, h->stream>>>(p->nslotL, p->d_orderL, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, b, x, p->d_flag, p->epoch, p->d_ticket);
+  B200_KERNEL_CHECK();
+  p->epoch++;
+  ilu_sweep_kernel<G, true><<<(p->nslotU + rows_per_cta - 1) / rows_per_cta, ILU_TPB, 0, h->stream>>>(p->nslotU, p->d_orderU, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, b, x, p->d_flag, p->epoch, p->d_ticket + 1);
+  B200_KERNEL_CHECK();
+  B200_LAUNCHED(2);
+  return 0;
+}
+
+extern "C" int b200Ilu0Solve(b200Handle h, b200IluPlan p, const double *d_b, double *d_x)
+{
+  B200_CHECK(h && p, B200_ERR_ARG_NULL, "null argument");
+  B200_CHECK(p->factored, B200_ERR_ORDER, "b200Ilu0Numeric must be called first");
+  if (p->n == 0) return 0;
+  B200_CHECK(d_b && d_x && d_b != d_x, B200_ERR_ARG_WRONG, "b and x must be distinct non-null vectors");
+  B200_CHECK(p->epoch < 2147483000, B200_ERR_SUP, "epoch counter exhausted");
+  switch (p->G) {
+  case 2: return sweeps_launch<2>(h, p, d_b, d_x);
+  case 4: return sweeps_launch<4>(h, p, d_b, d_x);
+  case 8: return sweeps_launch<8>(h, p, d_b, d_x);
+  case 16: return sweeps_launch<16>(h, p, d_b, d_x);
+  default: return sweeps_launch<32>(h, p, d_b, d_x);
+  }
+}
+
+extern "C" int b200Ilu0GetFactor(b200Handle h, b200IluPlan p, int *bi, int *bj, int *bdiag, double *ba)
+{
+  B200_CHECK(h && p, B200_ERR_ARG_NULL, "null argument");
+  if (bi) memcpy(bi, p->h_bi, sizeof(int) * (size_t)(p->n + 1));
+  if (bdiag) memcpy(bdiag, p->h_bdiag, sizeof(int) * (size_t)(p->n + 1));
+  if (bj) memcpy(bj, p->h_bj, sizeof(int) * (size_t)p->nnz);
+  if (ba && p->nnz) {
+    B200_CUDA(cudaMemcpyAsync(ba, p->d_ba, sizeof(double) * (size_t)p->nnz, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+extern "C" int b200Ilu0GetInfo(b200IluPlan p, int *nlevL, int *nlevU, int64_t *nnz)
+{
+  B200_CHECK(p, B200_ERR_ARG_NULL, "null plan");
+  if (nlevL) *nlevL = p->nlevL;
+  if (nlevU) *nlevU = p->nlevU;
+  if (nnz) *nnz = p->nnz;
+  return 0;
+}

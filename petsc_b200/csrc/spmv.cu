@@ -1,0 +1,577 @@
+/*
+ * spmv.cu -- CSR SpMV for MATSEQAIJ on sm_100a (HBM-bound gather; no tensor cores).
+ *
+ * Replaces the cusparseSpMV(CSR_ALG1) call site of the reference (aijcusparse.cu:2424-2568) and restates
+ * MatMult_SeqAIJ / MatMultAdd_SeqAIJ (aij.c:1444-1499, 1606-1655) for the GPU.
+ *
+ * Kernel design (row-binned, TMA-staged):
+ *   - The matrix is cut into row tiles of R consecutive rows.  R is the largest power of two for which every tile's
+ *     nonzero count fits the shared-memory stage (b200CsrPlanCreate measures this on the device).
+ *   - A persistent CTA walks its tiles through an S-stage shared-memory ring.  For every tile one elected thread issues
+ *     three 1-D TMA bulk copies (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes): the row-pointer
+ *     slice, the column-index slice and the value slice, all 16-byte granular, completing on one mbarrier.  val/col are
+ *     therefore read from HBM exactly once, fully coalesced, with no register staging, and S-1 tiles are always in
+ *     flight per CTA while one is being consumed.
+ *   - Consumers: G lanes per row (G = 1,2,4,...,32 chosen from the mean row length).  Each lane walks its share of the
+ *     row in shared memory, gathers x through the read-only path (x is the only operand with reuse: it lives in L2/L1),
+ *     and the G partial sums are combined with warp shuffles.
+ *   - G == 1 is the PARITY mode: one thread sums a row strictly left to right with __dmul_rn/__dadd_rn, i.e. exactly
+ *     the arithmetic of the generic PetscSparseDensePlusDot branch (aij.h:609-614) in the reference's -O2 x86-64 build.
+ *     y is then bit-identical to MatMult_SeqAIJ.  It is also the fastest mode for stencil matrices (<= ~12 nnz/row).
+ *   - Epilogues fused into the same kernel: y = A x; z = y + A x (sum starts at y[r], as aij.c:1639-1652 does);
+ *     w = dinv .* (A x) (PCApply_Jacobi fused, saves one n-vector write and read per Krylov iteration).
+ *   - Tiles whose nonzeros do not fit a stage (a few very long rows) take an in-kernel fallback that streams the rows
+ *     straight from global memory with the same G-lane decomposition.
+ *
+ * Algorithmic bytes per call: nnz*(8+4) + m*(4+8+8).
+ */
+#include "b200_internal.h"
+#include <stdlib.h>
+
+#define SPMV_TPB 256
+#define SPMV_MAX_STAGES 4
+
+struct b200CsrPlan_s {
+  int        m, n;
+  int64_t    nnz;
+  const int *d_rowptr, *d_colidx;
+  int        lanes;       /* G */
+  int        rows_tile;   /* R */
+  int        cap;         /* nnz capacity of one stage */
+  int        stages;
+  int        ctas_per_sm;
+  int        grid;
+  int        smem;
+  int        max_row_nnz;
+  int        num_sms;
+  int        user_lanes, user_rows, user_stages, user_ctas;
+  int        max_tile_nnz[16]; /* for R = 8 << k */
+};
+
+/* ------------------------------------------------------------------ PTX helpers: mbarrier + 1-D TMA bulk copy */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void     mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void     mbar_expect_tx(uint64_t *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void     mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "WAIT_LOOP:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra WAIT_DONE;\n"
+    "bra WAIT_LOOP;\n"
+    "WAIT_DONE:\n"
+    "}\n" ::"r"(smem_u32(bar)),
+    "r"(parity)
+    : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+/* ------------------------------------------------------------------ shared-memory stage layout */
+struct StageLayout {
+  int rp_off, col_off, val_off, stage_bytes;
+};
+__host__ __device__ inline StageLayout stage_layout(int R, int cap)
+{
+  StageLayout L;
+  L.val_off     = 0;                                   /* (cap+4) doubles */
+  L.col_off     = (cap + 4) * 8;                       /* (cap+4) ints    */
+  L.rp_off      = L.col_off + (cap + 4) * 4;           /* (R+4) ints      */
+  L.stage_bytes = (L.rp_off + (R + 4) * 4 + 127) & ~127;
+  return L;
+}
+
+/* ------------------------------------------------------------------ the kernel */
+template <int G>
+__global__ void __launch_bounds__(SPMV_TPB) csr_spmv_tile_kernel(int m, int R, int cap, int S, const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ val, const double *__restrict__ x, const double *yin, const double *__restrict__ dinv, double *yout, double *yplain)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t                           full_bar[SPMV_MAX_STAGES];
+  const StageLayout                             L      = stage_layout(R, cap);
+  const int                                     ntiles = (m + R - 1) / R;
+  const int                                     tid    = threadIdx.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  /* producer: issue the three bulk copies of tile t into stage s (or an empty arrival for an oversize tile) */
+  auto issue = [&](int t, int s, int k0, int k1) {
+    unsigned char *st   = smem + (size_t)s * L.stage_bytes;
+    const int      r0   = t * R;
+    const int      rows = min(R, m - r0);
+    const uint32_t rpcnt = (uint32_t)((rows + 1 + 3) & ~3);
+    if (k1 - k0 > cap) { /* fallback tile: only the row pointers are staged, the rows stream from global memory */
+      mbar_expect_tx(&full_bar[s], rpcnt * 4u);
+      tma_load_1d(st + L.rp_off, rowptr + r0, rpcnt * 4u, &full_bar[s]);
+      return;
+    }
+    const int      k0a   = k0 & ~3;                            /* 16-byte alignment for both arrays */
+    const int64_t  kend  = ((int64_t)k1 + 3) & ~(int64_t)3;    /* <= roundup4(nnz): inside the allocation pad */
+    const uint32_t cnt   = (uint32_t)(kend - k0a);
+    const uint32_t bytes = cnt * 12u + rpcnt * 4u;
+    mbar_expect_tx(&full_bar[s], bytes);
+    tma_load_1d(st + L.rp_off, rowptr + r0, rpcnt * 4u, &full_bar[s]);
+    if (cnt) {
+      tma_load_1d(st + L.col_off, colidx + k0a, cnt * 4u, &full_bar[s]);
+      tma_load_1d(st + L.val_off, val + k0a, cnt * 8u, &full_bar[s]);
+    }
+  };
+
+  /* prologue: fill the ring */
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) {
+      int t = blockIdx.x + s * gridDim.x;
+      if (t < ntiles) {
+        int r0 = t * R, r1 = min(r0 + R, m);
+        issue(t, s, __ldg(rowptr + r0), __ldg(rowptr + r1));
+      }
+    }
+  }
+
+  constexpr int RPP = SPMV_TPB / G; /* rows per pass */
+  const int     grp = tid / G, gl = tid % G;
+
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+    const int      s      = it % S;
+    const uint32_t parity = (uint32_t)((it / S) & 1);
+    /* bounds of the tile that will reuse this stage: loaded early so the latency hides behind the compute */
+    int       nk0 = 0, nk1 = 0;
+    const int tn = t + S * gridDim.x;
+    if (tid == 0 && tn < ntiles) {
+      int r0 = tn * R, r1 = min(r0 + R, m);
+      nk0 = __ldg(rowptr + r0);
+      nk1 = __ldg(rowptr + r1);
+    }
+    mbar_wait(&full_bar[s], parity);
+
+    unsigned char *st   = smem + (size_t)s * L.stage_bytes;
+    const int     *rp   = reinterpret_cast<const int *>(st + L.rp_off);
+    const int     *cs   = reinterpret_cast<const int *>(st + L.col_off);
+    const double  *vs   = reinterpret_cast<const double *>(st + L.val_off);
+    const int      r0   = t * R;
+    const int      rows = min(R, m - r0);
+    const int      k0   = rp[0];
+    const int      k1   = rp[rows];
+    const bool     staged = (k1 - k0 <= cap);
+    const int      k0a  = k0 & ~3;
+
+    /* the row loop bound is warp-uniform (lanes without a row stay in the loop and only join the shuffles) */
+    for (int base = 0; base < rows; base += RPP) {
+      const int  lr  = base + grp;
+      const bool act = lr < rows;
+      const int  r   = r0 + lr;
+      const int  ks  = act ? rp[lr] : 0, ke = act ? rp[lr + 1] : 0;
+      double     sum;
+      if (G == 1) {
+        /* parity mode: strict left-to-right, FMA-free (aij.h:609-614) */
+        sum = (act && yin) ? yin[r] : 0.0;
+        if (staged) {
+          for (int k = ks - k0a; k < ke - k0a; k++) sum = __dadd_rn(sum, __dmul_rn(vs[k], __ldg(x + cs[k])));
+        } else {
+          for (int k = ks; k < ke; k++) sum = __dadd_rn(sum, __dmul_rn(__ldg(val + k), __ldg(x + __ldg(colidx + k))));
+        }
+      } else {
+        sum = 0.0;
+        if (staged) {
+          for (int k = ks - k0a + gl; k < ke - k0a; k += G) sum = fma(vs[k], __ldg(x + cs[k]), sum);
+        } else {
+          for (int k = ks + gl; k < ke; k += G) sum = fma(__ldg(val + k), __ldg(x + __ldg(colidx + k)), sum);
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (act && yin) sum += yin[r];
+      }
+      if (act && (G == 1 || gl == 0)) {
+        if (yplain) yplain[r] = sum;
+        yout[r] = dinv ? __dmul_rn(sum, __ldg(dinv + r)) : sum;
+      }
+    }
+    __syncthreads(); /* every thread is done reading stage s */
+    if (tid == 0 && tn < ntiles) issue(tn, s, nk0, nk1);
+  }
+}
+
+/* ------------------------------------------------------------------ analysis kernels */
+__global__ void tile_nnz_max_kernel(int m, const int *__restrict__ rowptr, int *out /* [16] */, int *maxrow)
+{
+  /* for R = 8<<k : max over tiles of rowptr[min((t+1)R,m)] - rowptr[tR]; also the max row length */
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int           loc[16];
+  int           mr = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) loc[k] = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
+    int a = rowptr[r];
+    mr    = max(mr, rowptr[r + 1] - a);
+    if ((r & 7) == 0) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        int64_t R = (int64_t)8 << k;
+        if ((r & (R - 1)) == 0) {
+          int64_t e = r + R;
+          if (e > m) e = m;
+          loc[k] = max(loc[k], rowptr[e] - a);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    int v = loc[k];
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(&out[k], v);
+  }
+  for (int o = 16; o > 0; o >>= 1) mr = max(mr, __shfl_xor_sync(0xffffffffu, mr, o));
+  if ((threadIdx.x & 31) == 0 && mr) atomicMax(maxrow, mr);
+}
+
+__global__ void get_diagonal_kernel(int m, const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ val, double *diag, int *diagpos)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
+    int    pos = -1;
+    double d   = 0.0;
+    for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
+      int c = colidx[k];
+      if (c == (int)r) {
+        pos = k;
+        d   = val[k];
+        break;
+      }
+      if (c > (int)r) break; /* columns are sorted (MatAssemblyEnd_SeqAIJ) */
+    }
+    diag[r] = d;
+    if (diagpos) diagpos[r] = pos;
+  }
+}
+
+__global__ void jacobi_invert_kernel(int64_t n, const double *__restrict__ d, double *dinv, int *nzero)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int           z      = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double v = d[i];
+    if (v == 0.0) {
+      z++;
+      dinv[i] = 1.0; /* jacobi.c:253-266 */
+    } else dinv[i] = 1.0 / v;
+  }
+  if (z) atomicAdd(nzero, z);
+}
+
+/* ------------------------------------------------------------------ plan */
+static int pick_lanes(double avg)
+{
+  if (avg <= 12.0) return 1;
+  if (avg <= 24.0) return 2;
+  if (avg <= 48.0) return 4;
+  if (avg <= 96.0) return 8;
+  if (avg <= 192.0) return 16;
+  return 32;
+}
+
+static int roundup4(int v) { return (v + 3) & ~3; }
+
+static int plan_configure(b200CsrPlan p)
+{
+  double avg = p->m ? (double)p->nnz / p->m : 0.0;
+  int    G   = p->user_lanes ? p->user_lanes : pick_lanes(avg);
+  int    S   = p->user_stages ? p->user_stages : 2;
+  int    cps = p->user_ctas ? p->user_ctas : 2;
+  if (S > SPMV_MAX_STAGES) S = SPMV_MAX_STAGES;
+  /* shared-memory budget per CTA: 227 KB per SM, 1 KB reserved per resident CTA, static smem for the barriers */
+  const int budget = (227 * 1024) / cps - 1024 - 256;
+  int       minR   = SPMV_TPB / G; /* at least one full pass */
+  if (minR < 8) minR = 8;
+  int R = 0, cap = 0;
+  for (int k = 8; k >= 0 && !R; k--) { /* largest R = 8<<k whose worst tile fits one stage */
+    int Rk = 8 << k;
+    if (p->user_rows ? Rk != p->user_rows : Rk < minR) continue;
+    int capk = roundup4(p->max_tile_nnz[k]);
+    if (capk < 64) capk = 64;
+    if ((int64_t)stage_layout(Rk, capk).stage_bytes * S <= budget || p->user_rows) {
+      R   = Rk;
+      cap = capk;
+    }
+  }
+  if (!R) { /* user asked for an unsupported R, or even one pass of rows overflows: smallest R, fallback tiles */
+    R   = minR;
+    cap = 1 << 30;
+  }
+  /* clamp the capacity to what fits; tiles above it take the in-kernel global-memory path */
+  {
+    int fit = ((budget / S - (R + 4) * 4 - 128) / 12 - 4) & ~3;
+    if (fit < 64) fit = 64;
+    if (cap > fit) cap = fit;
+  }
+  StageLayout L  = stage_layout(R, cap);
+  p->lanes       = G;
+  p->rows_tile   = R;
+  p->cap         = cap;
+  p->stages      = S;
+  p->ctas_per_sm = cps;
+  p->smem        = L.stage_bytes * S;
+  int ntiles     = (p->m + R - 1) / R;
+  int grid       = p->num_sms * cps;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  p->grid = grid;
+  return 0;
+}
+
+extern "C" int b200CsrPlanCreate(b200Handle h, int m, int n, int64_t nnz, const int *d_rowptr, const int *d_colidx, b200CsrPlan *plan)
+{
+  B200_CHECK(h && plan, B200_ERR_ARG_NULL, "null argument");
+  B200_CHECK(m >= 0 && n >= 0 && nnz >= 0, B200_ERR_ARG_OUTOFRANGE, "negative size");
+  B200_CHECK(nnz <= 2147483647LL - 8, B200_ERR_SUP, "nnz %lld does not fit 32-bit PetscInt row pointers (needs --with-64-bit-indices)", (long long)nnz);
+  B200_CHECK(!m || (d_rowptr && (nnz == 0 || d_colidx)), B200_ERR_ARG_NULL, "null CSR arrays");
+  b200CsrPlan p = (b200CsrPlan)calloc(1, sizeof(*p));
+  B200_CHECK(p, B200_ERR_MEM, "out of host memory");
+  p->m = m; p->n = n; p->nnz = nnz; p->d_rowptr = d_rowptr; p->d_colidx = d_colidx; p->num_sms = h->num_sms;
+  if (m > 0) {
+    int *d_stats;
+    int  hstats[17];
+    B200_CUDA(cudaMalloc(&d_stats, sizeof(int) * 17));
+    B200_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(int) * 17, h->stream));
+    int g = (int)(((int64_t)m + 255) / 256);
+    if (g > h->num_sms * 8) g = h->num_sms * 8;
+    tile_nnz_max_kernel<<<g, 256, 0, h->stream>>>(m, d_rowptr, d_stats, d_stats + 16);
+    B200_LAUNCHED(1);
+    B200_KERNEL_CHECK();
+    B200_CUDA(cudaMemcpyAsync(hstats, d_stats, sizeof hstats, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    B200_CUDA(cudaFree(d_stats));
+    for (int k = 0; k < 16; k++) p->max_tile_nnz[k] = hstats[k];
+    p->max_row_nnz = hstats[16];
+  }
+  plan_configure(p);
+  *plan = p;
+  return 0;
+}
+
+extern "C" int b200CsrPlanDestroy(b200CsrPlan plan)
+{
+  free(plan);
+  return 0;
+}
+
+extern "C" int b200CsrPlanSetLayout(b200CsrPlan p, int lanes, int rows_per_tile, int stages, int ctas_per_sm)
+{
+  B200_CHECK(p, B200_ERR_ARG_NULL, "null plan");
+  B200_CHECK(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32, B200_ERR_ARG_OUTOFRANGE, "lanes_per_row must be 0,1,2,4,8,16,32");
+  B200_CHECK(rows_per_tile == 0 || (rows_per_tile >= 8 && rows_per_tile <= 2048 && (rows_per_tile & (rows_per_tile - 1)) == 0), B200_ERR_ARG_OUTOFRANGE, "rows_per_tile must be 0 or a power of two in [8,2048]");
+  B200_CHECK(stages >= 0 && stages <= SPMV_MAX_STAGES && ctas_per_sm >= 0 && ctas_per_sm <= 8, B200_ERR_ARG_OUTOFRANGE, "stages/ctas out of range");
+  p->user_lanes = lanes; p->user_rows = rows_per_tile; p->user_stages = stages; p->user_ctas = ctas_per_sm;
+  return plan_configure(p);
+}
+
+extern "C" int b200CsrPlanGetLayout(b200CsrPlan p, int *lanes, int *rows, int *stages, int *grid, int *smem, int *maxrow)
+{
+  B200_CHECK(p, B200_ERR_ARG_NULL, "null plan");
+  if (lanes) *lanes = p->lanes;
+  if (rows) *rows = p->rows_tile;
+  if (stages) *stages = p->stages;
+  if (grid) *grid = p->grid;
+  if (smem) *smem = p->smem;
+  if (maxrow) *maxrow = p->max_row_nnz;
+  return 0;
+}
+
+template <int G>
+static int spmv_launch_g(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
+{
+  static int configured = 0;
+  if (configured < p->smem) {
+    B200_CUDA(cudaFuncSetAttribute(csr_spmv_tile_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    configured = 227 * 1024;
+  }
+  csr_spmv_tile_kernel<G><<<p->grid, SPMV_TPB, p->smem, h->stream>>>(p->m, p->rows_tile, p->cap, p->stages, p->d_rowptr, p->d_colidx, val, x, yin, dinv, yout, yplain);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  return 0;
+}
+
+static int spmv_launch(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
+{
+  B200_CHECK(h && p, B200_ERR_ARG_NULL, "null handle/plan");
+  if (p->m == 0) return 0;
+  B200_CHECK(yout && x && (val || p->nnz == 0), B200_ERR_ARG_NULL, "null vector/value pointer");
+  B200_CHECK((((uintptr_t)val) & 15) == 0 && (((uintptr_t)p->d_colidx) & 15) == 0 && (((uintptr_t)p->d_rowptr) & 15) == 0, B200_ERR_ARG_WRONG, "CSR arrays must be 16-byte aligned (allocate with b200Malloc)");
+  switch (p->lanes) {
+  case 1: return spmv_launch_g<1>(h, p, val, x, yin, dinv, yout, yplain);
+  case 2: return spmv_launch_g<2>(h, p, val, x, yin, dinv, yout, yplain);
+  case 4: return spmv_launch_g<4>(h, p, val, x, yin, dinv, yout, yplain);
+  case 8: return spmv_launch_g<8>(h, p, val, x, yin, dinv, yout, yplain);
+  case 16: return spmv_launch_g<16>(h, p, val, x, yin, dinv, yout, yplain);
+  case 32: return spmv_launch_g<32>(h, p, val, x, yin, dinv, yout, yplain);
+  }
+  B200_CHECK(0, B200_ERR_ARG_WRONGSTATE, "bad plan");
+}
+
+extern "C" int b200CsrSpMV(b200Handle h, b200CsrPlan p, const double *val, const double *x, double *y) { return spmv_launch(h, p, val, x, NULL, NULL, y, NULL); }
+extern "C" int b200CsrSpMVAdd(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *y, double *z)
+{
+  B200_CHECK(y, B200_ERR_ARG_NULL, "null y");
+  return spmv_launch(h, p, val, x, y, NULL, z, NULL);
+}
+extern "C" int b200CsrSpMVJacobi(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *dinv, double *w, double *y)
+{
+  B200_CHECK(dinv, B200_ERR_ARG_NULL, "null dinv");
+  return spmv_launch(h, p, val, x, NULL, dinv, w, y);
+}
+
+extern "C" int b200CsrGetDiagonal(b200Handle h, int m, const int *rowptr, const int *colidx, const double *val, double *diag, int *diagpos)
+{
+  B200_CHECK(h, B200_ERR_ARG_NULL, "null handle");
+  if (m <= 0) return 0;
+  B200_CHECK(rowptr && diag, B200_ERR_ARG_NULL, "null pointer");
+  int g = (m + 255) / 256;
+  if (g > h->num_sms * 8) g = h->num_sms * 8;
+  get_diagonal_kernel<<<g, 256, 0, h->stream>>>(m, rowptr, colidx, val, diag, diagpos);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  return 0;
+}
+
+extern "C" int b200JacobiInvertDiagonal(b200Handle h, int64_t n, const double *diag, double *dinv, int *nzero_host)
+{
+  B200_CHECK(h, B200_ERR_ARG_NULL, "null handle");
+  if (nzero_host) *nzero_host = 0;
+  if (n <= 0) return 0;
+  B200_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+  int64_t g = (n + 255) / 256;
+  if (g > h->num_sms * 8) g = h->num_sms * 8;
+  jacobi_invert_kernel<<<(int)g, 256, 0, h->stream>>>(n, diag, dinv, h->d_flag);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  if (nzero_host) {
+    B200_CUDA(cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    *nzero_host = *h->h_flag;
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------ benchmark operator generator (device side) */
+/* number of stencil entries in rows [0, r) of the 7-point operator, closed form (no scan needed) */
+__host__ __device__ inline int64_t lap7_prefix(int nx, int ny, int nz, int64_t r)
+{
+  const int64_t nxy = (int64_t)nx * ny;
+  if (r <= 0) return 0;
+  int64_t z = r / nxy, rem = r % nxy, y = rem / nx, x = rem % nx;
+  /* entries = 7*r - (#rows with x==0) - (#x==nx-1) - (#y==0) - (#y==ny-1) - (#z==0) - (#z==nz-1) among rows < r */
+  int64_t full_planes = z, full_lines = z * ny + y;
+  int64_t cx0 = full_lines + (x > 0 ? 1 : 0);                    /* rows with x == 0 */
+  int64_t cx1 = full_lines + 0;                                   /* rows with x == nx-1: only in completed lines */
+  int64_t cy0 = full_planes * nx + (y > 0 ? nx : x);              /* y == 0 */
+  int64_t cy1 = full_planes * nx + (y == ny - 1 ? x : 0);         /* y == ny-1 */
+  int64_t cz0 = z > 0 ? nxy : rem;                                /* z == 0 */
+  int64_t cz1 = z == nz - 1 ? rem : 0;                            /* z == nz-1 */
+  if (nx == 1) cx1 = cx0;
+  return 7 * r - cx0 - cx1 - cy0 - cy1 - cz0 - cz1;
+}
+
+__global__ void lap7_fill_kernel(int nx, int ny, int nz, int64_t r0, int64_t r1, int64_t base, int *rowptr, int *colidx, double *val)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nxy    = (int64_t)nx * ny;
+  for (int64_t r = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < r1; r += stride) {
+    int     x = (int)(r % nx), y = (int)((r / nx) % ny), z = (int)(r / nxy);
+    int64_t k = lap7_prefix(nx, ny, nz, r) - base;
+    rowptr[r - r0] = (int)k;
+    if (z > 0) { colidx[k] = (int)(r - nxy); val[k++] = -1.0; }
+    if (y > 0) { colidx[k] = (int)(r - nx); val[k++] = -1.0; }
+    if (x > 0) { colidx[k] = (int)(r - 1); val[k++] = -1.0; }
+    colidx[k] = (int)r; val[k++] = 6.0;
+    if (x < nx - 1) { colidx[k] = (int)(r + 1); val[k++] = -1.0; }
+    if (y < ny - 1) { colidx[k] = (int)(r + nx); val[k++] = -1.0; }
+    if (z < nz - 1) { colidx[k] = (int)(r + nxy); val[k++] = -1.0; }
+    if (r == r1 - 1) rowptr[r1 - r0] = (int)k;
+  }
+}
+
+extern "C" int b200GenLaplace7Nnz(int nx, int ny, int nz, int64_t r0, int64_t r1, int64_t *nnz)
+{
+  *nnz = lap7_prefix(nx, ny, nz, r1) - lap7_prefix(nx, ny, nz, r0);
+  return 0;
+}
+
+extern "C" int b200GenLaplace7(b200Handle h, int nx, int ny, int nz, int64_t r0, int64_t r1, int *rowptr, int *colidx, double *val)
+{
+  B200_CHECK(h, B200_ERR_ARG_NULL, "null handle");
+  B200_CHECK(nx > 0 && ny > 0 && nz > 0 && r0 >= 0 && r1 >= r0 && r1 <= (int64_t)nx * ny * nz, B200_ERR_ARG_OUTOFRANGE, "bad grid/row range");
+  B200_CHECK((int64_t)nx * ny * nz <= 2147483647LL, B200_ERR_SUP, "global size exceeds 32-bit PetscInt");
+  if (r1 == r0) {
+    B200_CUDA(cudaMemsetAsync(rowptr, 0, sizeof(int), h->stream));
+    return 0;
+  }
+  int64_t g = (r1 - r0 + 255) / 256;
+  if (g > h->num_sms * 16) g = h->num_sms * 16;
+  lap7_fill_kernel<<<(int)g, 256, 0, h->stream>>>(nx, ny, nz, r0, r1, lap7_prefix(nx, ny, nz, r0), rowptr, colidx, val);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  return 0;
+}
+
+/* ------------------------------------------------------------------ compressed-row multadd (off-diagonal block of MATMPIAIJ) */
+/* MatMultAdd_SeqAIJ, compressed-row branch (aij.c:1626-1640): only rows that own entries are touched,
+   z[ridx[i]] = y[ridx[i]] + sum, strict left-to-right, FMA-free.  In place (z == y) the untouched rows need no copy. */
+__global__ void csr_multadd_compressed_kernel(int nrows, const int *__restrict__ cr_i, const int *__restrict__ ridx, const int *__restrict__ colidx, const double *__restrict__ val, const double *__restrict__ x, const double *y, double *z)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += stride) {
+    const int r   = ridx[i];
+    double    sum = y[r];
+    for (int k = cr_i[i]; k < cr_i[i + 1]; k++) sum = __dadd_rn(sum, __dmul_rn(val[k], __ldg(x + colidx[k])));
+    z[r] = sum;
+  }
+}
+
+extern "C" int b200CsrSpMVAddCompressed(b200Handle h, int nrows_c, const int *d_cr_i, const int *d_rindex, const int *d_colidx, const double *d_val, const double *d_x, const double *d_y, double *d_z)
+{
+  B200_CHECK(h, B200_ERR_ARG_NULL, "null handle");
+  if (nrows_c <= 0) return 0;
+  B200_CHECK(d_cr_i && d_rindex && d_colidx && d_val && d_x && d_y && d_z, B200_ERR_ARG_NULL, "null pointer");
+  int g = (nrows_c + 255) / 256;
+  if (g > h->num_sms * 8) g = h->num_sms * 8;
+  csr_multadd_compressed_kernel<<<g, 256, 0, h->stream>>>(nrows_c, d_cr_i, d_rindex, d_colidx, d_val, d_x, d_y, d_z);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  return 0;
+}
+
+/* compressed-row analysis (MatCheckCompressedRow, src/mat/utils/compressedrow.c): list of non-empty rows */
+__global__ void count_nonempty_kernel(int m, const int *__restrict__ rowptr, int *count)
+{
+  const int stride = gridDim.x * blockDim.x;
+  int       c      = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) c += (rowptr[r + 1] > rowptr[r]);
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+extern "C" int b200CsrCountNonemptyRows(b200Handle h, int m, const int *d_rowptr, int *count_host)
+{
+  B200_CHECK(h && count_host, B200_ERR_ARG_NULL, "null argument");
+  *count_host = 0;
+  if (m <= 0) return 0;
+  B200_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+  int g = (m + 255) / 256;
+  if (g > h->num_sms * 8) g = h->num_sms * 8;
+  count_nonempty_kernel<<<g, 256, 0, h->stream>>>(m, d_rowptr, h->d_flag);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  B200_CUDA(cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  *count_host = *h->h_flag;
+  return 0;
+}

@@ -1,0 +1,113 @@
+"""CPU-side checks of the C-ABI libraries: they load, export every symbol the headers declare, fail loudly without a GPU,
+and the pure host logic (options database, MPIAIJ column split, halo plan) matches the oracle.  No compute calls."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from petsc_b200 import _capi, petsc
+
+
+def test_kernel_library_exports_every_declared_symbol():
+    L = _capi.lib()
+    names = _capi.exported_symbols()
+    assert len(names) > 60
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert b"sm_100a" in L.b200Version()
+
+
+def test_host_library_exports_every_declared_symbol():
+    L = petsc.lib()
+    names = petsc.host_symbols()
+    assert len(names) > 100
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device the product path must raise, never compute on the CPU."""
+    n = C.c_int(0)
+    rc = _capi.lib().b200DeviceCount(C.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(petsc.PetscError) as e:
+        petsc.initialize()
+    assert e.value.code in (97, 96)  # PETSC_ERR_GPU
+    h = C.c_void_p()
+    assert _capi.lib().b200Create(C.byref(h), 0) == 97
+    assert b"cuda error" in _capi.lib().b200GetLastErrorString()
+
+
+def test_package_does_not_import_oracle():
+    import subprocess
+    import sys
+    out = subprocess.check_output([sys.executable, "-c", "import sys; import petsc_b200, petsc_b200.petsc; print([m for m in sys.modules if 'oracle' in m])"],
+                                  cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.strip() == b"[]"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "petsc_b200")):
+        for f in files:
+            if f.endswith((".py", ".c", ".cu", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, f), errors="replace").read().lower(), f
+
+
+def test_options_database():
+    L = petsc.lib()
+    petsc.options_clear()
+    petsc.options_insert("-ksp_type gmres -ksp_rtol 1e-7 -ksp_monitor -shift -1.5 -sub_pc_type ilu")
+    v = C.c_double(0); s = C.c_int(0); buf = C.create_string_buffer(64); b = C.c_int(0)
+    petsc.chk(L.PetscOptionsGetReal(None, None, b"-ksp_rtol", C.byref(v), C.byref(s))); assert s.value and v.value == 1e-7
+    petsc.chk(L.PetscOptionsGetReal(None, None, b"-shift", C.byref(v), C.byref(s))); assert s.value and v.value == -1.5
+    petsc.chk(L.PetscOptionsGetString(None, None, b"-ksp_type", buf, 64, C.byref(s))); assert buf.value == b"gmres"
+    petsc.chk(L.PetscOptionsGetString(None, b"sub_", b"-pc_type", buf, 64, C.byref(s))); assert buf.value == b"ilu"
+    petsc.chk(L.PetscOptionsGetBool(None, None, b"-ksp_monitor", C.byref(b), C.byref(s))); assert s.value and b.value
+    petsc.chk(L.PetscOptionsGetBool(None, None, b"-nope", C.byref(b), C.byref(s))); assert not s.value
+    petsc.options_set("-ksp_type", "cg")
+    petsc.chk(L.PetscOptionsGetString(None, None, b"-ksp_type", buf, 64, C.byref(s))); assert buf.value == b"cg"
+    assert L.PetscOptionsSetValue(None, b"bad", b"1") == 62  # PETSC_ERR_ARG_WRONG
+    assert b"must start with" in L.PetscB200GetLastErrorMessage()
+    petsc.options_clear()
+
+
+def _split(L, ai, ajg, aa, cstart, cend):
+    m = len(ai) - 1
+    P = C.POINTER
+    Ai, Aj, Bi, Bj, g = P(C.c_int)(), P(C.c_int)(), P(C.c_int)(), P(C.c_int)(), P(C.c_int)()
+    Aa, Ba = P(C.c_double)(), P(C.c_double)()
+    ec = C.c_int()
+    petsc.chk(L.PetscB200MPIAIJSplit(m, int(cstart), int(cend), ai.ctypes.data_as(C.c_void_p), ajg.ctypes.data_as(C.c_void_p), aa.ctypes.data_as(C.c_void_p),
+                                     C.byref(Ai), C.byref(Aj), C.byref(Aa), C.byref(Bi), C.byref(Bj), C.byref(Ba), C.byref(g), C.byref(ec)))
+    as_np = np.ctypeslib.as_array
+    ai_ = as_np(Ai, (m + 1,)).copy(); bi_ = as_np(Bi, (m + 1,)).copy()
+    A = (ai_, as_np(Aj, (max(ai_[-1], 1),))[:ai_[-1]].copy(), as_np(Aa, (max(ai_[-1], 1),))[:ai_[-1]].copy())
+    B = (bi_, as_np(Bj, (max(bi_[-1], 1),))[:bi_[-1]].copy(), as_np(Ba, (max(bi_[-1], 1),))[:bi_[-1]].copy())
+    return A, B, as_np(g, (max(ec.value, 1),))[:ec.value].copy()
+
+
+@pytest.mark.parametrize("size", [2, 3, 5])
+def test_mpiaij_split_and_halo_plan_match_oracle(oracle, size):
+    """MatSetUpMultiply_MPIAIJ restatement in the host library (index work: bit-exact) vs the oracle's, rank by rank."""
+    L = petsc.lib()
+    for gen in (lambda: oracle.lap5(9, 7), lambda: oracle.lap7(6, 5, 7), lambda: oracle.random_csr(211, 6, 5)):
+        ai, aj, aa = gen()
+        n = len(ai) - 1
+        rs = oracle.split_ownership(n, size)
+        ranges = np.ascontiguousarray(rs, dtype=np.int64)
+        for r in range(size):
+            r0, r1 = int(rs[r]), int(rs[r + 1])
+            lai = (ai[r0:r1 + 1] - ai[r0]).astype(np.int32)
+            laj = np.ascontiguousarray(aj[ai[r0]:ai[r1]]); laa = np.ascontiguousarray(aa[ai[r0]:ai[r1]])
+            A, B, g = _split(L, lai, laj, laa, r0, r1)
+            oA, oB, og = oracle.mpiaij_split(lai, laj.astype(np.int64), laa, r0, r1)
+            for x, y in zip(A + B, oA + oB):
+                assert np.array_equal(x, y)
+            assert np.array_equal(g, og) and np.all(np.diff(g) > 0)
+            rc = np.zeros(size, np.int32); ro = np.zeros(size, np.int32)
+            petsc.chk(L.PetscB200HaloPlanRecv(len(g), g.astype(np.int32).ctypes.data_as(C.c_void_p), size, ranges.ctypes.data_as(C.c_void_p),
+                                              rc.ctypes.data_as(C.c_void_p), ro.ctypes.data_as(C.c_void_p)))
+            assert rc[r] == 0 and rc.sum() == len(g)
+            for p in range(size):
+                seg = g[ro[p]:ro[p] + rc[p]]
+                assert np.all((seg >= rs[p]) & (seg < rs[p + 1]))
