@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract.
+
+Workload (BASELINE.json configs[1]): 3-D 7-point Laplacian 512^3 (n = 134 217 728, nnz = 937 951 232), MATSEQAIJ layout,
+KSPGMRES(30) + PCJACOBI, fp64, through the C host mirror (-mat_type aijb200 -vec_type b200).  A "step" is one GMRES(30)
+restart cycle = 30 Krylov iterations (initial residual, 30 x [SpMV+Jacobi, MDot, MAXPY, norm, scale], solution update).
+N > 1 is weak scaling: every rank owns a 512 x 512 x 512 slab of a 512 x 512 x (512 N) grid (row-partitioned MPIAIJ, NCCL
+halo + all-reduces); `value` counts iterations in units of one 512^3 problem so that it is extensive in N.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 512]
+
+Rank 0 prints ONE JSON line.  Timing: CUDA events on the library's stream around the whole timed region, barrier +
+synchronize on both sides, max over ranks.  Inputs (13.9 GB matrix, 36 GB Krylov basis) are far larger than the 126 MB
+L2, so no explicit flush is needed between iterations.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RESTART = 30
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+def measured_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (driver-measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip().split(", "))
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------- distributed plumbing
+class Dist:
+    def __init__(self):
+        self.rank, self.size, self.local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+        self.td = None
+        if self.size > 1:
+            import torch.distributed as td
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            td.init_process_group("gloo", rank=self.rank, world_size=self.size)  # control plane only; data moves over NCCL inside libpetscb200
+            self.td = td
+
+    def barrier(self):
+        if self.td:
+            self.td.barrier()
+
+    def bcast(self, obj):
+        if not self.td:
+            return obj
+        box = [obj]
+        self.td.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def max(self, v):
+        if not self.td:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64)
+        self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
+        return float(t[0])
+
+    def sum(self, v):
+        if not self.td:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64)
+        self.td.all_reduce(t, op=self.td.ReduceOp.SUM)
+        return float(t[0])
+
+    def close(self):
+        if self.td:
+            self.td.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------- product arm
+def run_product(a, D):
+    from petsc_b200 import _capi, petsc
+    K, W, n = a.steps, a.warmup, a.n
+    L = _capi.lib()
+    petsc.initialize(device=D.local)
+    if D.size > 1:
+        uid = D.bcast(petsc.comm_unique_id() if D.rank == 0 else None)
+        petsc.comm_init(D.rank, D.size, uid)
+    comm = petsc.COMM_WORLD
+    H = petsc.handle()
+
+    class Hh:  # adapter so _capi helpers can use the host library's handle
+        h = H
+    nloc = n * n * n
+    nzg = n * D.size
+    r0, r1 = D.rank * nloc, (D.rank + 1) * nloc
+    nnz = C.c_int64()
+    _capi.check(L.b200GenLaplace7Nnz(n, n, nzg, C.c_int64(r0), C.c_int64(r1), C.byref(nnz)))
+    nnz = nnz.value
+    d_i = _capi.DeviceArray(Hh, nloc + 1, np.int32)
+    d_j = _capi.DeviceArray(Hh, nnz, np.int32)
+    d_a = _capi.DeviceArray(Hh, nnz, np.float64)
+    _capi.check(L.b200GenLaplace7(H, n, n, nzg, C.c_int64(r0), C.c_int64(r1), d_i.ptr, d_j.ptr, d_a.ptr))
+
+    petsc.options_clear()
+    petsc.options_insert("-mat_type aijb200 -vec_type b200 -ksp_type gmres -ksp_gmres_restart %d -pc_type jacobi -ksp_rtol 1e-300 -ksp_atol 1e-300 -ksp_divtol 1e300" % RESTART)
+    if a.options:
+        petsc.options_insert(a.options)
+
+    def make_mat_from_device():
+        A = petsc.Mat.create(m=nloc, n=nloc, comm=comm)
+        A.set_csr_device(d_i.ptr, d_j.ptr, d_a.ptr)
+        return A
+
+    A = make_mat_from_device()
+    x, b = A.create_vecs()
+    u = x.duplicate(); u.set(1.0); A.mult(u, b); u.destroy()   # b = A*1 (ex2.c / bench_kspsolve.c convention)
+    ksp = petsc.KSP.create(comm)
+    ksp.set_operators(A)
+    ksp.set_from_options()
+
+    def solve(cycles):
+        ksp.set_tolerances(max_it=RESTART * cycles)
+        ksp.solve(b, x)
+        assert ksp.its() == RESTART * cycles, (ksp.its(), ksp.reason())
+
+    timer = _capi.Timer(Hh)
+    solve(max(W, 1))                       # warm-up (also allocates the Krylov basis)
+    clocks = ClockSampler(D.local)
+    D.barrier(); Hh_sync(L, H)
+    clocks.start()
+    l0 = _capi.launch_count()
+    timer.start()
+    solve(K)
+    timer.stop()
+    ms = timer.ms()
+    launches = _capi.launch_count() - l0
+    Hh_sync(L, H); D.barrier()
+    clk = clocks.stop()
+    ms = D.max(ms)
+    rnorm = ksp.rnorm()
+    its_per_s = RESTART * K / (ms * 1e-3)
+    value = its_per_s * D.size             # in units of one 512^3 problem (extensive under weak scaling)
+
+    # ---- dominant-kernel roofline: the CSR SpMV kernel alone, CUDA events on its stream
+    peak, peak_src = measured_peak()
+    Ad = A.mpiaij_blocks()[0] if D.size > 1 else A
+    xs, ys = Ad.create_vecs()
+    xs.set(1.0)
+    for _ in range(3):
+        Ad.mult(xs, ys)
+    reps = 20
+    t2 = _capi.Timer(Hh)
+    t2.start()
+    for _ in range(reps):
+        Ad.mult(xs, ys)
+    t2.stop()
+    spmv_ms = t2.ms() / reps
+    nnz_d = nnz if D.size == 1 else int(Ad.csr_nnz())
+    alg_bytes = nnz_d * 12 + nloc * 20     # nnz*(8+4) + rows*(4+8+8)
+    flops = 2 * nnz_d - nloc               # PETSc's own count (aij.c:1497)
+    achieved = alg_bytes / (spmv_ms * 1e-3) / 1e9
+    roofline = {"kernel": "csr_spmv_tile_kernel<1> (MatMult_SeqAIJB200)", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4), "peak_source": peak_src,
+                "traffic": a.traffic, "ms": round(spmv_ms, 4), "gflops": round(flops / (spmv_ms * 1e-3) / 1e9, 1), "algorithmic_bytes": alg_bytes}
+    xs.destroy(); ys.destroy()
+    # whole-iteration model: bytes/row/iteration averaged over a 30-cycle with Jacobi fused into the SpMV and the norm into MAXPY
+    it_bytes = nloc * (alg_bytes / nloc + 8 + sum(8 * (j + 2) + 8 * (j + 3) for j in range(RESTART)) / RESTART + 16)
+    iter_model = {"bytes_per_iteration": int(it_bytes), "achieved_gbs": round(it_bytes * its_per_s / 1e9, 1), "frac_of_peak": round(it_bytes * its_per_s / 1e9 / peak, 4),
+                  "spmv_bound_ratio": round((1.0 / its_per_s) / (it_bytes / (achieved * 1e9)), 3)}
+
+    # ---- e2e: public API with HOST buffers, host<->device copies inside the timed region
+    ksp.destroy(); x.destroy(); b.destroy(); A.destroy()
+    e2e = None
+    if not a.no_e2e:
+        e2e = run_e2e(a, D, petsc, _capi, L, H, Hh, d_i, d_j, d_a, nloc, nnz, comm, K)
+
+    out = {
+        "metric": "gmres30_jacobi_iterations_per_sec", "value": round(value, 3), "unit": "iterations/s (per 512^3-row problem unit; x n_gpus under weak scaling)",
+        "n_gpus": D.size, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D 7-point Laplacian %d^3 per GPU (global %dx%dx%d), MATSEQAIJ/MATMPIAIJ CSR int32+fp64, KSPGMRES(30)+PCJACOBI left-preconditioned, b=A*1, x0=0" % (n, n, n, nzg),
+                   "rows_per_gpu": nloc, "nnz_per_gpu": nnz, "step": "one GMRES(30) restart cycle = 30 iterations", "parallelism": "row-partitioned x%d, NCCL halo + all-reduce" % D.size,
+                   "l2_policy": "inputs_larger_than_L2 (13.9 GB matrix + 36 GB Krylov basis vs 126 MB L2)", "final_preconditioned_residual": rnorm},
+        "iterations_per_sec_global_problem": round(its_per_s, 3),
+        "spmv_gflops": roofline["gflops"], "roofline": roofline, "iteration_model": iter_model,
+        "gpu_launches": int(launches), "clocks": clk, "e2e": e2e,
+    }
+    if D.rank == 0 and D.size == 1 and not a.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(a, quick=True)
+    return out
+
+
+def Hh_sync(L, H):
+    from petsc_b200 import _capi
+    _capi.check(L.b200Synchronize(H))
+
+
+def run_e2e(a, D, petsc, _capi, L, H, Hh, d_i, d_j, d_a, nloc, nnz, comm, K):
+    """Host CSR + host b in pinned memory -> MatCreate...WithArrays / VecSetValues path (H2D inside) -> K x KSPSolve(30 its)
+    -> x back on the host after every solve (D2H inside)."""
+    vp = C.c_void_p
+
+    def pinned(nbytes):
+        p = vp()
+        _capi.check(L.b200MallocHost(C.byref(p), C.c_size_t(nbytes)))
+        return p
+
+    h_i, h_j, h_a = pinned(4 * (nloc + 1)), pinned(4 * nnz), pinned(8 * nnz)
+    _capi.check(L.b200MemcpyDtoH(H, h_i, d_i.ptr, C.c_size_t(4 * (nloc + 1))))
+    _capi.check(L.b200MemcpyDtoH(H, h_j, d_j.ptr, C.c_size_t(4 * nnz)))
+    _capi.check(L.b200MemcpyDtoH(H, h_a, d_a.ptr, C.c_size_t(8 * nnz)))
+    d_i.free(); d_j.free(); d_a.free()
+    hb = np.ones(nloc)  # placeholder right-hand side on the host, replaced by A*1 below
+    timer = _capi.Timer(Hh)
+    D.barrier(); Hh_sync(L, H)
+    timer.start()
+    A = petsc.Mat.create(m=nloc, n=nloc, comm=comm)
+    if D.size == 1:
+        petsc.chk(petsc.lib().MatSeqAIJSetPreallocationCSR(A.p, h_i, h_j, h_a))
+    else:
+        petsc.chk(petsc.lib().MatMPIAIJSetPreallocationCSR(A.p, h_i, h_j, h_a))
+    t_up = _capi.Timer(Hh); t_up.start(); t_up.stop()
+    x, b = A.create_vecs()
+    u = x.duplicate(); u.set(1.0); A.mult(u, b); u.destroy()
+    b.host_read()                                    # the user's right-hand side now lives in the Vec's pinned host mirror
+    ksp = petsc.KSP.create(comm)
+    ksp.set_operators(A)
+    ksp.set_from_options()
+    ksp.set_tolerances(max_it=RESTART)
+    h2d = 4 * (nloc + 1) + 12 * nnz
+    d2h = 8 * nloc
+    for _ in range(K):
+        b.touch_host()                               # this step's input is on the host: H2D from pinned memory on first device use
+        ksp.solve(b, x)
+        hx = x.host_read(1000)                       # D2H of this step's result into pinned memory
+        h2d += 8 * nloc; d2h += 8 * nloc
+    timer.stop()
+    ms = D.max(timer.ms())
+    res = {"value": round(RESTART * K / (ms * 1e-3) * D.size, 3), "unit": "iterations/s (same unit as value)", "h2d_bytes_per_step": int(h2d // K), "d2h_bytes_per_step": int(d2h // K),
+           "note": "timed region = host CSR -> device (MatSeqAIJSetPreallocationCSR) + K x [b host->device, KSPSolve 30 its, x device->host]; matrix upload amortised over %d steps" % K,
+           "ms_total": round(ms, 2), "x_checksum": float(sum(hx))}
+    ksp.destroy(); x.destroy(); b.destroy(); A.destroy()
+    for p in (h_i, h_j, h_a):
+        L.b200FreeHost(p)
+    return res
+
+
+# ---------------------------------------------------------------------------------------------- CPU arms (oracle)
+def cpu_baseline(a, quick=False, steps=1, warmup=0):
+    """The reference's CPU algorithm (restated in oracle/, OpenMP over all host cores) on a bounded sample of the workload:
+    the same 7-point operator at 256^3 (1/8 of the rows), one GMRES(30)+Jacobi cycle per step, scaled to the 512^3 unit
+    (the path is bandwidth bound, cost is linear in the number of rows)."""
+    from oracle import oracle_py as O
+    ns = a.cpu_n
+    ai, aj, aa = O.lap7(ns)
+    N = ns ** 3
+    b = O.matmult(ai, aj, aa, np.ones(N), omp=True)
+    thr = O.max_threads()
+    times = []
+    for s in range(warmup + steps):
+        t = time.time()
+        x, r = O.ksp_solve("gmres", ai, aj, aa, b, pc="jacobi", restart=RESTART, max_it=RESTART, rtol=1e-300, abstol=1e-300, dtol=1e300, omp=True)
+        dt = time.time() - t
+        if s >= warmup:
+            times.append(dt)
+        assert r["its"] == RESTART
+    dt = float(np.mean(times))
+    scale = N / float(a.n ** 3)
+    # CPU SpMV alone
+    t = time.time(); reps = 5
+    for _ in range(reps):
+        O.matmult(ai, aj, aa, b, omp=True)
+    spmv_s = (time.time() - t) / reps
+    return {"value": round(RESTART / dt * scale, 4), "unit": "iterations/s (512^3 unit)", "cores": thr, "kind": "port",
+            "sample": "oracle GMRES(30)+Jacobi, 7-pt %d^3 (%d rows), %d cycle(s) of 30 iterations, %.2f s per cycle, scaled by rows %d^3/%d^3" % (ns, N, steps, dt, ns, a.n),
+            "spmv_gflops": round((2 * len(aj) - N) / spmv_s / 1e9, 3), "seconds_per_step_sample": round(dt, 3)}
+
+
+def run_reference(a, D):
+    if D.rank != 0:
+        return None
+    cb = cpu_baseline(a, steps=a.steps, warmup=min(a.warmup, 1))
+    ms_step = cb["seconds_per_step_sample"] * 1e3 / ((a.cpu_n ** 3) / float(a.n ** 3))
+    return {"impl": "reference", "metric": "gmres30_jacobi_iterations_per_sec", "value": cb["value"], "unit": "iterations/s (per 512^3-row problem unit)", "n_gpus": D.size,
+            "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": round(ms_step, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": "3D 7-point Laplacian %d^3, KSPGMRES(30)+PCJACOBI on the host cores (bounded sample: %d^3, scaled by rows)" % (a.n, a.cpu_n),
+                                            "step": "one GMRES(30) restart cycle = 30 iterations"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--cpu-n", dest="cpu_n", type=int, default=256)
+    ap.add_argument("--options", default="")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes/launch of the SpMV kernel from the committed ncu capture")
+    a = ap.parse_args()
+    if a.traffic is None:
+        try:
+            a.traffic = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            a.traffic = None
+    D = Dist()
+    if a.impl == "reference":
+        out = run_reference(a, D)
+    else:
+        out = run_product(a, D)
+    if D.rank == 0 and out is not None:
+        print(json.dumps(out), flush=True)
+    D.close()
+
+
+if __name__ == "__main__":
+    main()

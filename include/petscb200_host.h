@@ -190,6 +190,11 @@ PetscErrorCode MatMultAdd(Mat mat, Vec v1, Vec v2, Vec v3);
 PetscErrorCode MatGetDiagonal(Mat mat, Vec v);
 PetscErrorCode MatGetDiagonalBlock(Mat A, Mat *a);                                                /* mpiaij.c:2758 */
 PetscErrorCode MatDestroy(Mat *A);
+typedef struct { /* include/petscmat.h MatInfo */
+  double block_size, nz_allocated, nz_used, nz_unneeded, memory, assemblies, mallocs, fill_ratio_given, fill_ratio_needed, factor_mallocs;
+} MatInfo;
+typedef enum { MAT_LOCAL = 1, MAT_GLOBAL_MAX = 2, MAT_GLOBAL_SUM = 3 } MatInfoType;
+PetscErrorCode MatGetInfo(Mat mat, MatInfoType flag, MatInfo *info);                              /* matrix.c MatGetInfo (nz_used, memory) */
 /* MPIAIJ internals exposed for parity tests: diag/off-diag blocks and garray (mpiaij.h:41-76, mmaij.c:8-126) */
 PetscErrorCode MatMPIAIJGetSeqAIJ(Mat A, Mat *Ad, Mat *Ao, const PetscInt *colmap[]);
 PetscErrorCode MatSeqAIJGetCSRHost(Mat A, PetscInt *m, const PetscInt **i, const PetscInt **j, const PetscScalar **a); /* host copy (downloads) */

@@ -14,6 +14,11 @@
 #include <omp.h>
 #endif
 
+/* CPU-baseline timing only: when set, the elementwise vector loops below also run under OpenMP (results of elementwise
+   loops are unchanged by threading; reductions use the *_omp variants explicitly) */
+static int g_omp = 0;
+#define OMP_FOR _Pragma("omp parallel for schedule(static) if (g_omp && n > 65536)")
+
 int ora_max_threads(void)
 {
 #ifdef _OPENMP
@@ -173,28 +178,34 @@ double ora_vecdot_omp(int64_t n, const double *x, const double *y)
   return s;
 }
 double ora_vecnorm2(int64_t n, const double *x) { return sqrt(ora_vecdot(n, x, x)); }
-void   ora_vecaxpy(int64_t n, double a, const double *x, double *y)
+void ora_vecaxpy(int64_t n, double a, const double *x, double *y)
 {
+  OMP_FOR
   for (int64_t i = 0; i < n; i++) y[i] += a * x[i];
 }
 void ora_vecaypx(int64_t n, double a, const double *x, double *y)
 {
+  OMP_FOR
   for (int64_t i = 0; i < n; i++) y[i] = x[i] + a * y[i];
 }
 void ora_vecaxpby(int64_t n, double a, double b, const double *x, double *y)
 {
+  OMP_FOR
   for (int64_t i = 0; i < n; i++) y[i] = a * x[i] + b * y[i];
 }
 void ora_vecwaxpy(int64_t n, double a, const double *x, const double *y, double *w)
 {
+  OMP_FOR
   for (int64_t i = 0; i < n; i++) w[i] = a * x[i] + y[i];
 }
 void ora_vecscale(int64_t n, double a, double *x)
 {
+  OMP_FOR
   for (int64_t i = 0; i < n; i++) x[i] *= a;
 }
 void ora_vecpointwisemult(int64_t n, const double *x, const double *y, double *w)
 {
+  OMP_FOR
   for (int64_t i = 0; i < n; i++) w[i] = x[i] * y[i];
 }
 void ora_vecreciprocal(int64_t n, double *x)
@@ -557,6 +568,7 @@ int ora_ksp_gmres(int n, const int *ai, const int *aj, const double *aa, const d
 {
   const int max_k = o->restart;
   ora_pc    pc;
+  g_omp = o->use_omp;
   int       rc = pc_setup(&pc, n, ai, aj, aa, o);
   if (rc) return rc;
   double **vv = (double **)malloc(sizeof(double *) * (size_t)(max_k + 1));
@@ -688,6 +700,7 @@ int ora_ksp_cg(int n, const int *ai, const int *aj, const double *aa, const doub
                ora_ksp_result *res, double *hist, int histcap)
 {
   ora_pc pc;
+  g_omp = o->use_omp;
   int    rc = pc_setup(&pc, n, ai, aj, aa, o);
   if (rc) return rc;
   double  *R = (double *)malloc(sizeof(double) * (size_t)n), *Z = (double *)malloc(sizeof(double) * (size_t)n);

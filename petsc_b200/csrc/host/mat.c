@@ -323,6 +323,26 @@ PetscErrorCode MatDestroy(Mat *A)
   *A = NULL;
   return PETSC_SUCCESS;
 }
+PetscErrorCode MatGetInfo(Mat mat, MatInfoType flag, MatInfo *info)
+{
+  PetscValidHeader(mat, 1);
+  PetscValidPointer(info, 3);
+  memset(info, 0, sizeof(*info));
+  info->block_size = 1.0;
+  double nz        = 0.0;
+  if (!strcmp(mat->hdr.type_name, MATSEQAIJB200) && mat->data) nz = (double)((Mat_SeqAIJB200 *)mat->data)->nz;
+  else if (!strcmp(mat->hdr.type_name, MATMPIAIJB200) && mat->data) {
+    Mat_MPIAIJB200 *a = (Mat_MPIAIJB200 *)mat->data; /* MatGetInfo_MPIAIJ: diag + off-diag blocks */
+    if (a->A && a->A->data) nz += (double)((Mat_SeqAIJB200 *)a->A->data)->nz;
+    if (a->B && a->B->data) nz += (double)((Mat_SeqAIJB200 *)a->B->data)->nz;
+  }
+  if (flag != MAT_LOCAL) PetscCall(PetscB200AllreduceHost(mat->hdr.comm, &nz, 1, flag == MAT_GLOBAL_MAX ? 1 : 0));
+  info->nz_used = info->nz_allocated = nz;
+  info->memory                       = nz * 12.0;
+  info->assemblies                   = (double)mat->assembled;
+  return PETSC_SUCCESS;
+}
+
 PetscErrorCode MatB200SetSpMVLayout(Mat A, PetscInt lanes, PetscInt rows, PetscInt stages, PetscInt ctas)
 {
   A->spmv_layout[0] = lanes; A->spmv_layout[1] = rows; A->spmv_layout[2] = stages; A->spmv_layout[3] = ctas;

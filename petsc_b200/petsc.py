@@ -165,6 +165,20 @@ class Vec:
         chk(lib().VecRestoreArrayRead(self.p, C.byref(p)))
         return out
 
+    def touch_host(self):
+        """Declare the pinned host mirror the valid copy (VecGetArrayWrite/Restore): the next device op uploads it."""
+        p = C.POINTER(dbl)()
+        chk(lib().VecGetArrayWrite(self.p, C.byref(p)))
+        chk(lib().VecRestoreArrayWrite(self.p, C.byref(p)))
+
+    def host_read(self, k=4):
+        """Bring the vector to the pinned host mirror (VecGetArrayRead: device->host copy) and return its first k entries."""
+        p = C.POINTER(dbl)()
+        chk(lib().VecGetArrayRead(self.p, C.byref(p)))
+        out = [p[i] for i in range(min(k, self.local_size()))]
+        chk(lib().VecRestoreArrayRead(self.p, C.byref(p)))
+        return out
+
     def device_ptr(self):
         p = vp()
         mt = i32()
@@ -329,6 +343,11 @@ class Mat:
 
     def get_diagonal(self, v):
         chk(lib().MatGetDiagonal(self.p, v.p))
+
+    def csr_nnz(self):
+        info = (dbl * 10)()
+        chk(lib().MatGetInfo(self.p, 1, info))
+        return int(info[2])
 
     def set_spmv_layout(self, lanes=0, rows=0, stages=0, ctas=0):
         chk(lib().MatB200SetSpMVLayout(self.p, lanes, rows, stages, ctas))
