@@ -88,6 +88,8 @@ int b200CsrPlanDestroy(b200CsrPlan plan);
 /* tuning / introspection: lanes_per_row in {0=auto,1,2,4,8,16,32}; lanes_per_row == 1 reproduces MatMult_SeqAIJ's
    strict left-to-right, FMA-free row sums bit for bit.  rows_per_tile 0 = auto. */
 int b200CsrPlanSetLayout(b200CsrPlan plan, int lanes_per_row, int rows_per_tile, int stages, int ctas_per_sm);
+/* L2 eviction hints: bit0 = stream val/col/rowptr as evict_first, bit1 = keep x as evict_last (default 3) */
+int b200CsrPlanSetCacheHints(b200CsrPlan plan, int hints);
 int b200CsrPlanGetLayout(b200CsrPlan plan, int *lanes_per_row, int *rows_per_tile, int *stages, int *grid, int *smem_bytes, int *max_row_nnz);
 /* y = A x                                             (MatMult_SeqAIJ, aij.c:1444-1499) */
 int b200CsrSpMV(b200Handle h, b200CsrPlan plan, const double *d_val, const double *d_x, double *d_y);
@@ -98,11 +100,20 @@ int b200CsrSpMVJacobi(b200Handle h, b200CsrPlan plan, const double *d_val, const
 /* compressed-row z = y + A x for a block whose rows are mostly empty (off-diagonal block B of MATMPIAIJ):
    only the nrows_c rows listed in d_rindex are read/written   (MatMultAdd_SeqAIJ compressed branch, aij.c:1626-1640) */
 int b200CsrSpMVAddCompressed(b200Handle h, int nrows_c, const int *d_cr_i, const int *d_rindex, const int *d_colidx, const double *d_val, const double *d_x, const double *d_y, double *d_z);
+/* MatAssemblyEnd_SeqAIJ invariants checked on the device: *bad_row = -1 if valid, else an offending row and
+   kind 1 = column out of range, 2 = columns not strictly increasing, 3 = decreasing row pointer */
+int b200CsrValidate(b200Handle h, int m, int n, const int *d_rowptr, const int *d_colidx, int *bad_row, int *kind);
 int b200CsrCountNonemptyRows(b200Handle h, int m, const int *d_rowptr, int *count_host);   /* MatCheckCompressedRow input */
 /* d[r] = a[diag(r)] or 0 ; d_diagpos (nullable) gets the position or -1   (MatGetDiagonal_SeqAIJ aij.c:1347, GetDiagonal_CSR aijcupm.hpp:115) */
 int b200CsrGetDiagonal(b200Handle h, int m, const int *d_rowptr, const int *d_colidx, const double *d_val, double *d_diag, int *d_diagpos);
 /* dinv[r] = 1/d[r], zero diagonal -> 1.0             (PCSetUp_Jacobi, jacobi.c:172-270) ; *nzero_host counts the zeros */
 int b200JacobiInvertDiagonal(b200Handle h, int64_t n, const double *d_diag, double *d_dinv, int *nzero_host);
+
+/* setup-time column split of a row block into the MATMPIAIJ diagonal block (local columns [cstart,cend), renumbered)
+   and off-diagonal block (global columns kept)   (MatSetUpMultiply_MPIAIJ first step, mmaij.c:25-61).  Outputs are
+   b200Malloc'ed and owned by the caller. */
+int b200CsrSplitColumns(b200Handle h, int m, const int *d_i, const int *d_j, const double *d_a, int cstart, int cend,
+                        int **d_Ai, int **d_Aj, double **d_Aa, int64_t *nzA, int **d_Bi, int **d_Bj, double **d_Ba, int64_t *nzB);
 
 /* ---- BLAS-1: VECSEQ ops / cuBLAS + MDot_kernel/MAXPY_kernel call sites in vecseqcupm_impl.hpp ---- */
 int b200VecSet(b200Handle h, int64_t n, double alpha, double *d_x);                                   /* VecSet */

@@ -131,6 +131,9 @@ class Handle:
     def csr_plan_set_layout(self, plan, lanes=0, rows=0, stages=0, ctas=0):
         check(lib().b200CsrPlanSetLayout(plan, lanes, rows, stages, ctas))
 
+    def csr_plan_set_hints(self, plan, hints):
+        check(lib().b200CsrPlanSetCacheHints(plan, int(hints)))
+
     def spmv(self, plan, d_val, d_x, d_y):
         check(lib().b200CsrSpMV(self.h, plan, d_val.ptr, d_x.ptr, d_y.ptr))
 

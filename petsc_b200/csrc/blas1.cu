@@ -202,14 +202,61 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[NV], double *partials,
 }
 
 /* ------------------------------------------------------------------ MDot */
-template <int NV, int UNR, bool VEC2>
-__global__ void __launch_bounds__(TPB) mdot_kernel(int64_t n, const double *__restrict__ x, PtrPack y, double *partials, unsigned int *counter, double *d_result, double *h_result)
+/* Generalised final stage: this CTA holds NVT accumulators per thread for the vectors [jbase, jbase+NVT); it is the
+   vb-th of nvb "virtual" CTAs walking x.  partials layout [nv][nvb]; the last CTA of the whole grid reduces them. */
+template <int NVT>
+__device__ __forceinline__ void grid_reduce_x(double (&acc)[NVT], int jbase, unsigned vb, unsigned nvb, int nv_total, double *partials, unsigned int *counter, double *d_result, double *h_result)
 {
-  double acc[NV];
+  __shared__ double   s_part[NVT][TPB / 32];
+  __shared__ unsigned s_last;
+  const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < NV; j++) acc[j] = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * TPB;
-  int64_t       i      = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  for (int j = 0; j < NVT; j++) {
+    double v = warp_sum(acc[j]);
+    if (lane == 0) s_part[j][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NVT) {
+    double v = s_part[threadIdx.x][0];
+#pragma unroll
+    for (int w = 1; w < TPB / 32; w++) v += s_part[threadIdx.x][w];
+    partials[(size_t)(jbase + threadIdx.x) * nvb + vb] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int j = warp; j < nv_total; j += TPB / 32) {
+      double v = 0.0;
+      for (unsigned b = lane; b < nvb; b += 32) v += __ldcg(&partials[(size_t)j * nvb + b]);
+      v = warp_sum(v);
+      if (lane == 0) {
+        d_result[j] = v;
+        if (h_result) h_result[j] = v;
+      }
+    }
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+/* Each thread owns NVT <= 16 accumulators.  SPLIT (nv > 16): the vectors are divided into two halves handled by the even
+   and the odd CTAs, which walk the same elements of x side by side (x comes from HBM once; the partner's read hits L2).
+   That bounds the register footprint (~64-80 registers -> 3-4 resident CTAs per SM) for every nv <= 32; without it
+   ptxas allocates up to 148 registers for some nv and occupancy collapses (profiles/round1_notes.md). */
+template <int NVT, int UNR, bool VEC2, bool SPLIT>
+__global__ void __launch_bounds__(TPB, (NVT <= 12 ? 4 : 3)) mdot_kernel(int64_t n, const double *__restrict__ x, PtrPack y, int nv_total, double *partials, unsigned int *counter, double *d_result, double *h_result)
+{
+  const int      sub   = SPLIT ? (int)(blockIdx.x & 1u) : 0;
+  const unsigned vb    = SPLIT ? (blockIdx.x >> 1) : blockIdx.x;
+  const unsigned nvb   = SPLIT ? (gridDim.x >> 1) : gridDim.x;
+  const int      jbase = sub * NVT;
+  double         acc[NVT];
+#pragma unroll
+  for (int j = 0; j < NVT; j++) acc[j] = 0.0;
+  const int64_t stride = (int64_t)nvb * TPB;
+  int64_t       i      = (int64_t)vb * TPB + threadIdx.x;
   if (VEC2) {
     const int64_t  nvec = n >> 1;
     const double2 *x2   = reinterpret_cast<const double2 *>(x);
@@ -221,8 +268,8 @@ __global__ void __launch_bounds__(TPB) mdot_kernel(int64_t n, const double *__re
         xv[u]     = k < nvec ? x2[k] : make_double2(0.0, 0.0);
       }
 #pragma unroll
-      for (int j = 0; j < NV; j++) {
-        const double2 *y2 = reinterpret_cast<const double2 *>(y.p[j]);
+      for (int j = 0; j < NVT; j++) {
+        const double2 *y2 = reinterpret_cast<const double2 *>(y.p[jbase + j]);
         double2        yv[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
@@ -236,38 +283,39 @@ __global__ void __launch_bounds__(TPB) mdot_kernel(int64_t n, const double *__re
         }
       }
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    if ((n & 1) && vb == 0 && threadIdx.x == 0) {
 #pragma unroll
-      for (int j = 0; j < NV; j++) acc[j] = fma(x[n - 1], y.p[j][n - 1], acc[j]);
+      for (int j = 0; j < NVT; j++) acc[j] = fma(x[n - 1], y.p[jbase + j][n - 1], acc[j]);
     }
   } else {
     for (; i < n; i += stride) {
       double xv = x[i];
 #pragma unroll
-      for (int j = 0; j < NV; j++) acc[j] = fma(xv, y.p[j][i], acc[j]);
+      for (int j = 0; j < NVT; j++) acc[j] = fma(xv, y.p[jbase + j][i], acc[j]);
     }
   }
-  grid_reduce<NV, 0>(acc, partials, counter, d_result, h_result);
+  grid_reduce_x<NVT>(acc, jbase, vb, nvb, nv_total, partials, counter, d_result, h_result);
 }
 
-template <int NV>
-static int mdot_launch_nv(b200Handle h, int64_t n, const double *x, const PtrPack &y, bool vec2, double *d_result, double *h_result)
+template <int NVT, bool SPLIT>
+static int mdot_launch_nv(b200Handle h, int64_t n, int nv, const double *x, const PtrPack &y, bool vec2, double *d_result, double *h_result)
 {
-  constexpr int UNR = NV <= 2 ? 4 : (NV <= 6 ? 2 : 1);
+  constexpr int UNR = NVT <= 2 ? 4 : (NVT <= 6 ? 2 : 1);
   static int    occ[2] = {0, 0};
-  void (*kern)(int64_t, const double *, PtrPack, double *, unsigned int *, double *, double *) = vec2 ? mdot_kernel<NV, UNR, true> : mdot_kernel<NV, 1, false>;
+  void (*kern)(int64_t, const double *, PtrPack, int, double *, unsigned int *, double *, double *) = vec2 ? mdot_kernel<NVT, UNR, true, SPLIT> : mdot_kernel<NVT, 1, false, SPLIT>;
   if (!occ[vec2]) {
     int o = 1;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, TPB, 0));
     occ[vec2] = o < 1 ? 1 : (o > 8 ? 8 : o);
   }
   int64_t work   = vec2 ? ((n >> 1) + UNR - 1) / UNR : n;
-  int64_t blocks = (work + TPB - 1) / TPB;
+  int64_t blocks = (work + TPB - 1) / TPB; /* virtual CTAs */
   int64_t cap    = (int64_t)h->num_sms * occ[vec2];
   if (cap > B200_RED_MAXGRID) cap = B200_RED_MAXGRID;
+  if (SPLIT) cap /= 2;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  kern<<<(int)blocks, TPB, 0, h->stream>>>(n, x, y, h->d_partials, h->d_counter, d_result, h_result);
+  kern<<<(int)(SPLIT ? 2 * blocks : blocks), TPB, 0, h->stream>>>(n, x, y, nv, h->d_partials, h->d_counter, d_result, h_result);
   B200_LAUNCHED(1);
   B200_KERNEL_CHECK();
   return 0;
@@ -281,13 +329,16 @@ static int mdot_dispatch(b200Handle h, int64_t n, int nv, const double *x, const
     y.p[j] = yp[j];
     vec2   = vec2 && aligned16(yp[j]);
   }
-  for (int j = nv; j < B200_MAX_NV; j++) y.p[j] = yp[0];
-  switch (nv) {
+  for (int j = nv; j < B200_MAX_NV; j++) y.p[j] = yp[0]; /* padding slots of the split layout read a valid vector */
+  switch (nv <= 16 ? nv : 100 + (nv + 1) / 2) {
 #define C_(N) \
-  case N: return mdot_launch_nv<N>(h, n, x, y, vec2, d_result, h_result);
+  case N: return mdot_launch_nv<N, false>(h, n, nv, x, y, vec2, d_result, h_result);
     C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14) C_(15) C_(16)
-    C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26) C_(27) C_(28) C_(29) C_(30) C_(31) C_(32)
 #undef C_
+#define S_(N) \
+  case 100 + N: return mdot_launch_nv<N, true>(h, n, nv, x, y, vec2, d_result, h_result);
+    S_(9) S_(10) S_(11) S_(12) S_(13) S_(14) S_(15) S_(16)
+#undef S_
   }
   B200_CHECK(0, B200_ERR_ARG_OUTOFRANGE, "nv=%d out of range", nv);
 }
@@ -433,28 +484,25 @@ extern "C" int b200VecMax(b200Handle h, int64_t n, const double *x, int64_t *idx
 extern "C" int b200VecMin(b200Handle h, int64_t n, const double *x, int64_t *idx, double *r) { return maxmin(h, n, x, idx, r, false); }
 
 /* ------------------------------------------------------------------ MAXPY (+ fused norm) */
-template <int NV>
-__device__ __forceinline__ double maxpy_elem(double xv, const double (&yv)[NV], const AlphaPack &al)
+/* VecMAXPY_Seq (dvec2.c:658-693, petscaxpy.h:125-150): the nv&3 remainder group first, then groups of 4; inside a group
+   the products are summed left to right and the group total is added to x.  No FMA contraction -> bit-identical.
+   The groups are walked two at a time by a real (not unrolled) loop: 8 x 128-bit loads in flight per thread and ~56
+   registers, i.e. 4 resident CTAs per SM for every nv (the fully unrolled form made ptxas allocate 102-128 registers
+   for nv >= 27 -> 2 CTAs/SM and 69% of peak, profiles/round1_notes.md). */
+template <int CNT>
+__device__ __forceinline__ double maxpy_group(const double *a, const double (&v)[CNT])
 {
-  /* VecMAXPY_Seq: remainder group of NV&3 vectors first, then groups of 4; within a group the products are summed left
-     to right and the group total is added to x (petscaxpy.h:125-150).  No FMA contraction. */
-  constexpr int g = NV & 3;
-  if (g == 1) xv = __dadd_rn(xv, __dmul_rn(al.a[0], yv[0]));
-  if (g == 2) xv = __dadd_rn(xv, __dadd_rn(__dmul_rn(al.a[0], yv[0]), __dmul_rn(al.a[1], yv[1])));
-  if (g == 3) xv = __dadd_rn(xv, __dadd_rn(__dadd_rn(__dmul_rn(al.a[0], yv[0]), __dmul_rn(al.a[1], yv[1])), __dmul_rn(al.a[2], yv[2])));
+  double t = __dmul_rn(a[0], v[0]);
 #pragma unroll
-  for (int j = g; j < NV; j += 4) {
-    double t = __dadd_rn(__dmul_rn(al.a[j], yv[j]), __dmul_rn(al.a[j + 1], yv[j + 1]));
-    t        = __dadd_rn(t, __dmul_rn(al.a[j + 2], yv[j + 2]));
-    t        = __dadd_rn(t, __dmul_rn(al.a[j + 3], yv[j + 3]));
-    xv       = __dadd_rn(xv, t);
-  }
-  return xv;
+  for (int k = 1; k < CNT; k++) t = __dadd_rn(t, __dmul_rn(a[k], v[k]));
+  return t;
 }
 
 template <int NV, bool NORM, bool VEC2>
-__global__ void __launch_bounds__(TPB) maxpy_kernel(int64_t n, double *x, PtrPack y, AlphaPack al, double *partials, unsigned int *counter, double *d_result, double *h_result)
+__global__ void __launch_bounds__(TPB, 4) maxpy_kernel(int64_t n, double *x, PtrPack y, AlphaPack al, double *partials, unsigned int *counter, double *d_result, double *h_result)
 {
+  constexpr int G0     = NV & 3;          /* remainder group size */
+  constexpr int NG     = (NV - G0) / 4;   /* groups of four */
   double        acc[1] = {0.0};
   const int64_t stride = (int64_t)gridDim.x * TPB;
   int64_t       i      = (int64_t)blockIdx.x * TPB + threadIdx.x;
@@ -463,36 +511,79 @@ __global__ void __launch_bounds__(TPB) maxpy_kernel(int64_t n, double *x, PtrPac
     double2      *x2   = reinterpret_cast<double2 *>(x);
     for (; i < nvec; i += stride) {
       double2 xv = x2[i];
-      double  y0[NV], y1[NV];
+      if (G0) {
+        double v0[G0 ? G0 : 1], v1[G0 ? G0 : 1];
 #pragma unroll
-      for (int j = 0; j < NV; j++) {
-        double2 t = __ldg(reinterpret_cast<const double2 *>(y.p[j]) + i);
-        y0[j]     = t.x;
-        y1[j]     = t.y;
+        for (int k = 0; k < G0; k++) {
+          double2 t = __ldg(reinterpret_cast<const double2 *>(y.p[k]) + i);
+          v0[k] = t.x; v1[k] = t.y;
+        }
+        xv.x = __dadd_rn(xv.x, maxpy_group<(G0 ? G0 : 1)>(al.a, v0));
+        xv.y = __dadd_rn(xv.y, maxpy_group<(G0 ? G0 : 1)>(al.a, v1));
       }
-      xv.x  = maxpy_elem<NV>(xv.x, y0, al);
-      xv.y  = maxpy_elem<NV>(xv.y, y1, al);
+      int j = G0;
+#pragma unroll 1
+      for (int p = 0; p < NG / 2; p++, j += 8) {
+        double v0[8], v1[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          double2 t = __ldg(reinterpret_cast<const double2 *>(y.p[j + k]) + i);
+          v0[k] = t.x; v1[k] = t.y;
+        }
+        double a8[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) a8[k] = al.a[j + k];
+        const double(&v0a)[4] = *reinterpret_cast<const double(*)[4]>(v0);
+        const double(&v0b)[4] = *reinterpret_cast<const double(*)[4]>(v0 + 4);
+        const double(&v1a)[4] = *reinterpret_cast<const double(*)[4]>(v1);
+        const double(&v1b)[4] = *reinterpret_cast<const double(*)[4]>(v1 + 4);
+        xv.x = __dadd_rn(xv.x, maxpy_group<4>(a8, v0a));
+        xv.y = __dadd_rn(xv.y, maxpy_group<4>(a8, v1a));
+        xv.x = __dadd_rn(xv.x, maxpy_group<4>(a8 + 4, v0b));
+        xv.y = __dadd_rn(xv.y, maxpy_group<4>(a8 + 4, v1b));
+      }
+      if (NG & 1) {
+        double v0[4], v1[4], a4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          double2 t = __ldg(reinterpret_cast<const double2 *>(y.p[NV - 4 + k]) + i);
+          v0[k] = t.x; v1[k] = t.y;
+          a4[k] = al.a[NV - 4 + k];
+        }
+        xv.x = __dadd_rn(xv.x, maxpy_group<4>(a4, v0));
+        xv.y = __dadd_rn(xv.y, maxpy_group<4>(a4, v1));
+      }
       x2[i] = xv;
       if (NORM) {
         acc[0] = fma(xv.x, xv.x, acc[0]);
         acc[0] = fma(xv.y, xv.y, acc[0]);
       }
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-      double y0[NV];
+  }
+  /* scalar path: odd tail of the vector path, or everything when some pointer is only 8-byte aligned */
+  {
+    int64_t s0 = VEC2 ? (n & ~(int64_t)1) : 0;
+    int64_t k0 = VEC2 ? ((blockIdx.x == 0 && threadIdx.x == 0) ? s0 : n) : (int64_t)blockIdx.x * TPB + threadIdx.x;
+    int64_t st = VEC2 ? 1 : stride;
+    for (int64_t e = k0; e < n; e += st) {
+      double xv = x[e];
+      if (G0) {
+        double v[G0 ? G0 : 1];
 #pragma unroll
-      for (int j = 0; j < NV; j++) y0[j] = y.p[j][n - 1];
-      double xv = maxpy_elem<NV>(x[n - 1], y0, al);
-      x[n - 1]  = xv;
-      if (NORM) acc[0] = fma(xv, xv, acc[0]);
-    }
-  } else {
-    for (; i < n; i += stride) {
-      double y0[NV];
+        for (int k = 0; k < G0; k++) v[k] = y.p[k][e];
+        xv = __dadd_rn(xv, maxpy_group<(G0 ? G0 : 1)>(al.a, v));
+      }
+#pragma unroll 1
+      for (int g = 0; g < NG; g++) {
+        double v[4], a4[4];
 #pragma unroll
-      for (int j = 0; j < NV; j++) y0[j] = y.p[j][i];
-      double xv = maxpy_elem<NV>(x[i], y0, al);
-      x[i]      = xv;
+        for (int k = 0; k < 4; k++) {
+          v[k]  = y.p[G0 + 4 * g + k][e];
+          a4[k] = al.a[G0 + 4 * g + k];
+        }
+        xv = __dadd_rn(xv, maxpy_group<4>(a4, v));
+      }
+      x[e] = xv;
       if (NORM) acc[0] = fma(xv, xv, acc[0]);
     }
   }

@@ -385,18 +385,17 @@ static PetscErrorCode MatSetCSR_SeqAIJB200(Mat A, const PetscInt *ai, const Pets
     nz = last;
   } else {
     nz = m ? ai[m] : 0;
-    for (PetscInt r = 0; r < m; r++) { /* MatAssemblyEnd_SeqAIJ invariants: sorted, in-range columns */
-      for (PetscInt k = ai[r]; k < ai[r + 1]; k++) {
-        PetscCheck(aj[k] >= 0 && aj[k] < A->n, A->hdr.comm, PETSC_ERR_ARG_OUTOFRANGE, "Column %d out of range [0,%d) in row %d", aj[k], A->n, r);
-        PetscCheck(k == ai[r] || aj[k] > aj[k - 1], A->hdr.comm, PETSC_ERR_ARG_WRONG, "Row %d: column indices must be strictly increasing", r);
-      }
-    }
   }
   a->nz = nz;
-  PetscCallB200(b200Malloc(H, (void **)&a->d_i, sizeof(int) * ((size_t)m + 1)));
-  PetscCallB200(b200Malloc(H, (void **)&a->d_j, sizeof(int) * (size_t)(nz + 1)));
-  PetscCallB200(b200Malloc(H, (void **)&a->d_a, sizeof(double) * (size_t)(nz + 1)));
-  if (on_device) {
+  if (on_device == 2) { /* adopt: the arrays were allocated with b200Malloc by the caller and now belong to the matrix */
+    a->d_i = (int *)ai; a->d_j = (int *)aj; a->d_a = (double *)aa;
+  } else {
+    PetscCallB200(b200Malloc(H, (void **)&a->d_i, sizeof(int) * ((size_t)m + 1)));
+    PetscCallB200(b200Malloc(H, (void **)&a->d_j, sizeof(int) * (size_t)(nz + 1)));
+    PetscCallB200(b200Malloc(H, (void **)&a->d_a, sizeof(double) * (size_t)(nz + 1)));
+  }
+  if (on_device == 2) {
+  } else if (on_device) {
     PetscCallB200(b200MemcpyDtoD(H, a->d_i, ai, sizeof(int) * ((size_t)m + 1)));
     PetscCallB200(b200MemcpyDtoD(H, a->d_j, aj, sizeof(int) * (size_t)nz));
     PetscCallB200(b200MemcpyDtoD(H, a->d_a, aa, sizeof(double) * (size_t)nz));
@@ -407,6 +406,13 @@ static PetscErrorCode MatSetCSR_SeqAIJB200(Mat A, const PetscInt *ai, const Pets
     } else PetscCallB200(b200MemcpyHtoD(H, a->d_i, ai, sizeof(int) * ((size_t)m + 1)));
     PetscCallB200(b200MemcpyHtoD(H, a->d_j, aj, sizeof(int) * (size_t)nz));
     PetscCallB200(b200MemcpyHtoD(H, a->d_a, aa, sizeof(double) * (size_t)nz));
+  }
+  { /* MatAssemblyEnd_SeqAIJ invariants (sorted, in-range columns), checked where the data now lives */
+    int bad = -1, kind = 0;
+    PetscCallB200(b200CsrValidate(H, m, A->n, a->d_i, a->d_j, &bad, &kind));
+    PetscCheck(kind != 1, A->hdr.comm, PETSC_ERR_ARG_OUTOFRANGE, "Column out of range [0,%d) in row %d", A->n, bad);
+    PetscCheck(kind != 2, A->hdr.comm, PETSC_ERR_ARG_WRONG, "Row %d: column indices must be strictly increasing", bad);
+    PetscCheck(kind != 3, A->hdr.comm, PETSC_ERR_ARG_WRONG, "Row %d: row pointer is decreasing", bad);
   }
   PetscCallB200(b200CsrPlanCreate(H, m, A->n, nz, a->d_i, a->d_j, &a->plan));
   if (A->spmv_layout[0] || A->spmv_layout[1] || A->spmv_layout[2] || A->spmv_layout[3]) PetscCallB200(b200CsrPlanSetLayout(a->plan, A->spmv_layout[0], A->spmv_layout[1], A->spmv_layout[2], A->spmv_layout[3]));
@@ -675,26 +681,63 @@ static PetscErrorCode MatSetUpMultiply_MPIAIJB200(Mat mat)
 static PetscErrorCode MatSetCSR_MPIAIJB200(Mat mat, const PetscInt *ai, const PetscInt *aj, const PetscScalar *aa, int on_device)
 {
   Mat_MPIAIJB200 *a = (Mat_MPIAIJB200 *)mat->data;
-  PetscInt       *hi = NULL, *hj = NULL;
-  PetscScalar    *ha = NULL;
   PetscInt        m  = mat->m;
-  if (on_device) { /* device-resident input: staged through the host for the split (setup time only) */
-    int nz = 0;
-    hi     = (PetscInt *)malloc(sizeof(PetscInt) * ((size_t)m + 1));
-    PetscCallB200(b200MemcpyDtoH(H, hi, ai, sizeof(PetscInt) * ((size_t)m + 1)));
-    nz = hi[m];
-    hj = (PetscInt *)malloc(sizeof(PetscInt) * ((size_t)nz + 1));
-    ha = (PetscScalar *)malloc(sizeof(PetscScalar) * ((size_t)nz + 1));
-    PetscCallB200(b200MemcpyDtoH(H, hj, aj, sizeof(PetscInt) * (size_t)nz));
-    PetscCallB200(b200MemcpyDtoH(H, ha, aa, sizeof(PetscScalar) * (size_t)nz));
-    ai = hi; aj = hj; aa = ha;
+  if (on_device) {
+    /* device-resident input: the column split runs on the device (b200CsrSplitColumns); only the small off-diagonal
+       block visits the host, where garray is built exactly as mmaij.c:25-61 does */
+    int    *dAi, *dAj, *dBi, *dBj;
+    double *dAa, *dBa;
+    int64_t nzA, nzB;
+    PetscCallB200(b200CsrSplitColumns(H, m, ai, aj, aa, mat->cstart, mat->cend, &dAi, &dAj, &dAa, &nzA, &dBi, &dBj, &dBa, &nzB));
+    PetscInt    *hBi = (PetscInt *)malloc(sizeof(PetscInt) * ((size_t)m + 1)), *hBj = (PetscInt *)malloc(sizeof(PetscInt) * ((size_t)nzB + 1));
+    PetscScalar *hBa = (PetscScalar *)malloc(sizeof(PetscScalar) * ((size_t)nzB + 1));
+    PetscCallB200(b200MemcpyDtoH(H, hBi, dBi, sizeof(PetscInt) * ((size_t)m + 1)));
+    PetscCallB200(b200MemcpyDtoH(H, hBj, dBj, sizeof(PetscInt) * (size_t)nzB));
+    PetscCallB200(b200MemcpyDtoH(H, hBa, dBa, sizeof(PetscScalar) * (size_t)nzB));
+    PetscCallB200(b200Free(H, dBi)); PetscCallB200(b200Free(H, dBj)); PetscCallB200(b200Free(H, dBa));
+    PetscInt *g = (PetscInt *)malloc(sizeof(PetscInt) * ((size_t)nzB + 1)), ec = 0;
+    memcpy(g, hBj, sizeof(PetscInt) * (size_t)nzB);
+    if (nzB) {
+      qsort(g, (size_t)nzB, sizeof(PetscInt), cmp_int);
+      ec = 1;
+      for (int64_t k = 1; k < nzB; k++)
+        if (g[k] != g[ec - 1]) g[ec++] = g[k];
+    }
+    for (int64_t k = 0; k < nzB; k++) { /* mmaij.c:55-61 */
+      PetscInt c = hBj[k], lo = 0, hi2 = ec - 1;
+      PetscCheck(c >= 0 && c < mat->N, mat->hdr.comm, PETSC_ERR_ARG_OUTOFRANGE, "Column %d out of range", c);
+      while (lo < hi2) {
+        PetscInt mid = (lo + hi2) / 2;
+        if (g[mid] < c) lo = mid + 1;
+        else hi2 = mid;
+      }
+      hBj[k] = lo;
+    }
+    free(a->garray);
+    a->garray = g;
+    a->ec     = ec;
+    PetscCall(MatDestroy(&a->A));
+    PetscCall(MatDestroy(&a->B));
+    PetscCall(MatCreate(PETSC_COMM_SELF, &a->A));
+    PetscCall(MatSetSizes(a->A, m, mat->n, m, mat->n));
+    PetscCall(MatSetType(a->A, MATSEQAIJB200));
+    for (int i = 0; i < 4; i++) a->A->spmv_layout[i] = mat->spmv_layout[i];
+    PetscCall(MatSetUp(a->A));
+    PetscCall((*a->A->ops.setcsr)(a->A, dAi, dAj, dAa, 2)); /* adopts the device arrays */
+    a->A->assembled = 1;
+    PetscCall(MatCreate(PETSC_COMM_SELF, &a->B));
+    PetscCall(MatSetSizes(a->B, m, ec, m, ec));
+    PetscCall(MatSetType(a->B, MATSEQAIJB200));
+    PetscCall(MatSeqAIJSetPreallocationCSR(a->B, hBi, hBj, hBa));
+    free(hBi); free(hBj); free(hBa);
+    PetscCall(MatSetUpMultiply_MPIAIJB200(mat));
+    return PETSC_SUCCESS;
   }
   PetscInt    *Ai, *Aj, *Bi, *Bj, *g, ec;
   PetscScalar *Aa, *Ba;
   for (PetscInt r = 0; r < m; r++)
     for (PetscInt k = ai[r]; k < ai[r + 1]; k++) PetscCheck(aj[k] >= 0 && aj[k] < mat->N, mat->hdr.comm, PETSC_ERR_ARG_OUTOFRANGE, "Column %d out of range in local row %d", aj[k], r);
   PetscCall(PetscB200MPIAIJSplit(m, mat->cstart, mat->cend, ai, aj, aa, &Ai, &Aj, &Aa, &Bi, &Bj, &Ba, &g, &ec));
-  free(hi); free(hj); free(ha);
   free(a->garray);
   a->garray = g;
   a->ec     = ec;

@@ -46,6 +46,7 @@ struct b200CsrPlan_s {
   int        num_sms;
   int        user_lanes, user_rows, user_stages, user_ctas;
   int        max_tile_nnz[16]; /* for R = 8 << k */
+  int        hints;            /* bit0: CSR streams evict_first, bit1: x evict_last */
 };
 
 /* ------------------------------------------------------------------ PTX helpers: mbarrier + 1-D TMA bulk copy */
@@ -72,6 +73,32 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
                : "memory");
 }
 
+/* L2 eviction-priority hints: the CSR streams (val/col/rowptr) are read exactly once -> evict_first; x is the only
+   operand with reuse (every entry is gathered ~nnz/row times within a window of a few grid planes) -> evict_last. */
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar, uint64_t pol)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ double ldg_hint(const double *p, uint64_t pol)
+{
+  double v;
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 /* ------------------------------------------------------------------ shared-memory stage layout */
 struct StageLayout {
   int rp_off, col_off, val_off, stage_bytes;
@@ -87,7 +114,7 @@ __host__ __device__ inline StageLayout stage_layout(int R, int cap)
 }
 
 /* ------------------------------------------------------------------ the kernel */
-template <int G>
+template <int G, int HINTS>
 __global__ void __launch_bounds__(SPMV_TPB) csr_spmv_tile_kernel(int m, int R, int cap, int S, const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ val, const double *__restrict__ x, const double *yin, const double *__restrict__ dinv, double *yout, double *yplain)
 {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -95,6 +122,13 @@ __global__ void __launch_bounds__(SPMV_TPB) csr_spmv_tile_kernel(int m, int R, i
   const StageLayout                             L      = stage_layout(R, cap);
   const int                                     ntiles = (m + R - 1) / R;
   const int                                     tid    = threadIdx.x;
+  const uint64_t pol_stream = (HINTS & 1) ? policy_evict_first() : 0;
+  const uint64_t pol_x      = (HINTS & 2) ? policy_evict_last() : 0;
+  auto tma = [&](void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    if (HINTS & 1) tma_load_1d_hint(dst, src, bytes, bar, pol_stream);
+    else tma_load_1d(dst, src, bytes, bar);
+  };
+  auto ldx = [&](const double *p) -> double { return (HINTS & 2) ? ldg_hint(p, pol_x) : __ldg(p); };
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) mbar_init(&full_bar[s], 1);
@@ -110,7 +144,7 @@ __global__ void __launch_bounds__(SPMV_TPB) csr_spmv_tile_kernel(int m, int R, i
     const uint32_t rpcnt = (uint32_t)((rows + 1 + 3) & ~3);
     if (k1 - k0 > cap) { /* fallback tile: only the row pointers are staged, the rows stream from global memory */
       mbar_expect_tx(&full_bar[s], rpcnt * 4u);
-      tma_load_1d(st + L.rp_off, rowptr + r0, rpcnt * 4u, &full_bar[s]);
+      tma(st + L.rp_off, rowptr + r0, rpcnt * 4u, &full_bar[s]);
       return;
     }
     const int      k0a   = k0 & ~3;                            /* 16-byte alignment for both arrays */
@@ -118,10 +152,10 @@ __global__ void __launch_bounds__(SPMV_TPB) csr_spmv_tile_kernel(int m, int R, i
     const uint32_t cnt   = (uint32_t)(kend - k0a);
     const uint32_t bytes = cnt * 12u + rpcnt * 4u;
     mbar_expect_tx(&full_bar[s], bytes);
-    tma_load_1d(st + L.rp_off, rowptr + r0, rpcnt * 4u, &full_bar[s]);
+    tma(st + L.rp_off, rowptr + r0, rpcnt * 4u, &full_bar[s]);
     if (cnt) {
-      tma_load_1d(st + L.col_off, colidx + k0a, cnt * 4u, &full_bar[s]);
-      tma_load_1d(st + L.val_off, val + k0a, cnt * 8u, &full_bar[s]);
+      tma(st + L.col_off, colidx + k0a, cnt * 4u, &full_bar[s]);
+      tma(st + L.val_off, val + k0a, cnt * 8u, &full_bar[s]);
     }
   };
 
@@ -175,14 +209,14 @@ __global__ void __launch_bounds__(SPMV_TPB) csr_spmv_tile_kernel(int m, int R, i
         /* parity mode: strict left-to-right, FMA-free (aij.h:609-614) */
         sum = (act && yin) ? yin[r] : 0.0;
         if (staged) {
-          for (int k = ks - k0a; k < ke - k0a; k++) sum = __dadd_rn(sum, __dmul_rn(vs[k], __ldg(x + cs[k])));
+          for (int k = ks - k0a; k < ke - k0a; k++) sum = __dadd_rn(sum, __dmul_rn(vs[k], ldx(x + cs[k])));
         } else {
           for (int k = ks; k < ke; k++) sum = __dadd_rn(sum, __dmul_rn(__ldg(val + k), __ldg(x + __ldg(colidx + k))));
         }
       } else {
         sum = 0.0;
         if (staged) {
-          for (int k = ks - k0a + gl; k < ke - k0a; k += G) sum = fma(vs[k], __ldg(x + cs[k]), sum);
+          for (int k = ks - k0a + gl; k < ke - k0a; k += G) sum = fma(vs[k], ldx(x + cs[k]), sum);
         } else {
           for (int k = ks + gl; k < ke; k += G) sum = fma(__ldg(val + k), __ldg(x + __ldg(colidx + k)), sum);
         }
@@ -285,8 +319,8 @@ static int plan_configure(b200CsrPlan p)
 {
   double avg = p->m ? (double)p->nnz / p->m : 0.0;
   int    G   = p->user_lanes ? p->user_lanes : pick_lanes(avg);
-  int    S   = p->user_stages ? p->user_stages : 2;
-  int    cps = p->user_ctas ? p->user_ctas : 4; /* measured on B200 (profiles/): 4 resident CTAs x 2 stages beats 2 x 2 by 27% */
+  int    S   = p->user_stages ? p->user_stages : 1;
+  int    cps = p->user_ctas ? p->user_ctas : 8; /* measured on B200 (profiles/round1_notes.md): 8 resident single-stage CTAs (1.95 ms) beat 6 (2.02), 4 x 2 stages (2.17) and 2 x 2 (2.79 ms): occupancy hides the TMA latency better than a deeper ring */
   if (S > SPMV_MAX_STAGES) S = SPMV_MAX_STAGES;
   /* shared-memory budget per CTA: 227 KB per SM, 1 KB reserved per resident CTA, static smem for the barriers */
   const int budget = (227 * 1024) / cps - 1024 - 256;
@@ -337,6 +371,7 @@ extern "C" int b200CsrPlanCreate(b200Handle h, int m, int n, int64_t nnz, const 
   b200CsrPlan p = (b200CsrPlan)calloc(1, sizeof(*p));
   B200_CHECK(p, B200_ERR_MEM, "out of host memory");
   p->m = m; p->n = n; p->nnz = nnz; p->d_rowptr = d_rowptr; p->d_colidx = d_colidx; p->num_sms = h->num_sms;
+  p->hints = 2; /* x evict_last only: best of the four combinations on the 512^3 7-point operator */
   if (m > 0) {
     int *d_stats;
     int  hstats[17];
@@ -374,6 +409,14 @@ extern "C" int b200CsrPlanSetLayout(b200CsrPlan p, int lanes, int rows_per_tile,
   return plan_configure(p);
 }
 
+extern "C" int b200CsrPlanSetCacheHints(b200CsrPlan p, int hints)
+{
+  B200_CHECK(p, B200_ERR_ARG_NULL, "null plan");
+  B200_CHECK(hints >= 0 && hints <= 3, B200_ERR_ARG_OUTOFRANGE, "hints must be 0..3");
+  p->hints = hints;
+  return 0;
+}
+
 extern "C" int b200CsrPlanGetLayout(b200CsrPlan p, int *lanes, int *rows, int *stages, int *grid, int *smem, int *maxrow)
 {
   B200_CHECK(p, B200_ERR_ARG_NULL, "null plan");
@@ -386,18 +429,28 @@ extern "C" int b200CsrPlanGetLayout(b200CsrPlan p, int *lanes, int *rows, int *s
   return 0;
 }
 
-template <int G>
-static int spmv_launch_g(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
+template <int G, int HINTS>
+static int spmv_launch_gh(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
 {
   static int configured = 0;
-  if (configured < p->smem) {
-    B200_CUDA(cudaFuncSetAttribute(csr_spmv_tile_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-    configured = 227 * 1024;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(csr_spmv_tile_kernel<G, HINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    configured = 1;
   }
-  csr_spmv_tile_kernel<G><<<p->grid, SPMV_TPB, p->smem, h->stream>>>(p->m, p->rows_tile, p->cap, p->stages, p->d_rowptr, p->d_colidx, val, x, yin, dinv, yout, yplain);
+  csr_spmv_tile_kernel<G, HINTS><<<p->grid, SPMV_TPB, p->smem, h->stream>>>(p->m, p->rows_tile, p->cap, p->stages, p->d_rowptr, p->d_colidx, val, x, yin, dinv, yout, yplain);
   B200_LAUNCHED(1);
   B200_KERNEL_CHECK();
   return 0;
+}
+template <int G>
+static int spmv_launch_g(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
+{
+  switch (p->hints & 3) {
+  case 0: return spmv_launch_gh<G, 0>(h, p, val, x, yin, dinv, yout, yplain);
+  case 1: return spmv_launch_gh<G, 1>(h, p, val, x, yin, dinv, yout, yplain);
+  case 2: return spmv_launch_gh<G, 2>(h, p, val, x, yin, dinv, yout, yplain);
+  default: return spmv_launch_gh<G, 3>(h, p, val, x, yin, dinv, yout, yplain);
+  }
 }
 
 static int spmv_launch(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
@@ -573,5 +626,50 @@ extern "C" int b200CsrCountNonemptyRows(b200Handle h, int m, const int *d_rowptr
   B200_CUDA(cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
   *count_host = *h->h_flag;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ CSR validation (MatAssemblyEnd_SeqAIJ invariants) */
+__global__ void csr_validate_kernel(int m, int n, const int *__restrict__ rowptr, const int *__restrict__ colidx, int *bad /* [2]: row+1 (min), kind */)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
+    int k0 = rowptr[r], k1 = rowptr[r + 1], kind = 0;
+    if (k1 < k0) kind = 3;
+    for (int k = k0; k < k1 && !kind; k++) {
+      int c = colidx[k];
+      if (c < 0 || c >= n) kind = 1;
+      else if (k > k0 && c <= colidx[k - 1]) kind = 2;
+    }
+    if (kind) {
+      int old = atomicCAS(&bad[0], 0, (int)r + 1);
+      if (old == 0 || (int)r + 1 < old) {
+        atomicMin(&bad[0], (int)r + 1);
+        bad[1] = kind;
+      }
+    }
+  }
+}
+
+/* *bad_row = -1 when the CSR is valid; otherwise a row that violates (kind 1: column out of range, 2: columns not
+   strictly increasing, 3: row pointer decreasing) */
+extern "C" int b200CsrValidate(b200Handle h, int m, int n, const int *d_rowptr, const int *d_colidx, int *bad_row, int *kind)
+{
+  B200_CHECK(h && bad_row && kind, B200_ERR_ARG_NULL, "null argument");
+  *bad_row = -1;
+  *kind    = 0;
+  if (m <= 0) return 0;
+  B200_CUDA(cudaMemsetAsync(h->d_flag, 0, 2 * sizeof(int), h->stream));
+  int64_t g = ((int64_t)m + 255) / 256;
+  if (g > h->num_sms * 8) g = h->num_sms * 8;
+  csr_validate_kernel<<<(int)g, 256, 0, h->stream>>>(m, n, d_rowptr, d_colidx, h->d_flag);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  B200_CUDA(cudaMemcpyAsync(h->h_flag, h->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->h_flag[0]) {
+    *bad_row = h->h_flag[0] - 1;
+    *kind    = h->h_flag[1];
+  }
   return 0;
 }

@@ -57,24 +57,26 @@ def main():
         bytes_alg = nnz * 12 + N * 20
         flops = 2 * nnz - N
         res["spmv"] = []
-        layouts = [(0, 0, 0, 0)]
+        layouts = [(0, 0, 0, 0, 3)]
         if a.layouts == "sweep":
-            layouts += [(1, r, s, c) for r in (128, 256, 512, 1024) for s in (2, 3, 4) for c in (1, 2, 3, 4)]
-        for (lanes, rows, stages, ctas) in layouts:
+            layouts += [(1, r, s, c, hh) for hh in (2,) for (r, s, c) in ((256, 1, 6), (256, 1, 7), (256, 1, 8), (128, 1, 8), (512, 1, 4), (512, 1, 3), (128, 2, 8), (256, 2, 4), (64, 1, 8))]
+        for (lanes, rows, stages, ctas, hh) in layouts:
             try:
                 H.csr_plan_set_layout(plan, lanes, rows, stages, ctas)
+                H.csr_plan_set_hints(plan, hh)
                 lay = H.csr_plan_layout(plan)
                 if lay["smem"] > 226 * 1024 // max(1, 1):
                     continue
                 med, best = timeit(H, lambda: H.spmv(plan, d_aa, d_x, d_y))
             except _capi.B200Error as e:
-                print("layout", lanes, rows, stages, ctas, "failed:", e)
+                print("layout", lanes, rows, stages, ctas, hh, "failed:", e)
                 continue
-            r = dict(layout=lay, req=[lanes, rows, stages, ctas], ms=med, ms_best=best, gbs=bytes_alg / med / 1e6, gflops=flops / med / 1e6,
+            r = dict(layout=lay, req=[lanes, rows, stages, ctas, hh], ms=med, ms_best=best, gbs=bytes_alg / med / 1e6, gflops=flops / med / 1e6,
                      frac_measured=bytes_alg / med / 1e6 / peak)
             res["spmv"].append(r)
             print("spmv", r)
         H.csr_plan_set_layout(plan, 0, 0, 0, 0)
+        H.csr_plan_set_hints(plan, 3)
         med, best = timeit(H, lambda: H.spmv_jacobi(plan, d_aa, d_x, d_dinv, d_y))
         res["spmv_jacobi"] = dict(ms=med, gbs=(bytes_alg + 8 * N) / med / 1e6)
         print("spmv_jacobi", res["spmv_jacobi"])
@@ -101,7 +103,7 @@ def main():
         rec("pmult", lambda: _capi.check(L.b200VecPointwiseMult(H.h, C.c_int64(N), x.ptr, y.ptr, vecs[0].ptr)), 24 * N)
         rec("norm2", lambda: H.norm2(N, x), 8 * N)
         rec("dot", lambda: H.dot(N, x, y), 16 * N)
-        for nv in (1, 2, 4, 8, 15, 16, 30):
+        for nv in (range(1, 31) if a.layouts == 'sweep' else (1, 2, 4, 8, 15, 16, 17, 24, 30)):
             rec("mdot%d" % nv, lambda nv=nv: H.mdot(N, x, vecs[:nv]), 8 * N * (nv + 1))
             al = [1e-12] * nv
             rec("maxpy%d" % nv, lambda nv=nv, al=al: H.maxpy(N, al, vecs[:nv], y), 8 * N * (nv + 2))
