@@ -306,7 +306,7 @@ def cpu_baseline(a, quick=False, steps=1, warmup=0):
     (the path is bandwidth bound, cost is linear in the number of rows)."""
     from oracle import oracle_py as O
     ns = a.cpu_n
-    ai, aj, aa = O.lap7(ns)
+    ai, aj, aa = O.lap7(ns, omp=True)                # filled by all threads: NUMA first touch
     N = ns ** 3
     b = O.matmult(ai, aj, aa, np.ones(N), omp=True)
     thr = O.max_threads()

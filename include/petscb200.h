@@ -88,7 +88,7 @@ int b200CsrPlanDestroy(b200CsrPlan plan);
 /* tuning / introspection: lanes_per_row in {0=auto,1,2,4,8,16,32}; lanes_per_row == 1 reproduces MatMult_SeqAIJ's
    strict left-to-right, FMA-free row sums bit for bit.  rows_per_tile 0 = auto. */
 int b200CsrPlanSetLayout(b200CsrPlan plan, int lanes_per_row, int rows_per_tile, int stages, int ctas_per_sm);
-/* L2 eviction hints: bit0 = stream val/col/rowptr as evict_first, bit1 = keep x as evict_last (default 3) */
+/* L2 eviction hints: bit0 = stream val/col/rowptr as evict_first, bit1 = keep x as evict_last (default 2) */
 int b200CsrPlanSetCacheHints(b200CsrPlan plan, int hints);
 int b200CsrPlanGetLayout(b200CsrPlan plan, int *lanes_per_row, int *rows_per_tile, int *stages, int *grid, int *smem_bytes, int *max_row_nnz);
 /* y = A x                                             (MatMult_SeqAIJ, aij.c:1444-1499) */
@@ -191,6 +191,11 @@ int b200HaloEnd(b200Handle h, b200Halo halo);
 /* rows [r0,r1) of the 7-point nx*ny*nz Laplacian, local row pointer, GLOBAL 32-bit columns */
 int b200GenLaplace7(b200Handle h, int nx, int ny, int nz, int64_t r0, int64_t r1, int *d_rowptr, int *d_colidx, double *d_val);
 int b200GenLaplace7Nnz(int nx, int ny, int nz, int64_t r0, int64_t r1, int64_t *nnz);
+/* the 27-point n^3 operator of bench_kspsolve.c:115-303; d_rowptr[n^3+1] */
+int b200GenLaplace27(b200Handle h, int n, int *d_rowptr, int *d_colidx, double *d_val);
+int b200GenLaplace27Nnz(int n, int64_t *nnz);
+/* random CSR, fixed row length d, sorted distinct stratified columns, values in (-1,1)   (BASELINE config 5) */
+int b200GenRandomCsr(b200Handle h, int n, int ncols, int d, uint64_t seed, int *d_rowptr, int *d_colidx, double *d_val);
 
 #ifdef __cplusplus
 }

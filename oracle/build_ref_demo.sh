@@ -1,0 +1,24 @@
+#!/bin/bash
+# Builds the reference-side demo artefacts into oracle/_ref/ (git-ignored; they travel to the GPU box with gpurun):
+#   oracle/_ref/petsc/lib/libpetsc.so*     the reference library as configured by the survey stage from an UNMODIFIED copy of
+#                                          /root/reference (CPU-only, MPIUNI, -O2) -- copied, not rebuilt
+#   oracle/_ref/petsc/bin/ex2              the reference's own tutorial programs, compiled from the sources where they lie
+#   oracle/_ref/petsc/bin/bench_kspsolve   under /root/reference/src/ksp/ksp/tutorials/ (never copied into the repo)
+#   oracle/_ref/ref_driver                 oracle/ref_driver.c (our driver against the reference's public API)
+#   petsc_plugin/libpetscb200plugin.so     the plugin, built against exactly this PETSc
+# Only runs in the build container (needs /root/reference and the configured PETSc build).  No reference SOURCE is copied.
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"; ROOT="$(dirname "$HERE")"
+PETSC_DIR="${PETSC_DIR:-/tmp/petsc-probe}"; PETSC_ARCH="${PETSC_ARCH:-arch-probe}"; REF=/root/reference
+BLASDIR=/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs
+[ -d "$PETSC_DIR/$PETSC_ARCH/lib" ] || { echo "no configured PETSc at $PETSC_DIR/$PETSC_ARCH: skipping the reference demo build"; exit 0; }
+OUT="$HERE/_ref/petsc"; mkdir -p "$OUT/lib" "$OUT/bin"
+cp -aL "$PETSC_DIR/$PETSC_ARCH/lib/libpetsc.so.3.025" "$OUT/lib/"; ln -sf libpetsc.so.3.025 "$OUT/lib/libpetsc.so"
+INC="-I$PETSC_DIR/include -I$PETSC_DIR/$PETSC_ARCH/include"
+LNK="-L$OUT/lib -lpetsc -Wl,-rpath,\$ORIGIN/../lib -Wl,-rpath,$BLASDIR -Wl,-rpath-link,$BLASDIR -Wl,--allow-shlib-undefined -lm"
+for ex in ex2 bench_kspsolve; do
+  /usr/bin/gcc -O2 -o "$OUT/bin/$ex" "$REF/src/ksp/ksp/tutorials/$ex.c" $INC $LNK
+done
+/usr/bin/gcc -O2 -o "$HERE/_ref/ref_driver" "$HERE/ref_driver.c" $INC -L$OUT/lib -lpetsc -Wl,-rpath,\$ORIGIN/petsc/lib -Wl,-rpath,$BLASDIR -Wl,-rpath-link,$BLASDIR -Wl,--allow-shlib-undefined -lm
+make -s -C "$ROOT/petsc_plugin" PETSC_DIR="$PETSC_DIR" PETSC_ARCH="$PETSC_ARCH"
+echo "reference demo built in $OUT"

@@ -90,6 +90,39 @@ void ora_lap7(int nx, int ny, int nz, int *ai, int *aj, double *aa)
   ora_lap7_rows(nx, ny, nz, 0, (int64_t)nx * ny * nz, ai, aj, aa);
 }
 
+/* Same operator, filled by all threads (first-touch places each thread's rows on its own NUMA node: only the CPU
+   baseline timing uses this; the content is identical to ora_lap7) */
+void ora_lap7_omp(int nx, int ny, int nz, int *ai, int *aj, double *aa)
+{
+  const int64_t N = (int64_t)nx * ny * nz;
+#ifdef _OPENMP
+  const int nt = omp_get_max_threads();
+#else
+  const int nt = 1;
+#endif
+  int64_t *start = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nt + 1));
+  start[0]       = 0;
+  for (int t = 0; t < nt; t++) start[t + 1] = start[t] + ora_lap7_rows_nnz(nx, ny, nz, N * t / nt, N * (t + 1) / nt);
+  ai[0] = 0;
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+  for (int t = 0; t < nt; t++) { /* thread t writes ai[r0+1 .. r1] and its own slice of aj/aa: no overlap */
+    const int64_t r0 = N * t / nt, r1 = N * (t + 1) / nt, nxy = (int64_t)nx * ny;
+    int64_t       k = start[t];
+    for (int64_t r = r0; r < r1; r++) {
+      int x = (int)(r % nx), y = (int)((r / nx) % ny), z = (int)(r / nxy);
+      if (z > 0) { aj[k] = (int)(r - nxy); aa[k++] = -1.0; }
+      if (y > 0) { aj[k] = (int)(r - nx); aa[k++] = -1.0; }
+      if (x > 0) { aj[k] = (int)(r - 1); aa[k++] = -1.0; }
+      aj[k] = (int)r; aa[k++] = 6.0;
+      if (x < nx - 1) { aj[k] = (int)(r + 1); aa[k++] = -1.0; }
+      if (y < ny - 1) { aj[k] = (int)(r + nx); aa[k++] = -1.0; }
+      if (z < nz - 1) { aj[k] = (int)(r + nxy); aa[k++] = -1.0; }
+      ai[r + 1] = (int)k;
+    }
+  }
+  free(start);
+}
+
 int64_t ora_lap27_nnz(int n)
 {
   /* sum over rows of prod_d (1 + (c_d>0) + (c_d<n-1)) = (3n-2)^3 */
@@ -207,6 +240,16 @@ void ora_vecpointwisemult(int64_t n, const double *x, const double *y, double *w
 {
   OMP_FOR
   for (int64_t i = 0; i < n; i++) w[i] = x[i] * y[i];
+}
+static void vcopy(int64_t n, const double *x, double *y)
+{
+  OMP_FOR
+  for (int64_t i = 0; i < n; i++) y[i] = x[i];
+}
+static void vzero(int64_t n, double *x)
+{
+  OMP_FOR
+  for (int64_t i = 0; i < n; i++) x[i] = 0.0;
 }
 void ora_vecreciprocal(int64_t n, double *x)
 {
@@ -582,18 +625,18 @@ int ora_ksp_gmres(int n, const int *ai, const int *aj, const double *aa, const d
   conv_ctx cv = {0, 0, o->rtol, o->abstol, o->dtol};
   int      its = 0, reason = 0, nh = 0, guess_zero = 1, itcount = 0;
   double   rnorm = -1.0;
-  memset(x, 0, sizeof(double) * (size_t)n);
+  vzero(n, x);
 
 #define LOGRES(r) do { if (hist && nh < histcap) hist[nh] = (r); nh++; } while (0)
   while (!reason) {
     /* KSPInitialResidual, itres.c:35-73, left PC */
     if (!guess_zero) {
       k_matmult(&pc, x, temp);
-      memcpy(tmat, b, sizeof(double) * (size_t)n);
+      vcopy(n, b, tmat);
       ora_vecaxpy(n, -1.0, temp, tmat);
       pc_apply(&pc, tmat, vv[0]);
     } else {
-      memcpy(tmat, b, sizeof(double) * (size_t)n);
+      vcopy(n, b, tmat);
       pc_apply(&pc, b, vv[0]);
     }
     /* KSPGMRESCycle, gmres.c:88-193 */
@@ -678,7 +721,7 @@ int ora_ksp_gmres(int n, const int *ai, const int *aj, const double *aa, const d
           if (*HH(kk, kk) == 0.0) { reason = -5; break; }
           nrs[kk] = t3 / *HH(kk, kk);
         }
-        memset(temp, 0, sizeof(double) * (size_t)n);
+        vzero(n, temp);
         ora_vecmaxpy(n, it, nrs, (const double *const *)vv, temp);
         ora_vecaxpy(n, 1.0, temp, x);
       } else reason = -5;

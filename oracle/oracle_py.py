@@ -71,13 +71,13 @@ def lap5(m, n):
     return ai, aj, aa
 
 
-def lap7(nx, ny=None, nz=None):
+def lap7(nx, ny=None, nz=None, omp=False):
     ny = nx if ny is None else ny
     nz = nx if nz is None else nz
     L = lib()
     nnz = L.ora_lap7_nnz(nx, ny, nz)
     ai = np.empty(nx * ny * nz + 1, np.int32); aj = np.empty(nnz, np.int32); aa = np.empty(nnz, np.float64)
-    L.ora_lap7(nx, ny, nz, _p(ai), _p(aj), _p(aa))
+    (L.ora_lap7_omp if omp else L.ora_lap7)(nx, ny, nz, _p(ai), _p(aj), _p(aa))
     return ai, aj, aa
 
 

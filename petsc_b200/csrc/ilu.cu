@@ -33,7 +33,8 @@ struct b200IluPlan_s {
   double *d_ba;
   int    *d_orderL, *d_orderU;       /* rows in level order, -1 padded to warp multiples */
   int     nslotL, nslotU;
-  int    *d_flag;                    /* per-row ready epoch */
+  int    *d_flag;                    /* per-row ready epoch (numeric factorisation) */
+  double *d_tmp;                     /* result of the lower sweep */
   int    *d_ticket;                  /* [4] tickets + status */
   int     epoch;
   int     nlevL, nlevU;
@@ -53,7 +54,7 @@ __device__ __forceinline__ int ld_acquire(const int *p)
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void wait_ready(const int *flag, int row, int epoch)
 {
-  while (ld_acquire(flag + row) != epoch) { }
+  while (ld_acquire(flag + row) != epoch) { } /* numeric factorisation only (setup path) */
 }
 
 /* Dynamic CTA index: CTAs are numbered in the order they actually start, so a CTA only ever waits on rows owned by
@@ -67,10 +68,36 @@ __device__ __forceinline__ int take_ticket(int *ticket)
 }
 
 /* ------------------------------------------------------------------ triangular sweeps */
-/* lower: x[i] = b[i] - sum_{k in L(i,:)} ba[k] x[bj[k]]            (aijfact.c:2431-2440)
-   upper: x[i] = (x[i] - sum_{k in U(i,:) strict} ba[k] x[bj[k]]) * ba[bdiag[i]]   (aijfact.c:2443-2451) */
+/* lower: t[i] = b[i] - sum_{k in L(i,:)} ba[k] t[bj[k]]                          (aijfact.c:2431-2440)
+   upper: x[i] = (t[i] - sum_{k in U(i,:) strict} ba[k] x[bj[k]]) * ba[bdiag[i]]   (aijfact.c:2443-2451)
+
+   Readiness travels WITH the value: the output vector of a sweep is pre-filled with a sentinel bit pattern
+   (0xFF..FF, one cudaMemsetAsync) and a consumer spins on the 8-byte entry itself until it is no longer the sentinel.
+   An aligned 8-byte store is single-copy atomic, so there is no separate flag, no release fence on the producer and no
+   acquire/L1-invalidate on the consumer: the per-level critical path is one L2 store + one L2 load.  (The first
+   version used a flag + __threadfence + ld.acquire per row and ran ~17 us per level; see profiles/round1_notes.md.) */
+#define ILU_SENTINEL 0xFFFFFFFFFFFFFFFFull
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const double *p)
+{
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_f64(double *p, double v)
+{
+  unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  if (u == ILU_SENTINEL) u = 0x7FFFFFFFFFFFFFFFull; /* a NaN that happens to equal the sentinel: store the canonical NaN */
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(u) : "memory");
+}
+__device__ __forceinline__ double wait_value(const double *p)
+{
+  unsigned long long v;
+  while ((v = ld_relaxed_u64(p)) == ILU_SENTINEL) { }
+  return __longlong_as_double((long long)v);
+}
+
 template <int G, bool UPPER>
-__global__ void __launch_bounds__(ILU_TPB) ilu_sweep_kernel(int nslot, const int *__restrict__ order, const int *__restrict__ bi, const int *__restrict__ bdiag, const int *__restrict__ bj, const double *__restrict__ ba, const double *b, double *x, int *flag, int epoch, int *ticket)
+__global__ void __launch_bounds__(ILU_TPB) ilu_sweep_kernel(int nslot, const int *__restrict__ order, const int *__restrict__ bi, const int *__restrict__ bdiag, const int *__restrict__ bj, const double *__restrict__ ba, const double *__restrict__ rhs, double *out, int *ticket)
 {
   const int      cta  = take_ticket(ticket);
   const int      slot = cta * (ILU_TPB / G) + threadIdx.x / G;
@@ -80,25 +107,19 @@ __global__ void __launch_bounds__(ILU_TPB) ilu_sweep_kernel(int nslot, const int
   const int i = order[slot];
   if (i < 0) return; /* padding: whole groups drop out together */
   int    ks, ke;
-  double sum, dinv = 0.0;
+  double sum = rhs[i], dinv = 0.0; /* lower: b[i]; upper: the lower sweep's t[i] (complete: previous kernel) */
   if (!UPPER) {
-    ks  = bi[i];
-    ke  = bi[i + 1];
-    sum = b[i];
+    ks = bi[i];
+    ke = bi[i + 1];
   } else {
     ks   = bdiag[i + 1] + 1;
     ke   = bdiag[i];
-    sum  = __ldcg(x + i);
     dinv = ba[ke];
   }
   for (int k0 = ks; k0 < ke; k0 += G) {
     const int k = k0 + gl;
     double    p = 0.0;
-    if (k < ke) {
-      const int c = bj[k];
-      wait_ready(flag, c, epoch);
-      p = __dmul_rn(ba[k], __ldcg(x + c));
-    }
+    if (k < ke) p = __dmul_rn(ba[k], wait_value(out + bj[k]));
     const int cnt = min(G, ke - k0);
 #pragma unroll
     for (int l = 0; l < G; l++) {
@@ -108,9 +129,7 @@ __global__ void __launch_bounds__(ILU_TPB) ilu_sweep_kernel(int nslot, const int
   }
   if (gl == 0) {
     if (UPPER) sum = __dmul_rn(sum, dinv);
-    x[i] = sum;
-    __threadfence();
-    st_release(flag + i, epoch);
+    st_relaxed_f64(out + i, sum);
   }
 }
 
@@ -213,7 +232,7 @@ extern "C" int b200Ilu0Destroy(b200IluPlan p)
 {
   if (!p) return 0;
   cudaFree(p->d_ai); cudaFree(p->d_adiag); cudaFree(p->d_bi); cudaFree(p->d_bj); cudaFree(p->d_bdiag); cudaFree(p->d_ba);
-  cudaFree(p->d_orderL); cudaFree(p->d_orderU); cudaFree(p->d_flag); cudaFree(p->d_ticket);
+  cudaFree(p->d_orderL); cudaFree(p->d_orderU); cudaFree(p->d_flag); cudaFree(p->d_ticket); cudaFree(p->d_tmp);
   free(p->h_bi); free(p->h_bj); free(p->h_bdiag);
   free(p);
   return 0;
@@ -312,6 +331,7 @@ extern "C" int b200Ilu0Symbolic(b200Handle h, int n, const int *ai, const int *a
   UP(d_orderU, orderU, p->nslotU, int);
 #undef UP
   B200_CUDA(cudaMalloc(&p->d_ba, sizeof(double) * ((size_t)nnz + 64)));
+  B200_CUDA(cudaMalloc(&p->d_tmp, sizeof(double) * ((size_t)n + 64)));
   B200_CUDA(cudaMalloc(&p->d_flag, sizeof(int) * ((size_t)n + 64)));
   B200_CUDA(cudaMemsetAsync(p->d_flag, 0, sizeof(int) * ((size_t)n + 64), h->stream));
   B200_CUDA(cudaMalloc(&p->d_ticket, 64));
@@ -369,12 +389,12 @@ template <int G>
 static int sweeps_launch(b200Handle h, b200IluPlan p, const double *b, double *x)
 {
   const int rows_per_cta = ILU_TPB / G;
-  p->epoch++;
   B200_CUDA(cudaMemsetAsync(p->d_ticket, 0, 64, h->stream));
-  ilu_sweep_kernel<G, false><<<(p->nslotL + rows_per_cta - 1) / rows_per_cta, ILU_TPB, 0, h->stream>>>(p->nslotL, p->d_orderL, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, b, x, p->d_flag, p->epoch, p->d_ticket);
+  B200_CUDA(cudaMemsetAsync(p->d_tmp, 0xFF, sizeof(double) * (size_t)p->n, h->stream)); /* sentinel fill */
+  B200_CUDA(cudaMemsetAsync(x, 0xFF, sizeof(double) * (size_t)p->n, h->stream));
+  ilu_sweep_kernel<G, false><<<(p->nslotL + rows_per_cta - 1) / rows_per_cta, ILU_TPB, 0, h->stream>>>(p->nslotL, p->d_orderL, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, b, p->d_tmp, p->d_ticket);
   B200_KERNEL_CHECK();
-  p->epoch++;
-  ilu_sweep_kernel<G, true><<<(p->nslotU + rows_per_cta - 1) / rows_per_cta, ILU_TPB, 0, h->stream>>>(p->nslotU, p->d_orderU, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, b, x, p->d_flag, p->epoch, p->d_ticket + 1);
+  ilu_sweep_kernel<G, true><<<(p->nslotU + rows_per_cta - 1) / rows_per_cta, ILU_TPB, 0, h->stream>>>(p->nslotU, p->d_orderU, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, p->d_tmp, x, p->d_ticket + 1);
   B200_KERNEL_CHECK();
   B200_LAUNCHED(2);
   return 0;

@@ -254,3 +254,28 @@ def test_launch_counter(H):
     d = H.zeros(1000)
     _capi.check(_capi.lib().b200VecScale(H.h, C.c_int64(1000), C.c_double(2.0), d.ptr))
     assert _capi.launch_count() == a + 1
+
+
+def test_device_laplace27_and_random_generators(H, oracle):
+    from petsc_b200 import _capi
+    L = _capi.lib()
+    for n in (2, 5, 9):
+        ai, aj, aa = oracle.lap27(n)
+        nnz = C.c_int64()
+        _capi.check(L.b200GenLaplace27Nnz(n, C.byref(nnz)))
+        assert nnz.value == len(aj)
+        d_i, d_j, d_a = H.empty(n ** 3 + 1, np.int32), H.empty(nnz.value, np.int32), H.empty(nnz.value)
+        _capi.check(L.b200GenLaplace27(H.h, n, d_i.ptr, d_j.ptr, d_a.ptr))
+        assert np.array_equal(d_i.download(), ai) and np.array_equal(d_j.download(), aj) and np.array_equal(d_a.download(), aa)
+    n, d = 5000, 32
+    d_i, d_j, d_a = H.empty(n + 1, np.int32), H.empty(n * d, np.int32), H.empty(n * d)
+    _capi.check(L.b200GenRandomCsr(H.h, n, n, d, C.c_uint64(7), d_i.ptr, d_j.ptr, d_a.ptr))
+    ai, aj, aa = d_i.download(), d_j.download().reshape(n, d), d_a.download()
+    assert np.array_equal(ai, np.arange(n + 1) * d) and np.all(np.diff(aj, axis=1) > 0) and aj.min() >= 0 and aj.max() < n
+    assert np.all(np.abs(aa) < 1.0) and abs(aa.mean()) < 0.01
+    x = np.random.default_rng(0).uniform(-1, 1, n)
+    plan = H.csr_plan(n, n, n * d, d_i, d_j)
+    d_x, d_y = H.array(x), H.empty(n)
+    H.csr_plan_set_layout(plan, lanes=1)
+    H.spmv(plan, d_a, d_x, d_y)
+    assert np.array_equal(d_y.download(), oracle.matmult(ai, aj.reshape(-1), aa, x))

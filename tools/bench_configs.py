@@ -1,0 +1,165 @@
+#!/usr/bin/env python
+"""Measurements for the other BASELINE.json configs (bench.py is configs[1]); writes one JSON object.
+
+  config 3: 27-point 256^3, KSPCG + PCILU(0)  (ILU(0) numeric on device, sync-free sweeps)
+  config 5: random CSR sweep n = 10 M (2.5 M for d = 512: 32-bit PetscInt), d in {5, 32, 128, 512}, MatMult only
+  config 1: ex2 100x100 GMRES(30)+Jacobi (latency-bound small case)
+
+usage: python tools/bench_configs.py [--what 3,5,1] [--n27 256] [--out gpurun_out/configs.json]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from petsc_b200 import _capi, petsc  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--what", default="3,5,1")
+    ap.add_argument("--n27", type=int, default=256)
+    ap.add_argument("--nrand", type=int, default=10_000_000)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    L = _capi.lib()
+    petsc.initialize(device=0)
+    H = petsc.handle()
+
+    class Hh:
+        h = H
+    peak = 6570.6
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    res = {"peak_gbs": peak}
+    what = a.what.split(",")
+
+    def timed(fn, reps, warm=2):
+        t = _capi.Timer(Hh)
+        for _ in range(warm):
+            fn()
+        t.start()
+        for _ in range(reps):
+            fn()
+        t.stop()
+        return t.ms() / reps
+
+    if "5" in what:
+        res["config5_random_csr"] = []
+        for d in (5, 32, 128, 512):
+            n = a.nrand if d < 512 else a.nrand // 4
+            nnz = n * d
+            d_i, d_j, d_a = _capi.DeviceArray(Hh, n + 1, np.int32), _capi.DeviceArray(Hh, nnz, np.int32), _capi.DeviceArray(Hh, nnz, np.float64)
+            _capi.check(L.b200GenRandomCsr(H, n, n, d, C.c_uint64(20260923 + d), d_i.ptr, d_j.ptr, d_a.ptr))
+            plan = C.c_void_p()
+            _capi.check(L.b200CsrPlanCreate(H, n, n, C.c_int64(nnz), d_i.ptr, d_j.ptr, C.byref(plan)))
+            x, y = _capi.DeviceArray(Hh, n, np.float64), _capi.DeviceArray(Hh, n, np.float64)
+            _capi.check(L.b200VecSet(H, C.c_int64(n), C.c_double(1.0), x.ptr))
+            lay = [C.c_int() for _ in range(6)]
+            best = None
+            for lanes in (0, 1, 2, 4, 8, 16, 32):
+                if lanes and (lanes > max(2 * d, 1)):
+                    continue
+                _capi.check(L.b200CsrPlanSetLayout(plan, lanes, 0, 0, 0))
+                _capi.check(L.b200CsrPlanGetLayout(plan, *[C.byref(v) for v in lay]))
+                ms = timed(lambda: _capi.check(L.b200CsrSpMV(H, plan, d_a.ptr, x.ptr, y.ptr)), 10)
+                r = dict(lanes_req=lanes, lanes=lay[0].value, rows_per_tile=lay[1].value, ms=ms)
+                if lanes == 0:
+                    auto = r
+                if best is None or ms < best["ms"]:
+                    best = r
+            alg = nnz * 12 + n * 20
+            row = dict(n=n, d=d, nnz=nnz, auto=auto, best=best, algorithmic_bytes=alg, gbs_auto=alg / auto["ms"] / 1e6, gbs_best=alg / best["ms"] / 1e6,
+                       frac_auto=alg / auto["ms"] / 1e6 / peak, gflops_auto=(2 * nnz - n) / auto["ms"] / 1e6,
+                       note="x gather is random over an n-vector (%d MB): beyond the 126 MB L2, so DRAM traffic exceeds the algorithmic bytes" % (n * 8 // 1000000))
+            res["config5_random_csr"].append(row)
+            print("config5", row, flush=True)
+            L.b200CsrPlanDestroy(plan)
+            for o in (d_i, d_j, d_a, x, y):
+                o.free()
+
+    if "3" in what:
+        n = a.n27
+        N = n ** 3
+        nnz = C.c_int64()
+        _capi.check(L.b200GenLaplace27Nnz(n, C.byref(nnz)))
+        nnz = nnz.value
+        d_i, d_j, d_a = _capi.DeviceArray(Hh, N + 1, np.int32), _capi.DeviceArray(Hh, nnz, np.int32), _capi.DeviceArray(Hh, nnz, np.float64)
+        _capi.check(L.b200GenLaplace27(H, n, d_i.ptr, d_j.ptr, d_a.ptr))
+        petsc.options_clear()
+        petsc.options_insert("-ksp_type cg -pc_type ilu -ksp_rtol 1e-8")
+        A = petsc.Mat.create(m=N, n=N, M=N, N=N, comm=petsc.COMM_SELF)
+        A.set_csr_device(d_i.ptr, d_j.ptr, d_a.ptr)
+        for o in (d_i, d_j, d_a):
+            o.free()
+        x, b = A.create_vecs()
+        u = x.duplicate(); u.set(1.0); A.mult(u, b)
+        spmv_ms = timed(lambda: A.mult(u, x), 20)
+        ksp = petsc.KSP.create(petsc.COMM_SELF)
+        ksp.set_operators(A); ksp.set_residual_history(); ksp.set_from_options()
+        t0 = time.time()
+        pc = ksp.get_pc()
+        ksp.solve(b, x)            # includes PCSetUp: host symbolic + level schedule, device numeric
+        _capi.check(L.b200Synchronize(H))
+        first = time.time() - t0
+        its = ksp.its()
+        t = _capi.Timer(Hh)
+        t.start(); ksp.solve(b, x); t.stop()
+        solve_ms = t.ms()
+        y = x.duplicate()
+        pcapply_ms = timed(lambda: pc.apply(b, y), 10)
+        err = float(np.abs(x.array() - 1.0).max())
+        alg_spmv = nnz * 12 + N * 20
+        alg_sptrsv = nnz * 12 + N * (4 + 4 + 4 + 4 + 8 * 3)
+        res["config3_cg_ilu0_27pt"] = dict(n=n, rows=N, nnz=nnz, iterations=its, reason=ksp.reason(), max_error=err, first_solve_incl_setup_s=first, solve_ms=solve_ms,
+                                           ms_per_iteration=solve_ms / max(its, 1), iterations_per_sec=its / (solve_ms * 1e-3), spmv_ms=spmv_ms, spmv_gbs=alg_spmv / spmv_ms / 1e6,
+                                           pcapply_ilu_ms=pcapply_ms, sptrsv_gbs=alg_sptrsv / pcapply_ms / 1e6, sptrsv_frac_of_peak=alg_sptrsv / pcapply_ms / 1e6 / peak,
+                                           levels=3 * n + 4 * (n - 1) - 2 if True else None)
+        print("config3", res["config3_cg_ilu0_27pt"], flush=True)
+        ksp.destroy(); A.destroy()
+
+    if "1" in what:
+        # ex2 -m 100 -n 100 -ksp_type gmres -pc_type jacobi (BASELINE configs[0]); matrix assembled on the host like ex2 does
+        m = 100
+        rows, cols, vals = [], [], []
+        ai = [0]; aj = []; aa = []
+        for Ii in range(m * m):
+            i, j = divmod(Ii, m)
+            for (J, v) in ((Ii - m, -1.0) if i > 0 else None, (Ii - 1, -1.0) if j > 0 else None, (Ii, 4.0), (Ii + 1, -1.0) if j < m - 1 else None, (Ii + m, -1.0) if i < m - 1 else None):
+                pass
+        # build CSR directly
+        for Ii in range(m * m):
+            i, j = divmod(Ii, m)
+            if i > 0: aj.append(Ii - m); aa.append(-1.0)
+            if j > 0: aj.append(Ii - 1); aa.append(-1.0)
+            aj.append(Ii); aa.append(4.0)
+            if j < m - 1: aj.append(Ii + 1); aa.append(-1.0)
+            if i < m - 1: aj.append(Ii + m); aa.append(-1.0)
+            ai.append(len(aj))
+        A = petsc.Mat.from_csr(np.array(ai), np.array(aj), np.array(aa))
+        x, b = A.create_vecs()
+        u = x.duplicate(); u.set(1.0); A.mult(u, b)
+        petsc.options_clear()
+        petsc.options_insert("-ksp_type gmres -pc_type jacobi -ksp_rtol %r" % (1e-2 / 10201))
+        ksp = petsc.KSP.create(petsc.COMM_SELF)
+        ksp.set_operators(A); ksp.set_from_options()
+        ksp.solve(b, x)
+        t = _capi.Timer(Hh)
+        t.start(); ksp.solve(b, x); t.stop()
+        res["config1_ex2_100x100"] = dict(iterations=ksp.its(), reason=ksp.reason(), rnorm=ksp.rnorm(), solve_ms=t.ms(), us_per_iteration=1e3 * t.ms() / ksp.its(),
+                                           error_norm=float(np.linalg.norm(x.array() - 1.0)), reference="719 its, residual 4.918891918633e-06, error 0.00920721 (SURVEY 6)")
+        print("config1", res["config1_ex2_100x100"], flush=True)
+    if a.out:
+        os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
+        json.dump(res, open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
