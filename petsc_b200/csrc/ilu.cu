@@ -38,6 +38,7 @@ struct b200IluPlan_s {
   int    *d_ticket;                  /* [4] tickets + status */
   int     epoch;
   int     nlevL, nlevU;
+  int     maxwL, maxwU;              /* widest level (rows) */
   int     G;                         /* lanes per row in the sweeps */
   int    *h_bi, *h_bj, *h_bdiag;     /* host copy of the layout (kept for GetFactor) */
   int     factored;
@@ -54,7 +55,11 @@ __device__ __forceinline__ int ld_acquire(const int *p)
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void wait_ready(const int *flag, int row, int epoch)
 {
-  while (ld_acquire(flag + row) != epoch) { } /* numeric factorisation only (setup path) */
+  unsigned ns = 0; /* numeric factorisation only (setup path); same back-off as wait_value */
+  while (ld_acquire(flag + row) != epoch) {
+    if (ns) __nanosleep(ns);
+    ns = ns ? (ns < 512 ? ns * 2 : 512) : 32;
+  }
 }
 
 /* Dynamic CTA index: CTAs are numbered in the order they actually start, so a CTA only ever waits on rows owned by
@@ -66,6 +71,15 @@ __device__ __forceinline__ int take_ticket(int *ticket)
   __syncthreads();
   return s_t;
 }
+
+#define ILU_BATCH 4
+__device__ __forceinline__ int warp_ticket(int *ticket)
+{
+  int t = 0;
+  if ((threadIdx.x & 31) == 0) t = atomicAdd(ticket, 1);
+  return __shfl_sync(0xffffffffu, t, 0);
+}
+
 
 /* ------------------------------------------------------------------ triangular sweeps */
 /* lower: t[i] = b[i] - sum_{k in L(i,:)} ba[k] t[bj[k]]                          (aijfact.c:2431-2440)
@@ -89,37 +103,63 @@ __device__ __forceinline__ void st_relaxed_f64(double *p, double v)
   if (u == ILU_SENTINEL) u = 0x7FFFFFFFFFFFFFFFull; /* a NaN that happens to equal the sentinel: store the canonical NaN */
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(u) : "memory");
 }
-__device__ __forceinline__ double wait_value(const double *p)
+__device__ int g_ilu_backoff_ns = 0; /* tunable: PETSCB200_ILU_BACKOFF_NS (0 = pure spinning; measured best) */
+static int     g_ilu_lookahead = 2, g_ilu_batch = 1; /* tunables: PETSCB200_ILU_LOOKAHEAD, PETSCB200_ILU_BATCH */
+
+/* Warp-convergent wait: every lane polls its own dependency (or nothing), the warp loops until ALL its lanes have seen a
+   value.  The rows of one warp-chunk belong to one level, so they become ready together; a convergent loop issues one
+   poll wavefront and at most one nanosleep per iteration for the whole warp (divergent per-lane spin loops serialise). */
+__device__ __forceinline__ double wait_value_warp(const double *p, bool active)
 {
-  unsigned long long v;
-  while ((v = ld_relaxed_u64(p)) == ILU_SENTINEL) { }
+  unsigned long long v     = 0;
+  bool               ready = !active;
+  unsigned           ns = 0, spins = 0;
+  const unsigned     cap = (unsigned)g_ilu_backoff_ns;
+  for (;;) {
+    if (!ready) {
+      v     = ld_relaxed_u64(p);
+      ready = (v != ILU_SENTINEL);
+    }
+    if (__all_sync(0xffffffffu, ready)) break;
+    if (++spins > 4 && cap) {
+      ns = ns ? (ns * 2 < cap ? ns * 2 : cap) : 32;
+      __nanosleep(ns);
+    }
+  }
   return __longlong_as_double((long long)v);
 }
 
 template <int G, bool UPPER>
-__global__ void __launch_bounds__(ILU_TPB) ilu_sweep_kernel(int nslot, const int *__restrict__ order, const int *__restrict__ bi, const int *__restrict__ bdiag, const int *__restrict__ bj, const double *__restrict__ ba, const double *__restrict__ rhs, double *out, int *ticket)
+__device__ __forceinline__ void ilu_sweep_row(int slot, int nslot, const int *__restrict__ order, const int *__restrict__ bi, const int *__restrict__ bdiag, const int *__restrict__ bj, const double *__restrict__ ba, const double *__restrict__ rhs, double *out)
 {
-  const int      cta  = take_ticket(ticket);
-  const int      slot = cta * (ILU_TPB / G) + threadIdx.x / G;
-  const int      gl   = threadIdx.x % G;
+  /* warp-convergent: groups without a row (padding, tail) run the same control flow with an empty range */
+  const int      gl    = threadIdx.x % G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
-  if (slot >= nslot) return;
-  const int i = order[slot];
-  if (i < 0) return; /* padding: whole groups drop out together */
-  int    ks, ke;
-  double sum = rhs[i], dinv = 0.0; /* lower: b[i]; upper: the lower sweep's t[i] (complete: previous kernel) */
-  if (!UPPER) {
-    ks = bi[i];
-    ke = bi[i + 1];
-  } else {
-    ks   = bdiag[i + 1] + 1;
-    ke   = bdiag[i];
-    dinv = ba[ke];
+  const int      i     = slot < nslot ? order[slot] : -1;
+  const bool     valid = i >= 0;
+  int            ks = 0, ke = 0;
+  double         sum = 0.0, dinv = 0.0;
+  if (valid) {
+    sum = rhs[i]; /* lower: b[i]; upper: the lower sweep's t[i] (complete: previous kernel) */
+    if (!UPPER) {
+      ks = bi[i];
+      ke = bi[i + 1];
+    } else {
+      ks   = bdiag[i + 1] + 1;
+      ke   = bdiag[i];
+      dinv = ba[ke];
+    }
   }
-  for (int k0 = ks; k0 < ke; k0 += G) {
-    const int k = k0 + gl;
-    double    p = 0.0;
-    if (k < ke) p = __dmul_rn(ba[k], wait_value(out + bj[k]));
+  int nchunk = (ke - ks + G - 1) / G;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nchunk = max(nchunk, __shfl_xor_sync(0xffffffffu, nchunk, o));
+  for (int c = 0; c < nchunk; c++) {
+    const int  k0  = ks + c * G;
+    const int  k   = k0 + gl;
+    const bool act = k < ke;
+    const double a = act ? ba[k] : 0.0; /* factor entry fetched while the dependency is still in flight */
+    double       p = wait_value_warp(out + (act ? bj[k] : 0), act);
+    if (act) p = __dmul_rn(a, p);
     const int cnt = min(G, ke - k0);
 #pragma unroll
     for (int l = 0; l < G; l++) {
@@ -127,9 +167,29 @@ __global__ void __launch_bounds__(ILU_TPB) ilu_sweep_kernel(int nslot, const int
       if (l < cnt) sum = __dsub_rn(sum, pl); /* strict left-to-right, FMA-free */
     }
   }
-  if (gl == 0) {
+  if (valid && gl == 0) {
     if (UPPER) sum = __dmul_rn(sum, dinv);
     st_relaxed_f64(out + i, sum);
+  }
+}
+
+/* Persistent warps: every warp repeatedly takes the next batch of ILU_BATCH warp-chunks (a chunk = 32/G consecutive slots
+   of the level order, never straddling a level) through one atomic ticket.  Tickets are handed out in dependency order,
+   so whatever a warp waits for is owned by a warp that already holds a ticket; no CTA is launched per chunk (the first
+   version launched ~1 M CTAs per sweep and was bound by CTA dispatch, 19 us per level; profiles/round1_notes.md). */
+template <int G, bool UPPER>
+__global__ void __launch_bounds__(ILU_TPB) ilu_sweep_kernel(int nslot, const int *__restrict__ order, const int *__restrict__ bi, const int *__restrict__ bdiag, const int *__restrict__ bj, const double *__restrict__ ba, const double *__restrict__ rhs, double *out, int *ticket, int batch)
+{
+  constexpr int RPW = 32 / G; /* rows per warp-chunk */
+  for (;;) {
+    const int64_t base = (int64_t)warp_ticket(ticket) * (batch * RPW);
+    if (base >= nslot) break;
+#pragma unroll 1
+    for (int q = 0; q < batch; q++) {
+      const int64_t slot = base + q * RPW + (threadIdx.x & 31) / G;
+      ilu_sweep_row<G, UPPER>((int)(slot < nslot ? slot : nslot), nslot, order, bi, bdiag, bj, ba, rhs, out);
+      __syncwarp();
+    }
   }
 }
 
@@ -148,10 +208,8 @@ __device__ __forceinline__ int find_col(const int *__restrict__ bj, int lo, int 
 }
 
 template <int G>
-__global__ void __launch_bounds__(ILU_TPB) ilu_numeric_kernel(int nslot, const int *__restrict__ order, const int *__restrict__ ai, const int *__restrict__ adiag, const double *__restrict__ aval, const int *__restrict__ bi, const int *__restrict__ bdiag, const int *__restrict__ bj, double *ba, double shift, double zeropivot, int *flag, int epoch, int *ticket, int *status)
+__device__ __forceinline__ void ilu_numeric_row(int slot, int nslot, const int *__restrict__ order, const int *__restrict__ ai, const int *__restrict__ adiag, const double *__restrict__ aval, const int *__restrict__ bi, const int *__restrict__ bdiag, const int *__restrict__ bj, double *ba, double shift, double zeropivot, int *flag, int epoch, int *status)
 {
-  const int      cta   = take_ticket(ticket);
-  const int      slot  = cta * (ILU_TPB / G) + threadIdx.x / G;
   const int      gl    = threadIdx.x % G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   if (slot >= nslot) return;
@@ -202,15 +260,32 @@ __global__ void __launch_bounds__(ILU_TPB) ilu_numeric_kernel(int nslot, const i
   }
 }
 
+template <int G>
+__global__ void __launch_bounds__(ILU_TPB) ilu_numeric_kernel(int nslot, const int *__restrict__ order, const int *__restrict__ ai, const int *__restrict__ adiag, const double *__restrict__ aval, const int *__restrict__ bi, const int *__restrict__ bdiag, const int *__restrict__ bj, double *ba, double shift, double zeropivot, int *flag, int epoch, int *ticket, int *status)
+{
+  constexpr int RPW = 32 / G;
+  for (;;) {
+    const int64_t base = (int64_t)warp_ticket(ticket) * (ILU_BATCH * RPW);
+    if (base >= nslot) break;
+#pragma unroll 1
+    for (int q = 0; q < ILU_BATCH; q++) {
+      const int64_t slot = base + q * RPW + (threadIdx.x & 31) / G;
+      ilu_numeric_row<G>((int)(slot < nslot ? slot : nslot), nslot, order, ai, adiag, aval, bi, bdiag, bj, ba, shift, zeropivot, flag, epoch, status);
+      __syncwarp();
+    }
+  }
+}
+
 /* ------------------------------------------------------------------ host: symbolic + level schedule */
-static int *levels_to_order(int n, const int *lev, int nlev, int rpw, int *nslot_out)
+static int *levels_to_order(int n, const int *lev, int nlev, int rpw, int *nslot_out, int *maxwidth_out)
 {
   /* counting sort by level, each level padded to a multiple of rpw (rows per warp) with -1 */
   int64_t *cnt = (int64_t *)calloc((size_t)nlev + 1, sizeof(int64_t));
   for (int i = 0; i < n; i++) cnt[lev[i] + 1]++;
-  int64_t tot = 0;
+  int64_t tot = 0, mw = 0;
   int64_t *start = (int64_t *)malloc(sizeof(int64_t) * ((size_t)nlev + 1));
   for (int l = 0; l < nlev; l++) {
+    if (cnt[l + 1] > mw) mw = cnt[l + 1];
     start[l] = tot;
     tot += (cnt[l + 1] + rpw - 1) / rpw * rpw;
   }
@@ -222,7 +297,8 @@ static int *levels_to_order(int n, const int *lev, int nlev, int rpw, int *nslot
   int *order = (int *)malloc(sizeof(int) * (size_t)(tot + 1));
   for (int64_t k = 0; k < tot; k++) order[k] = -1;
   for (int i = 0; i < n; i++) order[start[lev[i]]++] = i;
-  *nslot_out = (int)tot;
+  *nslot_out    = (int)tot;
+  *maxwidth_out = (int)mw;
   free(cnt);
   free(start);
   return order;
@@ -310,8 +386,8 @@ extern "C" int b200Ilu0Symbolic(b200Handle h, int n, const int *ai, const int *a
   }
   /* the numeric kernel uses 8 lanes per row; pad levels for the larger of the two groupings */
   const int rpw = 32 / (p->G < 8 ? p->G : 8); /* a multiple of the sweeps' rows-per-warp (32/G) as well */
-  int *orderL = levels_to_order(n, levL, nlevL, rpw, &p->nslotL);
-  int *orderU = levels_to_order(n, levU, nlevU, rpw, &p->nslotU);
+  int *orderL = levels_to_order(n, levL, nlevL, rpw, &p->nslotL, &p->maxwL);
+  int *orderU = levels_to_order(n, levU, nlevU, rpw, &p->nslotU, &p->maxwU);
   free(levL); free(levU);
   if (!orderL || !orderU) {
     free(orderL); free(orderU); free(adiag); free(bi); free(bdiag); free(bj); free(p);
@@ -344,11 +420,21 @@ extern "C" int b200Ilu0Symbolic(b200Handle h, int n, const int *ai, const int *a
   return 0;
 }
 
+/* Persistent grid sized to the parallelism that exists: about two levels' worth of rows in flight (warps that run
+   further ahead only poll), between one CTA per SM and the residency limit of 8 x 256 threads per SM */
+static int ilu_grid(b200Handle h, int maxwidth, int G)
+{
+  const int64_t rows_per_cta = (ILU_TPB / 32) * (32 / G);
+  int64_t       g            = (g_ilu_lookahead * (int64_t)maxwidth + rows_per_cta - 1) / rows_per_cta;
+  if (g < h->num_sms) g = h->num_sms;
+  if (g > (int64_t)h->num_sms * 8) g = (int64_t)h->num_sms * 8;
+  return (int)g;
+}
+
 template <int G>
 static int numeric_launch(b200Handle h, b200IluPlan p, const double *aval, double shift, double zeropivot)
 {
-  const int rows_per_cta = ILU_TPB / G;
-  const int grid         = (p->nslotL + rows_per_cta - 1) / rows_per_cta;
+  const int grid = ilu_grid(h, p->maxwL, G);
   ilu_numeric_kernel<G><<<grid, ILU_TPB, 0, h->stream>>>(p->nslotL, p->d_orderL, p->d_ai, p->d_adiag, aval, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, shift, zeropivot, p->d_flag, p->epoch, p->d_ticket, p->d_ticket + 8);
   B200_LAUNCHED(1);
   B200_KERNEL_CHECK();
@@ -385,16 +471,33 @@ extern "C" int b200Ilu0Numeric(b200Handle h, b200IluPlan p, const double *d_aval
   return 0;
 }
 
+static int ilu_set_backoff(void)
+{
+  static int done = 0;
+  if (!done) {
+    const char *e = getenv("PETSCB200_ILU_BACKOFF_NS");
+    if (e) {
+      int v = atoi(e);
+      B200_CUDA(cudaMemcpyToSymbol(g_ilu_backoff_ns, &v, sizeof(int)));
+    }
+    if ((e = getenv("PETSCB200_ILU_LOOKAHEAD")) && atoi(e) > 0) g_ilu_lookahead = atoi(e);
+    if ((e = getenv("PETSCB200_ILU_BATCH")) && atoi(e) > 0) g_ilu_batch = atoi(e);
+    done = 1;
+  }
+  return 0;
+}
+
 template <int G>
 static int sweeps_launch(b200Handle h, b200IluPlan p, const double *b, double *x)
 {
-  const int rows_per_cta = ILU_TPB / G;
+  if (ilu_set_backoff()) return B200_ERR_GPU;
+  const int gridL = ilu_grid(h, p->maxwL, G), gridU = ilu_grid(h, p->maxwU, G);
   B200_CUDA(cudaMemsetAsync(p->d_ticket, 0, 64, h->stream));
   B200_CUDA(cudaMemsetAsync(p->d_tmp, 0xFF, sizeof(double) * (size_t)p->n, h->stream)); /* sentinel fill */
   B200_CUDA(cudaMemsetAsync(x, 0xFF, sizeof(double) * (size_t)p->n, h->stream));
-  ilu_sweep_kernel<G, false><<<(p->nslotL + rows_per_cta - 1) / rows_per_cta, ILU_TPB, 0, h->stream>>>(p->nslotL, p->d_orderL, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, b, p->d_tmp, p->d_ticket);
+  ilu_sweep_kernel<G, false><<<gridL, ILU_TPB, 0, h->stream>>>(p->nslotL, p->d_orderL, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, b, p->d_tmp, p->d_ticket, g_ilu_batch);
   B200_KERNEL_CHECK();
-  ilu_sweep_kernel<G, true><<<(p->nslotU + rows_per_cta - 1) / rows_per_cta, ILU_TPB, 0, h->stream>>>(p->nslotU, p->d_orderU, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, p->d_tmp, x, p->d_ticket + 1);
+  ilu_sweep_kernel<G, true><<<gridU, ILU_TPB, 0, h->stream>>>(p->nslotU, p->d_orderU, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, p->d_tmp, x, p->d_ticket + 1, g_ilu_batch);
   B200_KERNEL_CHECK();
   B200_LAUNCHED(2);
   return 0;

@@ -209,14 +209,31 @@ __global__ void __launch_bounds__(SPMV_TPB) csr_spmv_tile_kernel(int m, int R, i
         /* parity mode: strict left-to-right, FMA-free (aij.h:609-614) */
         sum = (act && yin) ? yin[r] : 0.0;
         if (staged) {
-          for (int k = ks - k0a; k < ke - k0a; k++) sum = __dadd_rn(sum, __dmul_rn(vs[k], ldx(x + cs[k])));
+          /* four gathers in flight per thread, then the same left-to-right adds (order unchanged => still bit-exact) */
+          int k = ks - k0a;
+          for (; k + 4 <= ke - k0a; k += 4) {
+            const double x0 = ldx(x + cs[k]), x1 = ldx(x + cs[k + 1]), x2 = ldx(x + cs[k + 2]), x3 = ldx(x + cs[k + 3]);
+            sum = __dadd_rn(sum, __dmul_rn(vs[k], x0));
+            sum = __dadd_rn(sum, __dmul_rn(vs[k + 1], x1));
+            sum = __dadd_rn(sum, __dmul_rn(vs[k + 2], x2));
+            sum = __dadd_rn(sum, __dmul_rn(vs[k + 3], x3));
+          }
+          for (; k < ke - k0a; k++) sum = __dadd_rn(sum, __dmul_rn(vs[k], ldx(x + cs[k])));
         } else {
           for (int k = ks; k < ke; k++) sum = __dadd_rn(sum, __dmul_rn(__ldg(val + k), __ldg(x + __ldg(colidx + k))));
         }
       } else {
         sum = 0.0;
         if (staged) {
-          for (int k = ks - k0a + gl; k < ke - k0a; k += G) sum = fma(vs[k], ldx(x + cs[k]), sum);
+          int k = ks - k0a + gl;
+          for (; k + 3 * G < ke - k0a; k += 4 * G) { /* four independent gathers in flight per lane */
+            const double x0 = ldx(x + cs[k]), x1 = ldx(x + cs[k + G]), x2 = ldx(x + cs[k + 2 * G]), x3 = ldx(x + cs[k + 3 * G]);
+            sum = fma(vs[k], x0, sum);
+            sum = fma(vs[k + G], x1, sum);
+            sum = fma(vs[k + 2 * G], x2, sum);
+            sum = fma(vs[k + 3 * G], x3, sum);
+          }
+          for (; k < ke - k0a; k += G) sum = fma(vs[k], ldx(x + cs[k]), sum);
         } else {
           for (int k = ks + gl; k < ke; k += G) sum = fma(__ldg(val + k), __ldg(x + __ldg(colidx + k)), sum);
         }

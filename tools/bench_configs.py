@@ -128,12 +128,7 @@ def main():
     if "1" in what:
         # ex2 -m 100 -n 100 -ksp_type gmres -pc_type jacobi (BASELINE configs[0]); matrix assembled on the host like ex2 does
         m = 100
-        rows, cols, vals = [], [], []
         ai = [0]; aj = []; aa = []
-        for Ii in range(m * m):
-            i, j = divmod(Ii, m)
-            for (J, v) in ((Ii - m, -1.0) if i > 0 else None, (Ii - 1, -1.0) if j > 0 else None, (Ii, 4.0), (Ii + 1, -1.0) if j < m - 1 else None, (Ii + m, -1.0) if i < m - 1 else None):
-                pass
         # build CSR directly
         for Ii in range(m * m):
             i, j = divmod(Ii, m)
