@@ -19,6 +19,6 @@ LNK="-L$OUT/lib -lpetsc -Wl,-rpath,\$ORIGIN/../lib -Wl,-rpath,$BLASDIR -Wl,-rpat
 for ex in ex2 bench_kspsolve; do
   /usr/bin/gcc -O2 -o "$OUT/bin/$ex" "$REF/src/ksp/ksp/tutorials/$ex.c" $INC $LNK
 done
-/usr/bin/gcc -O2 -o "$HERE/_ref/ref_driver" "$HERE/ref_driver.c" $INC -L$OUT/lib -lpetsc -Wl,-rpath,\$ORIGIN/petsc/lib -Wl,-rpath,$BLASDIR -Wl,-rpath-link,$BLASDIR -Wl,--allow-shlib-undefined -lm
+/usr/bin/gcc -O2 -ffp-contract=off -fopenmp -o "$HERE/_ref/ref_driver" "$HERE/ref_driver.c" "$HERE/oracle.c" -I"$HERE" $INC -L$OUT/lib -lpetsc -Wl,-rpath,\$ORIGIN/petsc/lib -Wl,-rpath,$BLASDIR -Wl,-rpath-link,$BLASDIR -Wl,--allow-shlib-undefined -lm
 make -s -C "$ROOT/petsc_plugin" PETSC_DIR="$PETSC_DIR" PETSC_ARCH="$PETSC_ARCH"
 echo "reference demo built in $OUT"

@@ -35,7 +35,7 @@ OUT = os.path.join(ROOT, "tests", "golden")
 def build_driver():
     exe = os.path.join(HERE, "_ref", "ref_driver")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
-    cmd = ["/usr/bin/gcc", "-O2", "-o", exe, os.path.join(HERE, "ref_driver.c"),
+    cmd = ["/usr/bin/gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-o", exe, os.path.join(HERE, "ref_driver.c"), os.path.join(HERE, "oracle.c"), "-I" + HERE,
            "-I%s/include" % PETSC_DIR, "-I%s/%s/include" % (PETSC_DIR, PETSC_ARCH),
            "-L%s/%s/lib" % (PETSC_DIR, PETSC_ARCH), "-Wl,-rpath,%s/%s/lib" % (PETSC_DIR, PETSC_ARCH), "-lpetsc", "-lm",
            "-Wl,-rpath,%s" % BLASDIR, "-Wl,-rpath-link,%s" % BLASDIR, "-Wl,--allow-shlib-undefined"]

@@ -14,6 +14,56 @@
 #include <petscksp.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+#include "oracle.h"
+
+/* timing mode: ref_driver -bench7 <n> [petsc options]
+   builds the 7-point n^3 operator in memory (oracle generator; input data only), then times the REFERENCE's own
+   MatMult_SeqAIJ and KSPSolve (options from the command line) and prints one line:
+   REFBENCH n=<n> rows=<N> nnz=<nnz> matmult_s=<avg seconds> ksp_its=<its> ksp_s=<seconds> reason=<r> rnorm=<r> */
+static PetscErrorCode bench7(int n)
+{
+  PetscInt     N = n * n * n, its;
+  int64_t      nnz = ora_lap7_nnz(n, n, n);
+  PetscInt    *ai, *aj;
+  PetscScalar *aa;
+  Mat          A;
+  Vec          u, b, x;
+  KSP          ksp;
+  double       t0, tm, tk;
+  PetscReal    rnorm;
+  KSPConvergedReason reason;
+
+  PetscFunctionBeginUser;
+  PetscCall(PetscMalloc3(N + 1, &ai, nnz, &aj, nnz, &aa));
+  ora_lap7(n, n, n, ai, aj, aa);
+  PetscCall(MatCreateSeqAIJWithArrays(PETSC_COMM_SELF, N, N, ai, aj, aa, &A));
+  PetscCall(MatCreateVecs(A, &u, &b));
+  PetscCall(VecDuplicate(u, &x));
+  PetscCall(VecSet(u, 1.0));
+  PetscCall(MatMult(A, u, b));
+  PetscCall(PetscTime(&t0));
+  for (int r = 0; r < 5; r++) PetscCall(MatMult(A, u, x));
+  PetscCall(PetscTime(&tm));
+  tm = (tm - t0) / 5;
+  PetscCall(KSPCreate(PETSC_COMM_SELF, &ksp));
+  PetscCall(KSPSetOperators(ksp, A, A));
+  PetscCall(KSPSetFromOptions(ksp));
+  PetscCall(KSPSetUp(ksp));
+  PetscCall(PetscTime(&t0));
+  PetscCall(KSPSolve(ksp, b, x));
+  PetscCall(PetscTime(&tk));
+  tk -= t0;
+  PetscCall(KSPGetIterationNumber(ksp, &its));
+  PetscCall(KSPGetConvergedReason(ksp, &reason));
+  PetscCall(KSPGetResidualNorm(ksp, &rnorm));
+  printf("REFBENCH n=%d rows=%d nnz=%lld matmult_s=%.6f ksp_its=%d ksp_s=%.6f reason=%d rnorm=%.12e\n", n, (int)N, (long long)nnz, tm, (int)its, tk, (int)reason, (double)rnorm);
+  PetscCall(KSPDestroy(&ksp));
+  PetscCall(VecDestroy(&u)); PetscCall(VecDestroy(&b)); PetscCall(VecDestroy(&x));
+  PetscCall(MatDestroy(&A));
+  PetscCall(PetscFree3(ai, aj, aa));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
 
 static void *rd(const char *dir, const char *name, size_t bytes)
 {
@@ -52,6 +102,11 @@ int main(int argc, char **argv)
   if (argc < 2) return 1;
   dir = argv[1];
   PetscCall(PetscInitialize(&argc, &argv, NULL, NULL));
+  if (!strcmp(dir, "-bench7")) {
+    PetscCall(bench7(atoi(argv[2])));
+    PetscCall(PetscFinalize());
+    return 0;
+  }
   {
     char  p[4096];
     FILE *f;
