@@ -49,6 +49,7 @@ class ClockSampler:
     def __init__(self, gpu):
         self.gpu = gpu
         self.rows = []
+        self.first = 0
         self.p = None
 
     def start(self):
@@ -64,6 +65,10 @@ class ClockSampler:
         for line in self.p.stdout:
             self.rows.append(line.strip().split(", "))
 
+    def mark(self):
+        """Only samples taken after this call count (the sampler is started early: nvidia-smi needs ~0.5 s to start)."""
+        self.first = len(self.rows)
+
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -74,7 +79,7 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -178,10 +183,11 @@ def run_product(a, D):
         assert ksp.its() == RESTART * cycles, (ksp.its(), ksp.reason())
 
     timer = _capi.Timer(Hh)
-    solve(max(W, 1))                       # warm-up (also allocates the Krylov basis)
     clocks = ClockSampler(D.local)
-    D.barrier(); Hh_sync(L, H)
     clocks.start()
+    solve(max(W, 1))                       # warm-up (also allocates the Krylov basis)
+    D.barrier(); Hh_sync(L, H)
+    clocks.mark()
     l0 = _capi.launch_count()
     timer.start()
     solve(K)

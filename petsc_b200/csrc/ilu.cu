@@ -32,6 +32,7 @@ struct b200IluPlan_s {
   int    *d_bi, *d_bj, *d_bdiag;     /* factor layout */
   double *d_ba;
   int    *d_orderL, *d_orderU;       /* rows in level order, -1 padded to warp multiples */
+  int4   *d_metaL, *d_metaU;         /* per slot: (row, first entry, end entry, 0) of the sweep's row segment */
   int     nslotL, nslotU;
   int    *d_flag;                    /* per-row ready epoch (numeric factorisation) */
   double *d_tmp;                     /* result of the lower sweep */
@@ -104,7 +105,7 @@ __device__ __forceinline__ void st_relaxed_f64(double *p, double v)
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(u) : "memory");
 }
 __device__ int g_ilu_backoff_ns = 0; /* tunable: PETSCB200_ILU_BACKOFF_NS (0 = pure spinning; measured best) */
-static int     g_ilu_lookahead = 2, g_ilu_batch = 1; /* tunables: PETSCB200_ILU_LOOKAHEAD, PETSCB200_ILU_BATCH */
+static int     g_ilu_lookahead = 2, g_ilu_batch = 1, g_ilu_pipe = 1; /* tunables: PETSCB200_ILU_LOOKAHEAD, PETSCB200_ILU_BATCH */
 
 /* Warp-convergent wait: every lane polls its own dependency (or nothing), the warp loops until ALL its lanes have seen a
    value.  The rows of one warp-chunk belong to one level, so they become ready together; a convergent loop issues one
@@ -308,7 +309,7 @@ extern "C" int b200Ilu0Destroy(b200IluPlan p)
 {
   if (!p) return 0;
   cudaFree(p->d_ai); cudaFree(p->d_adiag); cudaFree(p->d_bi); cudaFree(p->d_bj); cudaFree(p->d_bdiag); cudaFree(p->d_ba);
-  cudaFree(p->d_orderL); cudaFree(p->d_orderU); cudaFree(p->d_flag); cudaFree(p->d_ticket); cudaFree(p->d_tmp);
+  cudaFree(p->d_orderL); cudaFree(p->d_orderU); cudaFree(p->d_metaL); cudaFree(p->d_metaU); cudaFree(p->d_flag); cudaFree(p->d_ticket); cudaFree(p->d_tmp);
   free(p->h_bi); free(p->h_bj); free(p->h_bdiag);
   free(p);
   return 0;
@@ -405,6 +406,22 @@ extern "C" int b200Ilu0Symbolic(b200Handle h, int n, const int *ai, const int *a
   UP(d_bj, bj, nnz, int);
   UP(d_orderL, orderL, p->nslotL, int);
   UP(d_orderU, orderU, p->nslotU, int);
+  { /* packed per-slot records for the sweeps: one coalesced 16-byte load replaces the order[] -> bi[]/bdiag[] chain */
+    int4 *mL = (int4 *)malloc(sizeof(int4) * ((size_t)p->nslotL + 1)), *mU = (int4 *)malloc(sizeof(int4) * ((size_t)p->nslotU + 1));
+    B200_CHECK(mL && mU, B200_ERR_MEM, "out of host memory");
+    for (int s2 = 0; s2 < p->nslotL; s2++) {
+      int i2 = orderL[s2];
+      mL[s2] = i2 < 0 ? make_int4(-1, 0, 0, 0) : make_int4(i2, bi[i2], bi[i2 + 1], 0);
+    }
+    for (int s2 = 0; s2 < p->nslotU; s2++) {
+      int i2 = orderU[s2];
+      mU[s2] = i2 < 0 ? make_int4(-1, 0, 0, 0) : make_int4(i2, bdiag[i2 + 1] + 1, bdiag[i2], 0);
+    }
+    UP(d_metaL, mL, p->nslotL, int4);
+    UP(d_metaU, mU, p->nslotU, int4);
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    free(mL); free(mU);
+  }
 #undef UP
   B200_CUDA(cudaMalloc(&p->d_ba, sizeof(double) * ((size_t)nnz + 64)));
   B200_CUDA(cudaMalloc(&p->d_tmp, sizeof(double) * ((size_t)n + 64)));
@@ -471,6 +488,100 @@ extern "C" int b200Ilu0Numeric(b200Handle h, b200IluPlan p, const double *d_aval
   return 0;
 }
 
+/* Software-pipelined sweep: every warp keeps THREE tickets in flight -- stage A (two ahead): ticket + packed row record;
+   stage B (one ahead): the first G factor entries, their column indices, the right-hand side and the inverted diagonal;
+   stage C: wait for the dependencies, accumulate strictly left to right, publish.  The three dependent global-memory
+   round trips of a chunk (ticket, record, entries) are thereby overlapped with the previous chunks' waits; what stays on
+   the per-level critical path is the poll + the ordered subtraction + the publishing store.  Deadlock-free: a warp works
+   through its tickets in increasing order and only ever waits on rows with a smaller slot. */
+template <int G, bool UPPER>
+__global__ void __launch_bounds__(ILU_TPB) ilu_sweep_pipe_kernel(int nslot, const int4 *__restrict__ meta, const int *__restrict__ bj, const double *__restrict__ ba, const double *__restrict__ rhs, double *out, int *ticket)
+{
+  constexpr int  RPW   = 32 / G;
+  const int      gl    = threadIdx.x % G;
+  const int      grp   = (threadIdx.x & 31) / G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+  auto record = [&](int tk) -> int4 {
+    const int64_t slot = (int64_t)tk * RPW + grp;
+    return slot < nslot ? __ldg(meta + slot) : make_int4(-1, 0, 0, 0);
+  };
+  /* chunk sequence of this warp: with a co-resident grid (cooperative launch) the static round-robin w, w+W, w+2W, ...
+     needs no atomics at all -- a single ticket counter serialises at ~0.6 G atomics/s, which was the whole cost of the
+     ticketed version at 256^3 (8.4 M tickets = 14 ms); ticket != NULL keeps the dynamic fallback */
+  const int wid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), W = (int)((gridDim.x * blockDim.x) >> 5);
+  int       seq = 0;
+  auto next_chunk = [&]() -> int {
+    if (ticket) return warp_ticket(ticket);
+    const int64_t t = (int64_t)wid + (int64_t)(seq++) * W;
+    return t > 2147483000LL ? 2147483000 : (int)t;
+  };
+  int  tkC = next_chunk();
+  int4 mC  = record(tkC);
+  int  tkB = next_chunk();
+  int4 mB  = record(tkB);
+  /* stage-B loads of the first chunk */
+  int    cC = 0;
+  double aC = 0.0, rC = 0.0, dC = 0.0;
+  if (mC.x >= 0) {
+    rC = rhs[mC.x];
+    if (UPPER) dC = ba[mC.z];
+    if (mC.y + gl < mC.z) {
+      cC = bj[mC.y + gl];
+      aC = ba[mC.y + gl];
+    }
+  }
+  for (;;) {
+    if ((int64_t)tkC * RPW >= nslot) break; /* warp-uniform */
+    /* stage A for the chunk two ahead, stage B for the chunk one ahead */
+    const int  tkA = next_chunk();
+    const int4 mA  = record(tkA);
+    int        cB = 0;
+    double     aB = 0.0, rB = 0.0, dB = 0.0;
+    if (mB.x >= 0) {
+      rB = rhs[mB.x];
+      if (UPPER) dB = ba[mB.z];
+      if (mB.y + gl < mB.z) {
+        cB = bj[mB.y + gl];
+        aB = ba[mB.y + gl];
+      }
+    }
+    /* stage C */
+    {
+      const bool valid = mC.x >= 0;
+      const int  ks = mC.y, ke = valid ? mC.z : mC.y;
+      double     sum = rC;
+      int        nchunk = (ke - ks + G - 1) / G;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nchunk = max(nchunk, __shfl_xor_sync(0xffffffffu, nchunk, o));
+      for (int c = 0; c < nchunk; c++) {
+        const int  k0  = ks + c * G, k = k0 + gl;
+        const bool act = k < ke;
+        int        col = cC;
+        double     a   = aC;
+        if (c > 0 && act) { /* rows longer than G entries: later chunks are fetched on the fly */
+          col = bj[k];
+          a   = ba[k];
+        }
+        double p = wait_value_warp(out + (act ? col : 0), act);
+        if (act) p = __dmul_rn(a, p);
+        const int cnt = min(G, ke - k0);
+#pragma unroll
+        for (int l = 0; l < G; l++) {
+          const double pl = __shfl_sync(gmask, p, l, G);
+          if (l < cnt) sum = __dsub_rn(sum, pl); /* strict left-to-right, FMA-free */
+        }
+      }
+      if (valid && gl == 0) {
+        if (UPPER) sum = __dmul_rn(sum, dC);
+        st_relaxed_f64(out + mC.x, sum);
+      }
+    }
+    __syncwarp();
+    tkC = tkB; mC = mB; cC = cB; aC = aB; rC = rB; dC = dB;
+    tkB = tkA; mB = mA;
+  }
+}
+
 static int ilu_set_backoff(void)
 {
   static int done = 0;
@@ -482,6 +593,7 @@ static int ilu_set_backoff(void)
     }
     if ((e = getenv("PETSCB200_ILU_LOOKAHEAD")) && atoi(e) > 0) g_ilu_lookahead = atoi(e);
     if ((e = getenv("PETSCB200_ILU_BATCH")) && atoi(e) > 0) g_ilu_batch = atoi(e);
+    if ((e = getenv("PETSCB200_ILU_PIPE"))) g_ilu_pipe = atoi(e);
     done = 1;
   }
   return 0;
@@ -495,10 +607,35 @@ static int sweeps_launch(b200Handle h, b200IluPlan p, const double *b, double *x
   B200_CUDA(cudaMemsetAsync(p->d_ticket, 0, 64, h->stream));
   B200_CUDA(cudaMemsetAsync(p->d_tmp, 0xFF, sizeof(double) * (size_t)p->n, h->stream)); /* sentinel fill */
   B200_CUDA(cudaMemsetAsync(x, 0xFF, sizeof(double) * (size_t)p->n, h->stream));
-  ilu_sweep_kernel<G, false><<<gridL, ILU_TPB, 0, h->stream>>>(p->nslotL, p->d_orderL, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, b, p->d_tmp, p->d_ticket, g_ilu_batch);
-  B200_KERNEL_CHECK();
-  ilu_sweep_kernel<G, true><<<gridU, ILU_TPB, 0, h->stream>>>(p->nslotU, p->d_orderU, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, p->d_tmp, x, p->d_ticket + 1, g_ilu_batch);
-  B200_KERNEL_CHECK();
+  if (g_ilu_pipe) {
+    /* co-resident persistent grid: cudaLaunchCooperativeKernel fails rather than deadlocks if the grid does not fit */
+    static int occ = 0, coop = -1;
+    if (!occ) {
+      B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ilu_sweep_pipe_kernel<G, true>, ILU_TPB, 0));
+      if (occ < 1) occ = 1;
+      B200_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    }
+    int gL = gridL, gU = gridU;
+    if (gL > occ * h->num_sms) gL = occ * h->num_sms;
+    if (gU > occ * h->num_sms) gU = occ * h->num_sms;
+    int          *tkL = coop == 1 ? NULL : p->d_ticket, *tkU = coop == 1 ? NULL : p->d_ticket + 1;
+    const double *rhsL = b, *rhsU = p->d_tmp;
+    double       *outL = p->d_tmp, *outU = x;
+    void *argsL[] = {&p->nslotL, &p->d_metaL, &p->d_bj, &p->d_ba, &rhsL, &outL, &tkL};
+    void *argsU[] = {&p->nslotU, &p->d_metaU, &p->d_bj, &p->d_ba, &rhsU, &outU, &tkU};
+    if (coop == 1) {
+      B200_CUDA(cudaLaunchCooperativeKernel((void *)ilu_sweep_pipe_kernel<G, false>, dim3(gL), dim3(ILU_TPB), argsL, 0, h->stream));
+      B200_CUDA(cudaLaunchCooperativeKernel((void *)ilu_sweep_pipe_kernel<G, true>, dim3(gU), dim3(ILU_TPB), argsU, 0, h->stream));
+    } else {
+      B200_CUDA(cudaLaunchKernel((void *)ilu_sweep_pipe_kernel<G, false>, dim3(gL), dim3(ILU_TPB), argsL, 0, h->stream));
+      B200_CUDA(cudaLaunchKernel((void *)ilu_sweep_pipe_kernel<G, true>, dim3(gU), dim3(ILU_TPB), argsU, 0, h->stream));
+    }
+  } else {
+    ilu_sweep_kernel<G, false><<<gridL, ILU_TPB, 0, h->stream>>>(p->nslotL, p->d_orderL, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, b, p->d_tmp, p->d_ticket, g_ilu_batch);
+    B200_KERNEL_CHECK();
+    ilu_sweep_kernel<G, true><<<gridU, ILU_TPB, 0, h->stream>>>(p->nslotU, p->d_orderU, p->d_bi, p->d_bdiag, p->d_bj, p->d_ba, p->d_tmp, x, p->d_ticket + 1, g_ilu_batch);
+    B200_KERNEL_CHECK();
+  }
   B200_LAUNCHED(2);
   return 0;
 }

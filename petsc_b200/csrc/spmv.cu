@@ -47,6 +47,7 @@ struct b200CsrPlan_s {
   int        user_lanes, user_rows, user_stages, user_ctas;
   int        max_tile_nnz[16]; /* for R = 8 << k */
   int        hints;            /* bit0: CSR streams evict_first, bit1: x evict_last */
+  int        hints_auto;
 };
 
 /* ------------------------------------------------------------------ PTX helpers: mbarrier + 1-D TMA bulk copy */
@@ -366,6 +367,12 @@ static int plan_configure(b200CsrPlan p)
   }
   StageLayout L  = stage_layout(R, cap);
   p->lanes       = G;
+  /* L2 hints (measured, profiles/round1_notes.md): stencil-like matrices (G = 1): x evict_last only (2); matrices with
+     scattered columns: also stream val/col as evict_first (3) so the gathered x keeps more of the L2 */
+  if (p->hints < 0 || p->hints_auto) {
+    p->hints      = (G == 1) ? 2 : 3;
+    p->hints_auto = 1;
+  }
   p->rows_tile   = R;
   p->cap         = cap;
   p->stages      = S;
@@ -388,7 +395,7 @@ extern "C" int b200CsrPlanCreate(b200Handle h, int m, int n, int64_t nnz, const 
   b200CsrPlan p = (b200CsrPlan)calloc(1, sizeof(*p));
   B200_CHECK(p, B200_ERR_MEM, "out of host memory");
   p->m = m; p->n = n; p->nnz = nnz; p->d_rowptr = d_rowptr; p->d_colidx = d_colidx; p->num_sms = h->num_sms;
-  p->hints = 2; /* x evict_last only: best of the four combinations on the 512^3 7-point operator */
+  p->hints = -1; /* auto, see plan_configure */
   if (m > 0) {
     int *d_stats;
     int  hstats[17];
@@ -430,7 +437,8 @@ extern "C" int b200CsrPlanSetCacheHints(b200CsrPlan p, int hints)
 {
   B200_CHECK(p, B200_ERR_ARG_NULL, "null plan");
   B200_CHECK(hints >= 0 && hints <= 3, B200_ERR_ARG_OUTOFRANGE, "hints must be 0..3");
-  p->hints = hints;
+  p->hints      = hints;
+  p->hints_auto = 0;
   return 0;
 }
 
