@@ -334,6 +334,11 @@ def cpu_baseline(a, quick=False, steps=1, warmup=0):
     port = {"value": round(RESTART / dt * scale, 4), "unit": "iterations/s (512^3 unit)", "cores": thr, "kind": "port",
             "sample": "oracle GMRES(30)+Jacobi (OpenMP, all host cores), 7-pt %d^3 (%d rows), %d cycle(s) of 30 iterations, %.2f s per cycle, scaled by rows %d^3/%d^3" % (ns, N, steps, dt, ns, a.n),
             "spmv_gflops": round((2 * len(aj) - N) / spmv_s / 1e9, 3), "seconds_per_step_sample": round(dt, 3)}
+    try:  # a container CPU quota (cgroup cpu.max) caps what "all host cores" can deliver: record it next to the number
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        port["cgroup_cpu_quota_cores"] = None if q == "max" else round(float(q) / float(per), 2)
+    except Exception:
+        pass
     ref = reference_1core(a)
     if ref is None:
         return port
