@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--what", default="3,5,1")
     ap.add_argument("--n27", type=int, default=256)
     ap.add_argument("--nrand", type=int, default=10_000_000)
+    ap.add_argument("--n7", type=int, default=384)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     L = _capi.lib()
@@ -121,8 +122,45 @@ def main():
         res["config3_cg_ilu0_27pt"] = dict(n=n, rows=N, nnz=nnz, iterations=its, reason=ksp.reason(), max_error=err, first_solve_incl_setup_s=first, solve_ms=solve_ms,
                                            ms_per_iteration=solve_ms / max(its, 1), iterations_per_sec=its / (solve_ms * 1e-3), spmv_ms=spmv_ms, spmv_gbs=alg_spmv / spmv_ms / 1e6,
                                            pcapply_ilu_ms=pcapply_ms, sptrsv_gbs=alg_sptrsv / pcapply_ms / 1e6, sptrsv_frac_of_peak=alg_sptrsv / pcapply_ms / 1e6 / peak,
-                                           levels=3 * n + 4 * (n - 1) - 2 if True else None)
+                                           levels=3 * n + 4 * (n - 1) - 2, rows_per_group=os.environ.get("PETSCB200_ILU_ROWS_PER_GROUP", "auto"))
         print("config3", res["config3_cg_ilu0_27pt"], flush=True)
+        ksp.destroy(); A.destroy()
+
+    if "4" in what:
+        # the per-rank block of config 4 (GMRES(30) + PCBJACOBI/ILU(0), 7-point): ILU(0) of the 7-point operator, PCApply timing
+        n = a.n7
+        N = n ** 3
+        nnz = C.c_int64()
+        _capi.check(L.b200GenLaplace7Nnz(n, n, n, C.c_int64(0), C.c_int64(N), C.byref(nnz)))
+        nnz = nnz.value
+        d_i, d_j, d_a = _capi.DeviceArray(Hh, N + 1, np.int32), _capi.DeviceArray(Hh, nnz, np.int32), _capi.DeviceArray(Hh, nnz, np.float64)
+        _capi.check(L.b200GenLaplace7(H, n, n, n, C.c_int64(0), C.c_int64(N), d_i.ptr, d_j.ptr, d_a.ptr))
+        petsc.options_clear()
+        petsc.options_insert("-ksp_type gmres -pc_type ilu -ksp_rtol 1e-8 -ksp_max_it 60")
+        A = petsc.Mat.create(m=N, n=N, M=N, N=N, comm=petsc.COMM_SELF)
+        A.set_csr_device(d_i.ptr, d_j.ptr, d_a.ptr)
+        for o in (d_i, d_j, d_a):
+            o.free()
+        x, b = A.create_vecs()
+        u = x.duplicate(); u.set(1.0); A.mult(u, b)
+        ksp = petsc.KSP.create(petsc.COMM_SELF)
+        ksp.set_operators(A); ksp.set_from_options()
+        t0 = time.time()
+        ksp.solve(b, x)
+        _capi.check(L.b200Synchronize(H))
+        first = time.time() - t0
+        its = ksp.its()
+        t = _capi.Timer(Hh)
+        t.start(); ksp.solve(b, x); t.stop()
+        pc = ksp.get_pc()
+        y = x.duplicate()
+        pcapply_ms = timed(lambda: pc.apply(b, y), 10)
+        alg_sptrsv = nnz * 12 + N * (4 + 4 + 4 + 4 + 8 * 3)
+        res["config4_block_gmres_ilu0_7pt"] = dict(n=n, rows=N, nnz=nnz, iterations=its, reason=ksp.reason(), first_solve_incl_setup_s=first, solve_ms=t.ms(),
+                                                   ms_per_iteration=t.ms() / max(its, 1), pcapply_ilu_ms=pcapply_ms, levels=3 * (n - 1) + 1,
+                                                   sptrsv_gbs=alg_sptrsv / pcapply_ms / 1e6, sptrsv_frac_of_peak=alg_sptrsv / pcapply_ms / 1e6 / peak,
+                                                   rows_per_group=os.environ.get("PETSCB200_ILU_ROWS_PER_GROUP", "auto"))
+        print("config4", res["config4_block_gmres_ilu0_7pt"], flush=True)
         ksp.destroy(); A.destroy()
 
     if "1" in what:
