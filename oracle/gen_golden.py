@@ -93,6 +93,45 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
         print(name, "ok")
 
+    # ---- COO assembly (MatSetPreallocationCOO / MatSetValuesCOO): repeats, negative (ignored) indices, sorted and unsorted input
+    crng = np.random.default_rng(20260924)
+    coo = {
+        "coo_rand_60x45": (60, 45, 4000, "random"),      # ~1.5 repeats per entry on average, up to ~7: pins the summation order
+        "coo_rowsorted_33": (33, 33, 900, "rowsorted"),   # rows arrive sorted: the row sort is skipped (aij.c:4558)
+        "coo_fem_q1_7x6": (56, 56, 0, "fem"),             # Q1 element loop on a 7x6 node grid: 16 entries per element, up to 4 repeats
+        "coo_empty_rows": (20, 20, 30, "random"),
+    }
+    for name, (M, N, n, kind) in coo.items():
+        if kind == "fem":
+            nx, ny = 7, 8
+            ii, jj = [], []
+            for ey in range(ny - 1):
+                for ex in range(nx - 1):
+                    nodes = [ey * nx + ex, ey * nx + ex + 1, (ey + 1) * nx + ex, (ey + 1) * nx + ex + 1]
+                    for a_ in nodes:
+                        for b_ in nodes:
+                            ii.append(a_); jj.append(b_)
+            ci, cj = np.array(ii, np.int32), np.array(jj, np.int32)
+            n = len(ci)
+        else:
+            ci = crng.integers(-1, M, n).astype(np.int32)
+            cj = crng.integers(-1, N, n).astype(np.int32)
+            if kind == "rowsorted":
+                ci = np.sort(ci[ci >= 0]).astype(np.int32); cj = cj[:len(ci)]; n = len(ci)
+        v1, v2 = crng.uniform(-1, 1, n), crng.uniform(-1, 1, n)
+        env = dict(os.environ)
+        env["LD_LIBRARY_PATH"] = "%s/%s/lib:%s:%s" % (PETSC_DIR, PETSC_ARCH, BLASDIR, env.get("LD_LIBRARY_PATH", ""))
+        with tempfile.TemporaryDirectory() as d:
+            for fn, arr in (("coo_i.i32", ci), ("coo_j.i32", cj), ("v1.f64", v1), ("v2.f64", v2)):
+                np.ascontiguousarray(arr).tofile(os.path.join(d, fn))
+            open(os.path.join(d, "meta_coo.txt"), "w").write("%d %d %d\n" % (M, N, n))
+            subprocess.check_call([exe, "-coo", d], env=env)
+            rec = dict(M=M, N=N, coo_i=ci, coo_j=cj, v1=v1, v2=v2,
+                       ref_ai=np.fromfile(os.path.join(d, "ref_ai.i32"), np.int32), ref_aj=np.fromfile(os.path.join(d, "ref_aj.i32"), np.int32),
+                       ref_aa1=np.fromfile(os.path.join(d, "ref_aa1.f64")), ref_aa2=np.fromfile(os.path.join(d, "ref_aa2.f64")))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print(name, "n", n, "nnz", len(rec["ref_aj"]))
+
     # ---- KSP cases: matrix by generator, b = A*1, reference options recorded ----
     ksp = {
         # ex2_1.out: -m 5 -n 5 -ksp_gmres_cgs_refinement_type refine_always, default PC (ILU), ex2.c rtol = 1e-2/((m+1)(n+1))

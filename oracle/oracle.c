@@ -789,3 +789,133 @@ int ora_ksp_cg(int n, const int *ai, const int *aj, const double *aa, const doub
   pc_destroy(&pc);
   return 0;
 }
+
+/* ================================================================================================================== */
+/* widening rows: transposed product and COO assembly                                                                 */
+/* ================================================================================================================== */
+void ora_matmulttranspose_seqaij(int m, int n, const int *ai, const int *aj, const double *aa, const double *x, const double *z, double *y)
+{
+  for (int c = 0; c < n; c++) y[c] = z ? z[c] : 0.0;
+  for (int i = 0; i < m; i++) {
+    const double alpha = x[i];
+    for (int k = ai[i]; k < ai[i + 1]; k++) {
+      const double p = alpha * aa[k];
+      y[aj[k]] = y[aj[k]] + p;
+    }
+  }
+}
+
+/* the reference's quicksort on a key array with one or two companion arrays (sorti.c:198-240); the permutation it produces
+   for equal keys is part of MatSetValuesCOO's summation order, so the recursion, the pivot choice and the partition are
+   followed exactly: Y may be NULL (two-array variant) */
+static int64_t coo_median_pos(const int *X, int64_t hi)
+{
+  const int64_t a = hi / 4, b = hi / 2, c = hi / 4 * 3;
+  if (X[a] < X[b]) {
+    if (X[b] < X[c]) return b;
+    return X[a] < X[c] ? c : a;
+  }
+  if (X[c] < X[b]) return b;
+  return X[a] < X[c] ? a : c;
+}
+static void coo_swap(int *X, int *Y, int64_t *Z, int64_t p, int64_t q)
+{
+  int     t = X[p];
+  int64_t u = Z[p];
+  X[p] = X[q]; X[q] = t;
+  Z[p] = Z[q]; Z[q] = u;
+  if (Y) { t = Y[p]; Y[p] = Y[q]; Y[q] = t; }
+}
+static void coo_quicksort(int64_t n, int *X, int *Y, int64_t *Z)
+{
+  const int64_t hi = n - 1;
+  if (n < 8) {
+    for (int64_t i = 0; i < n; i++) {
+      int pivot = X[i];
+      for (int64_t j = i + 1; j < n; j++) {
+        if (pivot > X[j]) {
+          coo_swap(X, Y, Z, i, j);
+          pivot = X[i];
+        }
+      }
+    }
+    return;
+  }
+  const int pivot = X[coo_median_pos(X, hi)];
+  int64_t   l = 0, r = hi;
+  for (;;) {
+    while (X[l] < pivot) l++;
+    while (X[r] > pivot) r--;
+    if (l >= r) { r++; break; }
+    coo_swap(X, Y, Z, l, r);
+    l++; r--;
+  }
+  coo_quicksort(l, X, Y, Z);
+  coo_quicksort(hi - r + 1, X + r, Y ? Y + r : NULL, Z + r);
+}
+
+int ora_coo_prealloc(int M, int N, int64_t coo_n, const int *coo_i, const int *coo_j, int *Ai, int *Aj, int64_t *jmap, int64_t *perm,
+                     int64_t *nnz_out, int64_t *atot_out)
+{
+  int     *i = (int *)malloc(sizeof(int) * (size_t)(coo_n + 1)), *j = (int *)malloc(sizeof(int) * (size_t)(coo_n + 1));
+  int64_t *pm = (int64_t *)malloc(sizeof(int64_t) * (size_t)(coo_n + 1));
+  int64_t  k, q = 0, nnz = 0, nneg;
+  int      sorted = 1, prev = INT32_MIN, rc = 0;
+  for (k = 0; k < coo_n; k++) {
+    i[k] = coo_j[k] < 0 ? -1 : coo_i[k];
+    j[k] = coo_j[k];
+    if (sorted) {
+      if (i[k] < prev) sorted = 0;
+      else prev = i[k];
+    }
+    pm[k] = k;
+  }
+  if (!sorted) coo_quicksort(coo_n, i, j, pm);
+  if (coo_n && i[coo_n - 1] >= M) { rc = 1; goto done; }
+  for (k = 0; k < coo_n; k++)
+    if (i[k] >= 0) break;
+  nneg = k;
+  for (int r = 0; r <= M; r++) Ai[r] = 0;
+  while (k < coo_n) {
+    const int     row = i[k];
+    const int64_t start = k;
+    int           jprev = INT32_MIN, strict = 1;
+    while (k < coo_n && i[k] == row) {
+      if (strict) {
+        if (j[k] <= jprev) strict = 0;
+        else jprev = j[k];
+      }
+      k++;
+    }
+    if (!strict) coo_quicksort(k - start, j + start, NULL, pm + start);
+    if (k > start && j[k - 1] >= N) { rc = 2; goto done; }
+    /* unique columns of this row; jmap[q+1] first holds the repeat count of the q-th nonzero */
+    for (int64_t p = start; p < k; p++) {
+      if (p == start || j[p] != j[p - 1]) {
+        Aj[q]       = j[p];
+        jmap[q + 1] = 1;
+        Ai[row + 1]++;
+        q++;
+        nnz++;
+      } else jmap[q]++;
+    }
+  }
+  for (int r = 0; r < M; r++) Ai[r + 1] += Ai[r];
+  jmap[0] = 0;
+  for (k = 0; k < nnz; k++) jmap[k + 1] += jmap[k];
+  for (k = 0; k < coo_n - nneg; k++) perm[k] = pm[k + nneg];
+  *nnz_out  = nnz;
+  *atot_out = coo_n - nneg;
+done:
+  free(i); free(j); free(pm);
+  return rc;
+}
+
+void ora_coo_setvalues(int64_t nnz, const int64_t *jmap, const int64_t *perm, const double *v, int insert, double *Aa)
+{
+  for (int64_t q = 0; q < nnz; q++) {
+    double sum = 0.0;
+    for (int64_t k = jmap[q]; k < jmap[q + 1]; k++) sum += v[perm[k]];
+    Aa[q] = (insert ? 0.0 : Aa[q]) + sum;
+  }
+}

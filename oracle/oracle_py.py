@@ -229,5 +229,37 @@ def ksp_solve(ksp_type, ai, aj, aa, b, pc="ilu", restart=30, refine="never", max
     return x, dict(its=res.its, reason=res.reason, rnorm=res.rnorm, hist=hist[:min(res.nhist, cap)].copy())
 
 
+def matmulttranspose(ai, aj, aa, x, n=None, z=None):
+    """MatMultTranspose[Add]_SeqAIJ: y = (z or 0) + A^T x."""
+    m = len(ai) - 1
+    n = m if n is None else n
+    x = _f64(x); y = np.empty(n)
+    zz = None if z is None else _f64(z)
+    lib().ora_matmulttranspose_seqaij(m, n, _p(_i32(ai)), _p(_i32(aj)), _p(_f64(aa)), _p(x), None if zz is None else _p(zz), _p(y))
+    return y
+
+
+def coo_prealloc(M, N, coo_i, coo_j):
+    """MatSetPreallocationCOO_SeqAIJ -> (Ai, Aj, jmap, perm) in the reference's own order."""
+    ci, cj = _i32(coo_i), _i32(coo_j)
+    n = len(ci)
+    Ai = np.empty(M + 1, np.int32); Aj = np.empty(max(n, 1), np.int32)
+    jmap = np.empty(n + 1, np.int64); perm = np.empty(max(n, 1), np.int64)
+    nnz = C.c_int64(); atot = C.c_int64()
+    rc = lib().ora_coo_prealloc(M, N, C.c_int64(n), _p(ci), _p(cj), _p(Ai), _p(Aj), _p(jmap), _p(perm), C.byref(nnz), C.byref(atot))
+    if rc:
+        raise ValueError("COO %s index out of range" % ("row" if rc == 1 else "column"))
+    return Ai, Aj[:nnz.value].copy(), jmap[:nnz.value + 1].copy(), perm[:atot.value].copy()
+
+
+def coo_setvalues(jmap, perm, v, Aa=None):
+    """MatSetValuesCOO_SeqAIJ: INSERT_VALUES when Aa is None, else ADD_VALUES onto a copy of Aa."""
+    nnz = len(jmap) - 1
+    out = np.zeros(nnz) if Aa is None else _f64(Aa).copy()
+    jm = np.ascontiguousarray(jmap, dtype=np.int64); pm = np.ascontiguousarray(perm, dtype=np.int64)
+    lib().ora_coo_setvalues(C.c_int64(nnz), _p(jm), _p(pm), _p(_f64(v)), 1 if Aa is None else 0, _p(out))
+    return out
+
+
 def max_threads():
     return lib().ora_max_threads()

@@ -65,6 +65,55 @@ static PetscErrorCode bench7(int n)
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
+static void *rd(const char *dir, const char *name, size_t bytes);
+static void  wr(const char *dir, const char *name, const void *buf, size_t bytes);
+
+/* -coo <dir>: MatSetPreallocationCOO + MatSetValuesCOO(INSERT) + MatSetValuesCOO(ADD) through the public API; the CSR the
+   reference builds and both value arrays are written back (the values pin the reference's summation order of repeats) */
+static PetscErrorCode coo_case(const char *dir)
+{
+  int                M, N;
+  long               n;
+  PetscInt          *ci, *cj;
+  const PetscInt    *ia, *ja;
+  PetscScalar       *v1, *v2;
+  const PetscScalar *a;
+  PetscInt           nr;
+  PetscBool          done;
+  Mat                A;
+  char               p[4096];
+  FILE              *f;
+
+  PetscFunctionBeginUser;
+  snprintf(p, sizeof p, "%s/meta_coo.txt", dir);
+  f = fopen(p, "r");
+  if (!f || fscanf(f, "%d %d %ld", &M, &N, &n) != 3) exit(2);
+  fclose(f);
+  ci = (PetscInt *)rd(dir, "coo_i.i32", sizeof(PetscInt) * (size_t)n);
+  cj = (PetscInt *)rd(dir, "coo_j.i32", sizeof(PetscInt) * (size_t)n);
+  v1 = (PetscScalar *)rd(dir, "v1.f64", sizeof(PetscScalar) * (size_t)n);
+  v2 = (PetscScalar *)rd(dir, "v2.f64", sizeof(PetscScalar) * (size_t)n);
+  PetscCall(MatCreate(PETSC_COMM_SELF, &A));
+  PetscCall(MatSetSizes(A, M, N, M, N));
+  PetscCall(MatSetType(A, MATSEQAIJ));
+  PetscCall(MatSetPreallocationCOO(A, (PetscCount)n, ci, cj));
+  PetscCall(MatSetValuesCOO(A, v1, INSERT_VALUES));
+  PetscCall(MatGetRowIJ(A, 0, PETSC_FALSE, PETSC_FALSE, &nr, &ia, &ja, &done));
+  wr(dir, "ref_ai.i32", ia, sizeof(PetscInt) * (size_t)(M + 1));
+  wr(dir, "ref_aj.i32", ja, sizeof(PetscInt) * (size_t)ia[M]);
+  PetscCall(MatSeqAIJGetArrayRead(A, &a));
+  wr(dir, "ref_aa1.f64", a, sizeof(PetscScalar) * (size_t)ia[M]);
+  PetscCall(MatSeqAIJRestoreArrayRead(A, &a));
+  PetscCall(MatSetValuesCOO(A, v2, ADD_VALUES));
+  PetscCall(MatSeqAIJGetArrayRead(A, &a));
+  wr(dir, "ref_aa2.f64", a, sizeof(PetscScalar) * (size_t)ia[M]);
+  PetscCall(MatSeqAIJRestoreArrayRead(A, &a));
+  PetscCall(MatRestoreRowIJ(A, 0, PETSC_FALSE, PETSC_FALSE, &nr, &ia, &ja, &done));
+  PetscCall(MatDestroy(&A));
+  free(ci); free(cj); free(v1); free(v2);
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
 static void *rd(const char *dir, const char *name, size_t bytes)
 {
   char  p[4096];
@@ -107,6 +156,11 @@ int main(int argc, char **argv)
     PetscCall(PetscFinalize());
     return 0;
   }
+  if (!strcmp(dir, "-coo")) {
+    PetscCall(coo_case(argv[2]));
+    PetscCall(PetscFinalize());
+    return 0;
+  }
   {
     char  p[4096];
     FILE *f;
@@ -137,6 +191,11 @@ int main(int argc, char **argv)
     PetscCall(VecGetArrayRead(vz, &z)); wr(dir, "ref_multadd.f64", z, sizeof(PetscScalar) * m); PetscCall(VecRestoreArrayRead(vz, &z));
     PetscCall(MatGetDiagonal(A, vd));
     PetscCall(VecGetArrayRead(vd, &z)); wr(dir, "ref_diag.f64", z, sizeof(PetscScalar) * m); PetscCall(VecRestoreArrayRead(vd, &z));
+    /* MatMultTranspose / MatMultTransposeAdd */
+    PetscCall(MatMultTranspose(A, vx, vz));
+    PetscCall(VecGetArrayRead(vz, &z)); wr(dir, "ref_multtr.f64", z, sizeof(PetscScalar) * m); PetscCall(VecRestoreArrayRead(vz, &z));
+    PetscCall(MatMultTransposeAdd(A, vx, vy, vz));
+    PetscCall(VecGetArrayRead(vz, &z)); wr(dir, "ref_multtradd.f64", z, sizeof(PetscScalar) * m); PetscCall(VecRestoreArrayRead(vz, &z));
   }
   /* VecMDot / VecMAXPY / VecDot / VecNorm */
   PetscCall(PetscMalloc1(nv, &vv));
