@@ -58,6 +58,8 @@ const char *b200GetLastErrorString(void);
 const char *b200Version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
 long long   b200KernelLaunchCount(void);
+/* PetscGetMemType analogue: 1 if ptr is device (or managed) memory, 0 for host memory */
+int         b200PointerIsDevice(const void *ptr, int *is_device);
 
 /* timing on the handle's stream (cudaEvent pair; bench.py measures kernels with these, not with host clocks) */
 typedef struct b200Event_s *b200Event;
@@ -186,6 +188,41 @@ int b200HaloDestroy(b200Halo halo);
 int b200HaloBegin(b200Handle h, b200Halo halo, const double *d_x, double *d_lvec);
 /* make the main stream wait for the exchange */
 int b200HaloEnd(b200Handle h, b200Halo halo);
+
+/* ---- COO assembly ----------------------------------------------------------------------------------
+ * replaces MatSetPreallocationCOO_SeqAIJ / MatSetValuesCOO_SeqAIJ (src/mat/impls/aij/seq/aij.c:4524-4732) and the value
+ * kernel of MatSetValuesCOO_SeqAIJCUSPARSE (aijcusparse.cu).  Index arrays are DEVICE pointers; entries with a negative
+ * row or column are ignored; a row >= M or column >= N is B200_ERR_ARG_OUTOFRANGE (aij.c:4561,4631).  The plan owns the
+ * CSR pattern it builds (sorted, unique columns per row).  Repeated (i,j) pairs are added in the order of the user's
+ * array; b200CooPlanCreateFromMaps instead adopts the reference's own jmap[nnz+1] / perm[atot] (MatCOOStruct_SeqAIJ,
+ * aij.h:170-176, HOST arrays of PetscCount) and then reproduces the reference's values bit for bit. */
+typedef struct b200CooPlan_s *b200CooPlan;
+int b200CooPlanCreate(b200Handle h, int M, int N, int64_t coo_n, const int *d_coo_i, const int *d_coo_j, b200CooPlan *plan);
+int b200CooPlanCreateFromMaps(b200Handle h, int64_t nnz, int64_t atot, const int64_t *h_jmap, const int64_t *h_perm, b200CooPlan *plan);
+int b200CooPlanDestroy(b200CooPlan plan);
+/* borrowed device pointers to rowptr[M+1] / colidx[nnz] (NULL for plans made from maps); atot = number of entries kept */
+int b200CooPlanGetCsr(b200CooPlan plan, int64_t *nnz, int64_t *atot, const int **d_rowptr, const int **d_colidx);
+/* copies jmap[nnz+1] and perm[atot] to HOST arrays (tests) */
+int b200CooPlanGetMaps(b200Handle h, b200CooPlan plan, int *h_jmap, int *h_perm);
+/* a[q] = (insert ? 0 : a[q]) + (0 + v[perm[jmap[q]]] + ... )   (aij.c:4724-4728); d_v has coo_n entries */
+int b200CooSetValues(b200Handle h, b200CooPlan plan, const double *d_v, int insert, double *d_a);
+
+/* ---- transposed product ---------------------------------------------------------------------------
+ * replaces MatMultTranspose_SeqAIJ / MatMultTransposeAdd_SeqAIJ (aij.c:1383-1440; reference device path: cusparseSpMV with
+ * CUSPARSE_OPERATION_TRANSPOSE or an explicit transpose, aijcusparse.cu MatSeqAIJCUSPARSEFormExplicitTranspose).  The
+ * transposed pattern is built once on the device; b200CsrTransposeSetValues re-gathers the values after A changed;
+ * the product adds x[i]*a(i,c) into y[c] in increasing row order starting from 0 (or z[c]) exactly like the reference
+ * (with one lane per row; see b200CsrTransposeGetPlan). */
+typedef struct b200CsrTranspose_s *b200CsrTranspose;
+int b200CsrTransposeCreate(b200Handle h, int m, int n, int64_t nnz, const int *d_rowptr, const int *d_colidx, b200CsrTranspose *T);
+int b200CsrTransposeDestroy(b200CsrTranspose T);
+int b200CsrTransposeSetValues(b200Handle h, b200CsrTranspose T, const double *d_a);
+int b200CsrTransposeSpMV(b200Handle h, b200CsrTranspose T, const double *d_x, const double *d_z, double *d_y);
+/* the SpMV plan on the transposed pattern, for b200CsrPlanSetLayout: lanes_per_row = 1 is the bit-exact parity mode (as for
+   MatMult); the automatic layout uses several lanes per long row and is then exact only to rounding */
+int b200CsrTransposeGetPlan(b200CsrTranspose T, b200CsrPlan *plan);
+/* copies the transposed pattern (tptr[n+1], trow[nnz]) and the value permutation tperm[nnz] to HOST arrays (tests) */
+int b200CsrTransposeGet(b200Handle h, b200CsrTranspose T, int *h_tptr, int *h_trow, int *h_tperm);
 
 /* ---- device-side generators of the benchmark operators (bench/test utility; SURVEY 8d inputs) ---- */
 /* rows [r0,r1) of the 7-point nx*ny*nz Laplacian, local row pointer, GLOBAL 32-bit columns */

@@ -31,6 +31,7 @@ typedef double   PetscReal;
 typedef int      PetscBool;
 typedef int      MPI_Comm;       /* as MPIUNI does (include/petsc/mpiuni/mpi.h) */
 typedef int      PetscMemType;
+typedef int64_t  PetscCount;
 #define PETSC_TRUE  1
 #define PETSC_FALSE 0
 #define PETSC_SUCCESS 0
@@ -187,6 +188,12 @@ PetscErrorCode MatGetOwnershipRange(Mat mat, PetscInt *m, PetscInt *n);
 PetscErrorCode MatCreateVecs(Mat mat, Vec *right, Vec *left);                                     /* matrix.c:10069 (defaultvectype) */
 PetscErrorCode MatMult(Mat mat, Vec x, Vec y);                                                    /* matrix.c:2696 */
 PetscErrorCode MatMultAdd(Mat mat, Vec v1, Vec v2, Vec v3);
+PetscErrorCode MatMultTranspose(Mat mat, Vec x, Vec y);                /* matrix.c MatMultTranspose -> aij.c:1434 (seqaijb200 only) */
+PetscErrorCode MatMultTransposeAdd(Mat mat, Vec v1, Vec v2, Vec v3);   /* aij.c:1383 */
+/* COO assembly (matrix.c MatSetPreallocationCOO / MatSetValuesCOO -> aij.c:4524,4710): coo_i/coo_j/v may be host or device
+   arrays (detected like PetscGetMemType); negative indices are ignored; seqaijb200 only */
+PetscErrorCode MatSetPreallocationCOO(Mat A, PetscCount ncoo, PetscInt coo_i[], PetscInt coo_j[]);
+PetscErrorCode MatSetValuesCOO(Mat A, const PetscScalar coo_v[], InsertMode imode);
 PetscErrorCode MatGetDiagonal(Mat mat, Vec v);
 PetscErrorCode MatGetDiagonalBlock(Mat A, Mat *a);                                                /* mpiaij.c:2758 */
 PetscErrorCode MatDestroy(Mat *A);

@@ -6,6 +6,7 @@
 #   oracle/_ref/petsc/bin/bench_kspsolve   under /root/reference/src/ksp/ksp/tutorials/ (never copied into the repo)
 #   oracle/_ref/ref_driver                 oracle/ref_driver.c (our driver against the reference's public API)
 #   petsc_plugin/libpetscb200plugin.so     the plugin, built against exactly this PETSc
+#   oracle/_ref/petsc/bin/plugin_driver    petsc_plugin/plugin_driver.c (our PETSc program for device COO / transposed products)
 # Only runs in the build container (needs /root/reference and the configured PETSc build).  No reference SOURCE is copied.
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"; ROOT="$(dirname "$HERE")"
@@ -21,4 +22,6 @@ for ex in ex2 bench_kspsolve; do
 done
 /usr/bin/gcc -O2 -ffp-contract=off -fopenmp -o "$HERE/_ref/ref_driver" "$HERE/ref_driver.c" "$HERE/oracle.c" -I"$HERE" $INC -L$OUT/lib -lpetsc -Wl,-rpath,\$ORIGIN/petsc/lib -Wl,-rpath,$BLASDIR -Wl,-rpath-link,$BLASDIR -Wl,--allow-shlib-undefined -lm
 make -s -C "$ROOT/petsc_plugin" PETSC_DIR="$PETSC_DIR" PETSC_ARCH="$PETSC_ARCH"
+# a PETSc program for the plugin paths the tutorials do not reach (device COO, MatMultTranspose, MatBindToCPU)
+/usr/bin/gcc -O2 -o "$OUT/bin/plugin_driver" "$ROOT/petsc_plugin/plugin_driver.c" $INC -I"$ROOT/include" $LNK -L"$ROOT/petsc_b200/lib" -lpetscb200 -Wl,-rpath,\$ORIGIN/../../../../petsc_b200/lib
 echo "reference demo built in $OUT"

@@ -206,3 +206,19 @@ extern "C" int b200EventElapsedMs(b200Event a, b200Event b, double *ms)
   *ms = f;
   return 0;
 }
+
+/* PetscGetMemType analogue (include/petscdevice.h, used by MatSetPreallocationCOO/MatSetValuesCOO to accept host or device arrays) */
+extern "C" int b200PointerIsDevice(const void *ptr, int *is_device)
+{
+  B200_CHECK(is_device, B200_ERR_ARG_NULL, "null argument");
+  *is_device = 0;
+  if (!ptr) return 0;
+  cudaPointerAttributes at;
+  cudaError_t           e = cudaPointerGetAttributes(&at, ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return 0; /* unregistered host memory on old drivers */
+  }
+  *is_device = (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+  return 0;
+}

@@ -160,6 +160,10 @@ struct _MatOps { /* include/petsc/private/matimpl.h (subset) */
   PetscErrorCode (*setcsr)(Mat, const PetscInt *, const PetscInt *, const PetscScalar *, int on_device);
   /* fused MatMult + PCApply_Jacobi: w = dinv .* (A x) (the ops->applyBA hook of precon.c:810-865 lands here) */
   PetscErrorCode (*multjacobi)(Mat, Vec x, Vec dinv, Vec w);
+  PetscErrorCode (*multtranspose)(Mat, Vec, Vec);
+  PetscErrorCode (*multtransposeadd)(Mat, Vec, Vec, Vec);
+  PetscErrorCode (*setpreallocationcoo)(Mat, PetscCount, const PetscInt[], const PetscInt[]);
+  PetscErrorCode (*setvaluescoo)(Mat, const PetscScalar[], InsertMode);
 };
 typedef struct { /* Mat_SeqAIJ (aij.h:47-92) device mirror */
   PetscInt    m, n;
@@ -174,6 +178,11 @@ typedef struct { /* Mat_SeqAIJ (aij.h:47-92) device mirror */
   int    *h_i, *h_j;
   double *h_a;
   PetscInt nonzerorowcnt;
+  /* explicit transpose for MatMultTranspose (built on first use; values re-gathered when the matrix state moved on) */
+  b200CsrTranspose T;
+  int64_t          T_state;
+  /* COO assembly plan (MatSetPreallocationCOO) */
+  b200CooPlan coo;
 } Mat_SeqAIJB200;
 typedef struct { /* Mat_MPIAIJ (mpiaij.h:41-76) */
   Mat       A, B;     /* diag and off-diag blocks (seqaijb200) */
@@ -198,6 +207,7 @@ struct _p_Mat {
   COOEntry *coo;
   size_t    ncoo, coocap;
   int       spmv_layout[4];
+  int64_t   coo_n; /* length of the arrays given to MatSetPreallocationCOO */
 };
 PetscErrorCode MatCreate_SeqAIJB200(Mat A);
 PetscErrorCode PetscB200MPIAIJSplit(PetscInt m, PetscInt cstart, PetscInt cend, const PetscInt *ai, const PetscInt *aj, const PetscScalar *aa, PetscInt **Ai, PetscInt **Aj, PetscScalar **Aa, PetscInt **Bi, PetscInt **Bj, PetscScalar **Ba, PetscInt **garray, PetscInt *ec);

@@ -296,6 +296,58 @@ PetscErrorCode MatMultAdd(Mat mat, Vec v1, Vec v2, Vec v3)
   PetscCall((*mat->ops.multadd)(mat, v1, v2, v3));
   return PETSC_SUCCESS;
 }
+PetscErrorCode MatMultTranspose(Mat mat, Vec x, Vec y)
+{
+  PetscValidHeader(mat, 1);
+  PetscValidHeader(x, 2);
+  PetscValidHeader(y, 3);
+  MatCheckAssembled(mat);
+  PetscCheck(x != y, mat->hdr.comm, PETSC_ERR_ARG_IDN, "x and y must be different vectors");
+  PetscCheck(mat->ops.multtranspose, mat->hdr.comm, PETSC_ERR_SUP, "No method multtranspose for Mat of type %s", mat->hdr.type_name);
+  PetscInt nx, ny;
+  PetscCall(VecGetLocalSize(x, &nx));
+  PetscCall(VecGetLocalSize(y, &ny));
+  PetscCheck(mat->m == nx, mat->hdr.comm, PETSC_ERR_ARG_SIZ, "Mat mat,Vec x: local dim %d %d", mat->m, nx);
+  PetscCheck(mat->n == ny, mat->hdr.comm, PETSC_ERR_ARG_SIZ, "Mat mat,Vec y: local dim %d %d", mat->n, ny);
+  PetscCall((*mat->ops.multtranspose)(mat, x, y));
+  return PETSC_SUCCESS;
+}
+PetscErrorCode MatMultTransposeAdd(Mat mat, Vec v1, Vec v2, Vec v3)
+{
+  PetscValidHeader(mat, 1);
+  MatCheckAssembled(mat);
+  PetscCheck(v1 != v3, mat->hdr.comm, PETSC_ERR_ARG_IDN, "v1 and v3 must be different vectors");
+  PetscCheck(mat->ops.multtransposeadd, mat->hdr.comm, PETSC_ERR_SUP, "No method multtransposeadd for Mat of type %s", mat->hdr.type_name);
+  PetscInt n1, n2, n3;
+  PetscCall(VecGetLocalSize(v1, &n1));
+  PetscCall(VecGetLocalSize(v2, &n2));
+  PetscCall(VecGetLocalSize(v3, &n3));
+  PetscCheck(mat->m == n1 && mat->n == n2 && mat->n == n3, mat->hdr.comm, PETSC_ERR_ARG_SIZ, "Mat/Vec local dimensions do not conform");
+  PetscCall((*mat->ops.multtransposeadd)(mat, v1, v2, v3));
+  return PETSC_SUCCESS;
+}
+PetscErrorCode MatSetPreallocationCOO(Mat A, PetscCount ncoo, PetscInt coo_i[], PetscInt coo_j[])
+{
+  PetscValidHeader(A, 1);
+  PetscCheck(ncoo >= 0, A->hdr.comm, PETSC_ERR_ARG_OUTOFRANGE, "ncoo %lld overflowed or negative", (long long)ncoo);
+  PetscCall(MatPrep(A));
+  PetscCheck(A->ops.setpreallocationcoo, A->hdr.comm, PETSC_ERR_SUP, "No method setpreallocationcoo for Mat of type %s", A->hdr.type_name);
+  PetscCall((*A->ops.setpreallocationcoo)(A, ncoo, coo_i, coo_j));
+  A->coo_n     = ncoo;
+  A->assembled = 1; /* matrix.c MatSetPreallocationCOO: the pattern is final, values are zero */
+  A->hdr.state++;
+  return PETSC_SUCCESS;
+}
+PetscErrorCode MatSetValuesCOO(Mat A, const PetscScalar coo_v[], InsertMode imode)
+{
+  PetscValidHeader(A, 1);
+  PetscCheck(imode == INSERT_VALUES || imode == ADD_VALUES, A->hdr.comm, PETSC_ERR_ARG_WRONG, "InsertMode must be INSERT_VALUES or ADD_VALUES");
+  PetscCheck(A->ops.setvaluescoo, A->hdr.comm, PETSC_ERR_SUP, "No method setvaluescoo for Mat of type %s", A->hdr.type_name);
+  PetscCall((*A->ops.setvaluescoo)(A, coo_v, imode));
+  A->assembled = 1;
+  A->hdr.state++;
+  return PETSC_SUCCESS;
+}
 PetscErrorCode MatGetDiagonal(Mat mat, Vec v)
 {
   PetscValidHeader(mat, 1);
@@ -349,6 +401,11 @@ PetscErrorCode MatB200SetSpMVLayout(Mat A, PetscInt lanes, PetscInt rows, PetscI
   if (!strcmp(A->hdr.type_name, MATSEQAIJB200) && A->data) {
     Mat_SeqAIJB200 *a = (Mat_SeqAIJB200 *)A->data;
     if (a->plan) PetscCallB200(b200CsrPlanSetLayout(a->plan, lanes, rows, stages, ctas));
+    if (a->T) {
+      b200CsrPlan tp;
+      PetscCallB200(b200CsrTransposeGetPlan(a->T, &tp));
+      PetscCallB200(b200CsrPlanSetLayout(tp, lanes, rows, stages, ctas));
+    }
   } else if (!strcmp(A->hdr.type_name, MATMPIAIJB200) && A->data) {
     Mat_MPIAIJB200 *a = (Mat_MPIAIJB200 *)A->data;
     if (a->A) PetscCall(MatB200SetSpMVLayout(a->A, lanes, rows, stages, ctas));
@@ -361,6 +418,10 @@ static PetscErrorCode MatSeqAIJB200_Free(Mat_SeqAIJB200 *a)
 {
   if (a->plan) b200CsrPlanDestroy(a->plan);
   a->plan = NULL;
+  if (a->T) b200CsrTransposeDestroy(a->T);
+  a->T = NULL;
+  if (a->coo) b200CooPlanDestroy(a->coo);
+  a->coo = NULL;
   PetscCallB200(b200Free(H, a->d_i)); PetscCallB200(b200Free(H, a->d_j)); PetscCallB200(b200Free(H, a->d_a));
   PetscCallB200(b200Free(H, a->d_cr_i)); PetscCallB200(b200Free(H, a->d_cr_rindex));
   a->d_i = a->d_j = a->d_cr_i = a->d_cr_rindex = NULL;
@@ -487,6 +548,106 @@ static PetscErrorCode MatMultJacobi_SeqAIJB200(Mat A, Vec x, Vec dinv, Vec w)
   PetscCallB200(b200CsrSpMVJacobi(H, a->plan, a->d_a, dx, dd, dw, NULL));
   return PETSC_SUCCESS;
 }
+/* MatMultTranspose[Add]_SeqAIJ (aij.c:1383-1440) through the explicit transposed pattern */
+static PetscErrorCode MatTransposeSync_SeqAIJB200(Mat A)
+{
+  Mat_SeqAIJB200 *a = (Mat_SeqAIJB200 *)A->data;
+  if (!a->T) {
+    PetscCallB200(b200CsrTransposeCreate(H, a->m, a->n, a->nz, a->d_i, a->d_j, &a->T));
+    a->T_state = -1;
+    if (A->spmv_layout[0] || A->spmv_layout[1] || A->spmv_layout[2] || A->spmv_layout[3]) { /* -mat_b200_spmv_lanes etc. apply to A^T too */
+      b200CsrPlan tp;
+      PetscCallB200(b200CsrTransposeGetPlan(a->T, &tp));
+      PetscCallB200(b200CsrPlanSetLayout(tp, A->spmv_layout[0], A->spmv_layout[1], A->spmv_layout[2], A->spmv_layout[3]));
+    }
+  }
+  if (a->T_state != A->hdr.state) {
+    PetscCallB200(b200CsrTransposeSetValues(H, a->T, a->d_a));
+    a->T_state = A->hdr.state;
+  }
+  return PETSC_SUCCESS;
+}
+static PetscErrorCode MatMultTranspose_SeqAIJB200(Mat A, Vec x, Vec y)
+{
+  Mat_SeqAIJB200 *a = (Mat_SeqAIJB200 *)A->data;
+  const double   *dx;
+  double         *dy;
+  PetscCall(MatTransposeSync_SeqAIJB200(A));
+  PetscCall(VecB200GetArrayRead(x, &dx));
+  PetscCall(VecB200GetArrayWrite(y, &dy));
+  PetscCallB200(b200CsrTransposeSpMV(H, a->T, dx, NULL, dy));
+  return PETSC_SUCCESS;
+}
+static PetscErrorCode MatMultTransposeAdd_SeqAIJB200(Mat A, Vec x, Vec y, Vec z)
+{
+  Mat_SeqAIJB200 *a = (Mat_SeqAIJB200 *)A->data;
+  const double   *dx, *dy;
+  double         *dz;
+  PetscCall(MatTransposeSync_SeqAIJB200(A));
+  PetscCall(VecB200GetArrayRead(x, &dx));
+  PetscCall(VecB200GetArrayRead(y, &dy));
+  if (z == y) PetscCall(VecB200GetArray(z, &dz));
+  else PetscCall(VecB200GetArrayWrite(z, &dz));
+  PetscCallB200(b200CsrTransposeSpMV(H, a->T, dx, dy, dz));
+  return PETSC_SUCCESS;
+}
+/* MatSetPreallocationCOO_SeqAIJ (aij.c:4524): the sort / unique / CSR construction run on the device */
+static PetscErrorCode MatSetPreallocationCOO_SeqAIJB200(Mat A, PetscCount ncoo, const PetscInt coo_i[], const PetscInt coo_j[])
+{
+  Mat_SeqAIJB200 *a;
+  int             dev_i = 0, dev_j = 0;
+  int            *d_ci = NULL, *d_cj = NULL;
+  double         *d_zero = NULL;
+  b200CooPlan     plan = NULL;
+  const int      *d_rp, *d_cx;
+  int64_t         nnz, atot;
+  PetscCallB200(b200PointerIsDevice(coo_i, &dev_i));
+  PetscCallB200(b200PointerIsDevice(coo_j, &dev_j));
+  if (!dev_i && ncoo) {
+    PetscCallB200(b200Malloc(H, (void **)&d_ci, sizeof(int) * (size_t)ncoo));
+    PetscCallB200(b200MemcpyHtoD(H, d_ci, coo_i, sizeof(int) * (size_t)ncoo));
+  }
+  if (!dev_j && ncoo) {
+    PetscCallB200(b200Malloc(H, (void **)&d_cj, sizeof(int) * (size_t)ncoo));
+    PetscCallB200(b200MemcpyHtoD(H, d_cj, coo_j, sizeof(int) * (size_t)ncoo));
+  }
+  {
+    int rc = b200CooPlanCreate(H, A->m, A->n, ncoo, dev_i ? coo_i : d_ci, dev_j ? coo_j : d_cj, &plan);
+    PetscCallB200(b200Free(H, d_ci));
+    PetscCallB200(b200Free(H, d_cj));
+    PetscCheck(rc != B200_ERR_ARG_OUTOFRANGE, A->hdr.comm, PETSC_ERR_ARG_OUTOFRANGE, "%s", b200GetLastErrorString());
+    PetscCallB200(rc);
+  }
+  PetscCallB200(b200CooPlanGetCsr(plan, &nnz, &atot, &d_rp, &d_cx));
+  PetscCallB200(b200Malloc(H, (void **)&d_zero, sizeof(double) * (size_t)(nnz + 1)));
+  PetscCallB200(b200VecSet(H, nnz, 0.0, d_zero));
+  PetscCall(MatSetCSR_SeqAIJB200(A, d_rp, d_cx, d_zero, 1)); /* copies the pattern; frees a previous COO plan */
+  PetscCallB200(b200Free(H, d_zero));
+  a      = (Mat_SeqAIJB200 *)A->data;
+  a->coo = plan;
+  return PETSC_SUCCESS;
+}
+static PetscErrorCode MatSetValuesCOO_SeqAIJB200(Mat A, const PetscScalar v[], InsertMode imode)
+{
+  Mat_SeqAIJB200 *a = (Mat_SeqAIJB200 *)A->data;
+  int             dev = 0;
+  double         *d_v = NULL;
+  int64_t         nnz, atot;
+  PetscCheck(a->coo, A->hdr.comm, PETSC_ERR_PLIB, "Not found MatCOOStruct on this matrix"); /* aij.c:4721 */
+  PetscCallB200(b200CooPlanGetCsr(a->coo, &nnz, &atot, NULL, NULL));
+  PetscCallB200(b200PointerIsDevice(v, &dev));
+  if (!dev && v) {
+    int64_t n = A->coo_n;
+    PetscCallB200(b200Malloc(H, (void **)&d_v, sizeof(double) * (size_t)(n + 1)));
+    PetscCallB200(b200MemcpyHtoD(H, d_v, v, sizeof(double) * (size_t)n));
+  }
+  PetscCallB200(b200CooSetValues(H, a->coo, dev ? v : d_v, imode == INSERT_VALUES, a->d_a));
+  PetscCallB200(b200Free(H, d_v));
+  free(a->h_i); free(a->h_j); free(a->h_a); /* host copies handed out by MatSeqAIJGetCSRHost are stale now */
+  a->h_i = a->h_j = NULL;
+  a->h_a = NULL;
+  return PETSC_SUCCESS;
+}
 static PetscErrorCode MatGetDiagonal_SeqAIJB200(Mat A, Vec v)
 {
   Mat_SeqAIJB200 *a = (Mat_SeqAIJB200 *)A->data;
@@ -527,6 +688,10 @@ PetscErrorCode MatCreate_SeqAIJB200(Mat A)
   A->ops.getdiagonalblock = MatGetDiagonalBlock_SeqAIJB200;
   A->ops.setcsr      = MatSetCSR_SeqAIJB200;
   A->ops.multjacobi  = MatMultJacobi_SeqAIJB200;
+  A->ops.multtranspose       = MatMultTranspose_SeqAIJB200;
+  A->ops.multtransposeadd    = MatMultTransposeAdd_SeqAIJB200;
+  A->ops.setpreallocationcoo = MatSetPreallocationCOO_SeqAIJB200;
+  A->ops.setvaluescoo        = MatSetValuesCOO_SeqAIJB200;
   strcpy(A->hdr.type_name, MATSEQAIJB200);
   strcpy(A->defaultvectype, VECB200); /* aijcusparse.cu:2820 analogue */
   return PETSC_SUCCESS;

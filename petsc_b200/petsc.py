@@ -341,6 +341,29 @@ class Mat:
     def mult_add(self, x, y, z):
         chk(lib().MatMultAdd(self.p, x.p, y.p, z.p))
 
+    def mult_transpose(self, x, y):
+        chk(lib().MatMultTranspose(self.p, x.p, y.p))
+
+    def mult_transpose_add(self, x, y, z):
+        chk(lib().MatMultTransposeAdd(self.p, x.p, y.p, z.p))
+
+    def set_preallocation_coo(self, coo_i, coo_j, n=None):
+        """MatSetPreallocationCOO: numpy int arrays (host) or raw device pointers (then pass n)."""
+        if n is None:
+            ci, cj = _i32(coo_i), _i32(coo_j)
+            self._coo_keep = (ci, cj)
+            chk(lib().MatSetPreallocationCOO(self.p, C.c_int64(len(ci)), ci.ctypes.data_as(vp), cj.ctypes.data_as(vp)))
+        else:
+            chk(lib().MatSetPreallocationCOO(self.p, C.c_int64(n), coo_i, coo_j))
+
+    def set_values_coo(self, v, add=False):
+        """MatSetValuesCOO(INSERT_VALUES | ADD_VALUES): numpy array (host) or a raw device pointer."""
+        if isinstance(v, np.ndarray) or isinstance(v, (list, tuple)):
+            v = _f64(v)
+            chk(lib().MatSetValuesCOO(self.p, v.ctypes.data_as(vp), 2 if add else 1))
+        else:
+            chk(lib().MatSetValuesCOO(self.p, v, 2 if add else 1))
+
     def get_diagonal(self, v):
         chk(lib().MatGetDiagonal(self.p, v.p))
 

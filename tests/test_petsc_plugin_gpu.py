@@ -86,3 +86,39 @@ def test_bench_kspsolve_through_plugin():
     assert len(ha) == len(hb) and np.allclose(ha, hb, rtol=1e-8)
     mm = run("bench_kspsolve", ["-n", "32", "-matmult", "-its", "5", "-print_timing", "false"] + B200)
     assert "Number of nonzeros = %d" % ((3 * 32 - 2) ** 3) in mm
+
+
+@pytest.mark.skipif(not have(), reason="oracle/_ref/petsc not built (needs the build container)")
+def test_ex2_fused_jacobi_pc_matches_pcjacobi():
+    """-pc_type jacobib200 (PCRegister'ed by the plugin; ops->applyBA = one fused SpMV+Jacobi kernel) gives the residual history
+    of the reference's PCJACOBI on the same types to the last digit printed, and of the CPU types to 1e-10."""
+    opts = ["-m", "100", "-n", "100", "-ksp_type", "gmres", "-ksp_monitor"]
+    a = run("ex2", opts + ["-pc_type", "jacobib200"] + B200)
+    b = run("ex2", opts + ["-pc_type", "jacobi"] + B200)
+    c = run("ex2", opts + ["-pc_type", "jacobi"])
+    ha, hb, hc = history(a), history(b), history(c)
+    assert len(ha) == len(hb) and np.array_equal(ha, hb)      # same arithmetic: row sum, then one multiply
+    k = min(len(ha), len(hc), 31)
+    assert np.allclose(ha[:k], hc[:k], rtol=1e-10, atol=1e-12 * hc[0])
+    view = run("ex2", ["-m", "8", "-n", "8", "-ksp_view", "-pc_type", "jacobib200"] + B200)
+    assert "jacobib200" in view
+
+
+@pytest.mark.skipif(not have(), reason="oracle/_ref/petsc not built (needs the build container)")
+def test_ex2_bicg_uses_device_transpose():
+    """KSPBICG needs MatMultTranspose and PCApplyTranspose: the plugin's explicit-transpose product vs the CPU types."""
+    opts = ["-m", "40", "-n", "40", "-ksp_type", "bicg", "-pc_type", "jacobi", "-ksp_monitor"]
+    ha, hb = history(run("ex2", opts + B200)), history(run("ex2", opts))
+    assert abs(len(ha) - len(hb)) <= 1
+    k = min(len(ha), len(hb), 25)
+    assert np.allclose(ha[:k], hb[:k], rtol=1e-8, atol=1e-12 * hb[0])
+
+
+@pytest.mark.skipif(not (have() and os.path.exists(os.path.join(BIN, "plugin_driver"))), reason="oracle/_ref/petsc/bin/plugin_driver not built")
+def test_plugin_driver_device_coo_transpose_bindtocpu():
+    out = run("plugin_driver", B200 + ["-mat_b200_spmv_lanes", "1"])  # parity mode: the products are compared bit for bit
+    assert "all ok" in out and "FAILED" not in out, out
+    for name in ("coo_device_insert_equals_reference", "coo_device_add_equals_reference", "coo_host_values_equals_reference", "matmult_bit_exact",
+                 "matmulttranspose_bit_exact", "matmulttransposeadd_bit_exact", "matmulttransposeadd_inplace_bit_exact", "matmulttranspose_after_matscale",
+                 "current_memtype_is_device", "matmult_bound_to_cpu"):
+        assert "ok " + name in out, out
