@@ -90,7 +90,8 @@ int b200CsrPlanDestroy(b200CsrPlan plan);
 /* tuning / introspection: lanes_per_row in {0=auto,1,2,4,8,16,32}; lanes_per_row == 1 reproduces MatMult_SeqAIJ's
    strict left-to-right, FMA-free row sums bit for bit.  rows_per_tile 0 = auto. */
 int b200CsrPlanSetLayout(b200CsrPlan plan, int lanes_per_row, int rows_per_tile, int stages, int ctas_per_sm);
-/* L2 eviction hints: bit0 = stream val/col/rowptr as evict_first, bit1 = keep x as evict_last (default 2) */
+/* L2 hints: bit0 = stream val/col/rowptr as evict_first, bit1 = keep x as evict_last, bit2 = persisting access-policy
+   window on x for the launch (default: 2 for one lane per row, else 3, plus bit2 when x fits the L2 set-aside) */
 int b200CsrPlanSetCacheHints(b200CsrPlan plan, int hints);
 int b200CsrPlanGetLayout(b200CsrPlan plan, int *lanes_per_row, int *rows_per_tile, int *stages, int *grid, int *smem_bytes, int *max_row_nnz);
 /* y = A x                                             (MatMult_SeqAIJ, aij.c:1444-1499) */

@@ -162,7 +162,10 @@ PetscErrorCode VecGetLocalVector(Vec v, Vec w);                                 
 PetscErrorCode VecRestoreLocalVector(Vec v, Vec w);
 PetscErrorCode VecGetLocalVectorRead(Vec v, Vec w);
 PetscErrorCode VecRestoreLocalVectorRead(Vec v, Vec w);
-PetscErrorCode VecCreateSeqWithArray(MPI_Comm comm, PetscInt bs, PetscInt n, const PetscScalar array[], Vec *V); /* copies in */
+PetscErrorCode VecCreateSeqWithArray(MPI_Comm comm, PetscInt bs, PetscInt n, const PetscScalar array[], Vec *V); /* bvec2.c: the user's HOST array is the host storage */
+PetscErrorCode VecCreateMPIWithArray(MPI_Comm comm, PetscInt bs, PetscInt n, PetscInt N, const PetscScalar array[], Vec *V); /* pbvec.c */
+PetscErrorCode VecPlaceArray(Vec vec, const PetscScalar array[]);                                                         /* rvector.c:2593 */
+PetscErrorCode VecResetArray(Vec vec);
 
 /* ---- Mat (src/mat/interface/{matrix.c,matreg.c}, impls/aij) ---- */
 PetscErrorCode MatCreate(MPI_Comm comm, Mat *A);

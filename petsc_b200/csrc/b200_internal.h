@@ -13,6 +13,9 @@
 struct b200Handle_s {
   int          device;
   int          num_sms;
+  int          l2_persist_max;  /* cudaDevAttrMaxPersistingL2CacheSize (bytes) */
+  int          l2_window_max;   /* cudaDevAttrMaxAccessPolicyWindowSize (bytes) */
+  int          l2_persist_set;  /* cudaLimitPersistingL2CacheSize raised by this handle */
   cudaStream_t stream;      /* current stream */
   cudaStream_t own_stream;  /* created with the handle */
   cudaStream_t halo_stream; /* second stream for the NCCL halo exchange */

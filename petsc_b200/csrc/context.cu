@@ -37,6 +37,8 @@ extern "C" int b200Create(b200Handle *hp, int device)
   h->device = device;
   h->nranks = 1;
   B200_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+  B200_CUDA(cudaDeviceGetAttribute(&h->l2_persist_max, cudaDevAttrMaxPersistingL2CacheSize, device));
+  B200_CUDA(cudaDeviceGetAttribute(&h->l2_window_max, cudaDevAttrMaxAccessPolicyWindowSize, device));
   B200_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   B200_CUDA(cudaStreamCreateWithFlags(&h->halo_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;

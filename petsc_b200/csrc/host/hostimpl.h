@@ -125,7 +125,10 @@ struct _p_Vec {
   int               sizes_set, type_set;
   /* data (Vec_Seq / Vec_MPI + device mirror) */
   double          *d_array;     /* device array (owned unless slab/alias) */
-  double          *h_array;     /* pinned host mirror, lazily allocated */
+  double          *h_array;     /* pinned host mirror, lazily allocated -- or the user's array (VecCreateSeqWithArray / VecPlaceArray) */
+  int              h_user;      /* h_array belongs to the user: never freed here */
+  double          *h_saved;     /* our own mirror while a user array is placed (VecResetArray restores it) */
+  int              h_saved_user;
   PetscOffloadMask offloadmask;
   int              owns_device; /* 0: part of a VecDuplicateVecs slab or an alias (VecGetLocalVector) */
   void            *slab;        /* slab base pointer shared by the group (freed by the first vector) */

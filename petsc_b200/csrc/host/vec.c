@@ -156,6 +156,8 @@ static PetscErrorCode VecSyncToHost(Vec v, int need_values)
   if (need_values && v->offloadmask == OFFLOAD_GPU) {
     PetscCallB200(b200MemcpyDtoH(H, v->h_array, v->d_array, sizeof(double) * (size_t)v->n));
     v->offloadmask = OFFLOAD_BOTH;
+  } else if (v->offloadmask == OFFLOAD_BOTH) {
+    PetscCallB200(b200Synchronize(H)); /* an asynchronous host->device copy of this array may still be reading it */
   }
   return PETSC_SUCCESS;
 }
@@ -560,10 +562,55 @@ PetscErrorCode VecCreateSeqWithArray(MPI_Comm comm, PetscInt bs, PetscInt n, con
   PetscCall(VecSetSizes(*V, n, n));
   PetscCall(VecSetType(*V, VECSEQB200));
   PetscCall(VecSetUp_Private(*V));
-  if (array && n) {
-    PetscCallB200(b200MemcpyHtoD(H, (*V)->d_array, array, sizeof(double) * (size_t)n));
-    VecStateIncrease(*V);
-  }
+  if (array) PetscCall(VecPlaceArray(*V, array)); /* the user's array IS the host storage (bvec2.c VecCreateSeqWithArray) */
+  return PETSC_SUCCESS;
+}
+PetscErrorCode VecCreateMPIWithArray(MPI_Comm comm, PetscInt bs, PetscInt n, PetscInt N, const PetscScalar array[], Vec *V)
+{
+  (void)bs;
+  PetscCall(VecCreate(comm, V));
+  PetscCall(VecSetSizes(*V, n, N));
+  PetscCall(VecSetType(*V, PetscB200CommSize(comm) > 1 ? VECMPIB200 : VECSEQB200));
+  PetscCall(VecSetUp_Private(*V));
+  if (array) PetscCall(VecPlaceArray(*V, array));
+  return PETSC_SUCCESS;
+}
+/* VecPlaceArray / VecResetArray (rvector.c:2593, bvec2.c VecPlaceArray_Seq): the vector uses the user's HOST array as its host
+   storage from now on; its current contents are the vector's values (the device mirror is refreshed on the next device use,
+   straight from that array: pinned user memory is copied at full PCIe speed) */
+PetscErrorCode VecPlaceArray(Vec v, const PetscScalar array[])
+{
+  PetscValidHeader(v, 1);
+  PetscCall(VecSetUp_Private(v));
+  PetscCheck(!v->array_gotten, v->hdr.comm, PETSC_ERR_ARG_WRONGSTATE, "Vector is locked by an outstanding VecGetArray()");
+  PetscCheck(!v->h_saved && !v->h_saved_user, v->hdr.comm, PETSC_ERR_ARG_WRONGSTATE, "VecPlaceArray() was already called on this vector, without a call to VecResetArray()");
+  PetscCheck(array || !v->n, v->hdr.comm, PETSC_ERR_ARG_NULL, "null array");
+  v->h_saved      = v->h_array;
+  v->h_saved_user = v->h_user | 2; /* bit 1: something is saved */
+  v->h_array      = (double *)array;
+  v->h_user       = 1;
+  v->offloadmask  = OFFLOAD_CPU;
+  VecStateIncrease(v);
+  return PETSC_SUCCESS;
+}
+PetscErrorCode VecResetArray(Vec v)
+{
+  PetscValidHeader(v, 1);
+  PetscCheck(v->h_saved_user & 2, v->hdr.comm, PETSC_ERR_ARG_WRONGSTATE, "VecResetArray() without VecPlaceArray()");
+  PetscCheck(!v->array_gotten, v->hdr.comm, PETSC_ERR_ARG_WRONGSTATE, "Vector is locked by an outstanding VecGetArray()");
+  v->h_array      = v->h_saved;
+  v->h_user       = v->h_saved_user & 1;
+  v->h_saved      = NULL;
+  v->h_saved_user = 0;
+  /* the original array's contents become the values again (bvec2.c VecResetArray_Seq); without one the device copy stays */
+  if (v->h_array) {
+    v->offloadmask = OFFLOAD_CPU;
+    VecStateIncrease(v);
+  } else if (v->offloadmask == OFFLOAD_CPU) {
+    PetscCallB200(b200Memset(H, v->d_array, 0, sizeof(double) * (size_t)v->n));
+    v->offloadmask = OFFLOAD_GPU;
+    VecStateIncrease(v);
+  } else v->offloadmask = OFFLOAD_GPU; /* no host mirror left: the device copy is the only one */
   return PETSC_SUCCESS;
 }
 
@@ -576,7 +623,8 @@ static PetscErrorCode VecDestroy_B200(Vec v)
       free(v->slab_ref);
     }
   } else if (v->owns_device && v->d_array) PetscCallB200(b200Free(H, v->d_array));
-  if (v->h_array) PetscCallB200(b200FreeHost(v->h_array));
+  if (v->h_array && !v->h_user) PetscCallB200(b200FreeHost(v->h_array));
+  if (v->h_saved && !(v->h_saved_user & 1)) PetscCallB200(b200FreeHost(v->h_saved));
   if (v->d_sumsq) PetscCallB200(b200Free(H, v->d_sumsq));
   return PETSC_SUCCESS;
 }

@@ -27,6 +27,7 @@
  */
 #include "b200_internal.h"
 #include <stdlib.h>
+#include <string.h>
 
 #define SPMV_TPB 256
 #define SPMV_MAX_STAGES 4
@@ -46,7 +47,8 @@ struct b200CsrPlan_s {
   int        num_sms;
   int        user_lanes, user_rows, user_stages, user_ctas;
   int        max_tile_nnz[16]; /* for R = 8 << k */
-  int        hints;            /* bit0: CSR streams evict_first, bit1: x evict_last */
+  int        hints;            /* bit0: CSR streams evict_first, bit1: x evict_last, bit2: persisting L2 window on x */
+  int        l2_persist_max;   /* of the device the plan was made on */
   int        hints_auto;
 };
 
@@ -371,6 +373,8 @@ static int plan_configure(b200CsrPlan p)
      scattered columns: also stream val/col as evict_first (3) so the gathered x keeps more of the L2 */
   if (p->hints < 0 || p->hints_auto) {
     p->hints      = (G == 1) ? 2 : 3;
+    /* scattered columns and an x that fits the L2 set-aside: pin x with a persisting access-policy window (bit 2) */
+    if (G > 1 && p->l2_persist_max > 0 && (int64_t)p->n * 8 >= (4 << 20) && (int64_t)p->n * 8 <= (int64_t)p->l2_persist_max) p->hints |= 4;
     p->hints_auto = 1;
   }
   p->rows_tile   = R;
@@ -394,7 +398,7 @@ extern "C" int b200CsrPlanCreate(b200Handle h, int m, int n, int64_t nnz, const 
   B200_CHECK(!m || (d_rowptr && (nnz == 0 || d_colidx)), B200_ERR_ARG_NULL, "null CSR arrays");
   b200CsrPlan p = (b200CsrPlan)calloc(1, sizeof(*p));
   B200_CHECK(p, B200_ERR_MEM, "out of host memory");
-  p->m = m; p->n = n; p->nnz = nnz; p->d_rowptr = d_rowptr; p->d_colidx = d_colidx; p->num_sms = h->num_sms;
+  p->m = m; p->n = n; p->nnz = nnz; p->d_rowptr = d_rowptr; p->d_colidx = d_colidx; p->num_sms = h->num_sms; p->l2_persist_max = h->l2_persist_max;
   p->hints = -1; /* auto, see plan_configure */
   if (m > 0) {
     int *d_stats;
@@ -436,7 +440,7 @@ extern "C" int b200CsrPlanSetLayout(b200CsrPlan p, int lanes, int rows_per_tile,
 extern "C" int b200CsrPlanSetCacheHints(b200CsrPlan p, int hints)
 {
   B200_CHECK(p, B200_ERR_ARG_NULL, "null plan");
-  B200_CHECK(hints >= 0 && hints <= 3, B200_ERR_ARG_OUTOFRANGE, "hints must be 0..3");
+  B200_CHECK(hints >= 0 && hints <= 7, B200_ERR_ARG_OUTOFRANGE, "hints must be 0..7");
   p->hints      = hints;
   p->hints_auto = 0;
   return 0;
@@ -478,7 +482,35 @@ static int spmv_launch_g(b200Handle h, b200CsrPlan p, const double *val, const d
   }
 }
 
+static int spmv_launch_lanes(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain);
+
+/* hints bit 2: the gathered vector x is given a persisting access-policy window for the duration of the launch (the CSR
+   streams then miss as "streaming" and cannot push x out of the L2); the set-aside is raised once per handle */
 static int spmv_launch(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
+{
+  B200_CHECK(h && p, B200_ERR_ARG_NULL, "null handle/plan");
+  if (!(p->hints & 4) || h->l2_persist_max <= 0 || h->l2_window_max <= 0 || !x) return spmv_launch_lanes(h, p, val, x, yin, dinv, yout, yplain);
+  if (!h->l2_persist_set) {
+    B200_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)h->l2_persist_max));
+    h->l2_persist_set = 1;
+  }
+  size_t bytes = (size_t)p->n * sizeof(double);
+  if (bytes > (size_t)h->l2_window_max) bytes = (size_t)h->l2_window_max;
+  cudaStreamAttrValue at;
+  memset(&at, 0, sizeof at);
+  at.accessPolicyWindow.base_ptr  = (void *)x;
+  at.accessPolicyWindow.num_bytes = bytes;
+  at.accessPolicyWindow.hitRatio  = bytes <= (size_t)h->l2_persist_max ? 1.0f : (float)h->l2_persist_max / (float)bytes;
+  at.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
+  at.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
+  B200_CUDA(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &at));
+  const int rc = spmv_launch_lanes(h, p, val, x, yin, dinv, yout, yplain);
+  at.accessPolicyWindow.num_bytes = 0; /* later kernels on this stream run without a window */
+  B200_CUDA(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &at));
+  return rc;
+}
+
+static int spmv_launch_lanes(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
 {
   B200_CHECK(h && p, B200_ERR_ARG_NULL, "null handle/plan");
   if (p->m == 0) return 0;

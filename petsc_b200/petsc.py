@@ -118,6 +118,29 @@ class Vec:
         v.set_array(a)
         return v
 
+    @classmethod
+    def with_array(cls, host_ptr, n, N=None, comm=COMM_SELF):
+        """VecCreateSeqWithArray / VecCreateMPIWithArray: the caller's HOST buffer (a raw pointer, e.g. pinned memory from
+        b200MallocHost, or a numpy array that outlives the Vec) is the vector's host storage; nothing is copied here."""
+        v = cls()
+        if isinstance(host_ptr, np.ndarray):
+            v._keep = host_ptr
+            host_ptr = host_ptr.ctypes.data_as(vp)
+        if N is None:
+            chk(lib().VecCreateSeqWithArray(comm, 1, int(n), host_ptr, C.byref(v.p)))
+        else:
+            chk(lib().VecCreateMPIWithArray(comm, 1, int(n), int(N), host_ptr, C.byref(v.p)))
+        return v
+
+    def place_array(self, host_ptr):
+        if isinstance(host_ptr, np.ndarray):
+            self._keep = host_ptr
+            host_ptr = host_ptr.ctypes.data_as(vp)
+        chk(lib().VecPlaceArray(self.p, host_ptr))
+
+    def reset_array(self):
+        chk(lib().VecResetArray(self.p))
+
     def duplicate(self):
         w = Vec()
         chk(lib().VecDuplicate(self.p, C.byref(w.p)))

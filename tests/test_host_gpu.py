@@ -252,3 +252,32 @@ def test_gmres_restart_and_maxit(P, oracle):
     assert o["its"] == 23 and o["reason"] == -3
     assert np.allclose(r["hist"], o["hist"], rtol=1e-9)
     assert len(r["hist"]) == len(o["hist"])
+
+
+def test_vec_user_array_is_the_host_storage(P):
+    """VecCreateSeqWithArray / VecPlaceArray / VecResetArray (bvec2.c, rvector.c:2593): the caller's host array is the vector's
+    host storage -- device results land in it on the next host access, host edits reach the device on the next device op."""
+    petsc = P
+    a = np.arange(12.0)
+    v = petsc.Vec.with_array(a, 12)
+    w = v.duplicate(); w.set(2.0)
+    v.axpy(1.0, w)                                   # device op: uploads a, computes a + 2
+    assert np.array_equal(a, np.arange(12.0))        # nothing came back yet
+    assert np.array_equal(v.array(), np.arange(12.0) + 2.0)
+    assert np.array_equal(a, np.arange(12.0) + 2.0)  # the host access copied into the user's array itself
+    a[:] = 5.0; v.touch_host()                       # the user changes the array and says so (VecGetArrayWrite/Restore)
+    assert v.norm() == pytest.approx(5.0 * np.sqrt(12.0), rel=1e-14)
+    # place / reset on a vector that owns its storage
+    u = w.duplicate(); u.set(1.0)
+    b = np.full(12, 7.0)
+    u.place_array(b)
+    assert np.array_equal(u.array(), b)
+    u.scale(2.0)
+    assert np.array_equal(u.array(), np.full(12, 14.0)) and np.array_equal(b, np.full(12, 14.0))
+    with pytest.raises(petsc.PetscError):
+        u.place_array(b)                             # second VecPlaceArray without VecResetArray (PETSC_ERR_ARG_WRONGSTATE)
+    u.reset_array()
+    u.set(3.0)
+    assert np.array_equal(u.array(), np.full(12, 3.0)) and np.array_equal(b, np.full(12, 14.0))
+    for o in (u, v, w):
+        o.destroy()

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--n27", type=int, default=256)
     ap.add_argument("--nrand", type=int, default=10_000_000)
     ap.add_argument("--n7", type=int, default=384)
+    ap.add_argument("--nasm", type=int, default=160)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     L = _capi.lib()
@@ -76,8 +77,14 @@ def main():
                     auto = r
                 if best is None or ms < best["ms"]:
                     best = r
+            # L2 hints at the automatic layout: 3 = evict hints only, 7 = + persisting access-policy window on x
+            _capi.check(L.b200CsrPlanSetLayout(plan, 0, 0, 0, 0))
+            hint_ms = {}
+            for hints in (3, 7):
+                _capi.check(L.b200CsrPlanSetCacheHints(plan, hints))
+                hint_ms[str(hints)] = timed(lambda: _capi.check(L.b200CsrSpMV(H, plan, d_a.ptr, x.ptr, y.ptr)), 10)
             alg = nnz * 12 + n * 20
-            row = dict(n=n, d=d, nnz=nnz, auto=auto, best=best, algorithmic_bytes=alg, gbs_auto=alg / auto["ms"] / 1e6, gbs_best=alg / best["ms"] / 1e6,
+            row = dict(n=n, d=d, nnz=nnz, auto=auto, best=best, hints_ms=hint_ms, algorithmic_bytes=alg, gbs_auto=alg / auto["ms"] / 1e6, gbs_best=alg / best["ms"] / 1e6,
                        frac_auto=alg / auto["ms"] / 1e6 / peak, gflops_auto=(2 * nnz - n) / auto["ms"] / 1e6,
                        note="x gather is random over an n-vector (%d MB): beyond the 126 MB L2, so DRAM traffic exceeds the algorithmic bytes" % (n * 8 // 1000000))
             res["config5_random_csr"].append(row)
@@ -162,6 +169,66 @@ def main():
                                                    rows_per_group=os.environ.get("PETSCB200_ILU_ROWS_PER_GROUP", "auto"))
         print("config4", res["config4_block_gmres_ilu0_7pt"], flush=True)
         ksp.destroy(); A.destroy()
+
+    if "tr" in what or "coo" in what:
+        # widening rows: transposed product and COO assembly on the 27-point operator (n = --nasm)
+        n = a.nasm
+        N = n ** 3
+        nnz = C.c_int64()
+        _capi.check(L.b200GenLaplace27Nnz(n, C.byref(nnz)))
+        nnz = nnz.value
+        d_i, d_j, d_a = _capi.DeviceArray(Hh, N + 1, np.int32), _capi.DeviceArray(Hh, nnz, np.int32), _capi.DeviceArray(Hh, nnz, np.float64)
+        _capi.check(L.b200GenLaplace27(H, n, d_i.ptr, d_j.ptr, d_a.ptr))
+        x, y = _capi.DeviceArray(Hh, N, np.float64), _capi.DeviceArray(Hh, N, np.float64)
+        _capi.check(L.b200VecSet(H, C.c_int64(N), C.c_double(1.0), x.ptr))
+        if "tr" in what:
+            T = C.c_void_p()
+            t0 = time.time()
+            _capi.check(L.b200CsrTransposeCreate(H, N, N, C.c_int64(nnz), d_i.ptr, d_j.ptr, C.byref(T)))
+            _capi.check(L.b200Synchronize(H))
+            create_s = time.time() - t0
+            gather_ms = timed(lambda: _capi.check(L.b200CsrTransposeSetValues(H, T, d_a.ptr)), 10)
+            out = {}
+            for lanes in (0, 1):
+                tp = C.c_void_p()
+                _capi.check(L.b200CsrTransposeGetPlan(T, C.byref(tp)))
+                _capi.check(L.b200CsrPlanSetLayout(tp, lanes, 0, 0, 0))
+                out["spmv_ms_lanes%d" % lanes] = timed(lambda: _capi.check(L.b200CsrTransposeSpMV(H, T, x.ptr, None, y.ptr)), 20)
+            plan = C.c_void_p()
+            _capi.check(L.b200CsrPlanCreate(H, N, N, C.c_int64(nnz), d_i.ptr, d_j.ptr, C.byref(plan)))
+            fwd_ms = timed(lambda: _capi.check(L.b200CsrSpMV(H, plan, d_a.ptr, x.ptr, y.ptr)), 20)
+            L.b200CsrPlanDestroy(plan)
+            alg = nnz * 12 + N * 20
+            res["transpose_27pt"] = dict(n=n, rows=N, nnz=nnz, create_s=create_s, gather_ms=gather_ms, gather_gbs=nnz * 20 / gather_ms / 1e6, forward_spmv_ms=fwd_ms,
+                                         forward_gbs=alg / fwd_ms / 1e6, transposed_gbs_auto=alg / out["spmv_ms_lanes0"] / 1e6, transposed_gbs_parity=alg / out["spmv_ms_lanes1"] / 1e6,
+                                         frac_of_peak_auto=alg / out["spmv_ms_lanes0"] / 1e6 / peak, **out)
+            print("transpose", res["transpose_27pt"], flush=True)
+            L.b200CsrTransposeDestroy(T)
+        if "coo" in what:
+            # the (i,j,v) triples of the same operator in a shuffled order, resident on the device
+            hi = np.empty(N + 1, np.int32)
+            _capi.check(L.b200MemcpyDtoH(H, hi.ctypes.data_as(C.c_void_p), d_i.ptr, C.c_size_t(4 * (N + 1))))
+            rows = np.repeat(np.arange(N, dtype=np.int32), np.diff(hi))
+            cols, vals = d_j.download(), d_a.download()
+            perm = np.random.default_rng(3).permutation(nnz)
+            c_i, c_j, c_v = _capi.DeviceArray(Hh, nnz, np.int32), _capi.DeviceArray(Hh, nnz, np.int32), _capi.DeviceArray(Hh, nnz, np.float64)
+            c_i.upload(rows[perm]); c_j.upload(cols[perm]); c_v.upload(vals[perm])
+            del rows, cols, perm
+            times = []
+            for _ in range(3):
+                plan = C.c_void_p()
+                t = _capi.Timer(Hh); t.start()
+                _capi.check(L.b200CooPlanCreate(H, N, N, C.c_int64(nnz), c_i.ptr, c_j.ptr, C.byref(plan)))
+                t.stop(); times.append(t.ms())
+                if _ < 2:
+                    L.b200CooPlanDestroy(plan)
+            out_a = _capi.DeviceArray(Hh, nnz + 1, np.float64)
+            set_ms = timed(lambda: _capi.check(L.b200CooSetValues(H, plan, c_v.ptr, 1, out_a.ptr)), 10)
+            same = bool(np.array_equal(out_a.download()[:nnz], vals))
+            res["coo_27pt"] = dict(n=n, rows=N, coo_n=nnz, prealloc_ms=min(times), prealloc_Mentries_per_s=nnz / min(times) / 1e3, setvalues_ms=set_ms,
+                                   setvalues_gbs=nnz * (4 + 4 + 8 + 8) / set_ms / 1e6, values_equal_generator=same)
+            print("coo", res["coo_27pt"], flush=True)
+            L.b200CooPlanDestroy(plan)
 
     if "1" in what:
         # ex2 -m 100 -n 100 -ksp_type gmres -pc_type jacobi (BASELINE configs[0]); matrix assembled on the host like ex2 does
