@@ -428,13 +428,18 @@ def main():
             a.traffic = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json")))["dram_bytes_per_launch"]
         except Exception:
             a.traffic = None
+    # stdout carries exactly ONE line (the JSON): anything libraries print while we run (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     D = Dist()
     if a.impl == "reference":
         out = run_reference(a, D)
     else:
         out = run_product(a, D)
+    sys.stdout.flush()
     if D.rank == 0 and out is not None:
-        print(json.dumps(out), flush=True)
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     D.close()
 
 

@@ -898,6 +898,23 @@ static PetscErrorCode MatSetCSR_MPIAIJB200(Mat mat, const PetscInt *ai, const Pe
     PetscCall(MatSetUpMultiply_MPIAIJB200(mat));
     return PETSC_SUCCESS;
   }
+  if (m && ai[m] > (1 << 16)) {
+    /* large host CSR: one host->device copy of the three arrays, then the device split above -- the host loop below walks
+       every entry twice and costs seconds per 10^9 nonzeros, the copy runs at PCIe speed */
+    int           *d_i = NULL, *d_j = NULL;
+    double        *d_a = NULL;
+    const size_t   nz  = (size_t)ai[m];
+    PetscErrorCode ierr;
+    PetscCallB200(b200Malloc(H, (void **)&d_i, sizeof(int) * ((size_t)m + 1)));
+    PetscCallB200(b200Malloc(H, (void **)&d_j, sizeof(int) * nz));
+    PetscCallB200(b200Malloc(H, (void **)&d_a, sizeof(double) * nz));
+    PetscCallB200(b200MemcpyHtoD(H, d_i, ai, sizeof(int) * ((size_t)m + 1)));
+    PetscCallB200(b200MemcpyHtoD(H, d_j, aj, sizeof(int) * nz));
+    PetscCallB200(b200MemcpyHtoD(H, d_a, aa, sizeof(double) * nz));
+    ierr = MatSetCSR_MPIAIJB200(mat, d_i, d_j, d_a, 1);
+    PetscCallB200(b200Free(H, d_i)); PetscCallB200(b200Free(H, d_j)); PetscCallB200(b200Free(H, d_a));
+    return ierr;
+  }
   PetscInt    *Ai, *Aj, *Bi, *Bj, *g, ec;
   PetscScalar *Aa, *Ba;
   for (PetscInt r = 0; r < m; r++)
