@@ -209,6 +209,7 @@ PetscErrorCode MatGetInfo(Mat mat, MatInfoType flag, MatInfo *info);            
 PetscErrorCode MatMPIAIJGetSeqAIJ(Mat A, Mat *Ad, Mat *Ao, const PetscInt *colmap[]);
 PetscErrorCode MatSeqAIJGetCSRHost(Mat A, PetscInt *m, const PetscInt **i, const PetscInt **j, const PetscScalar **a); /* host copy (downloads) */
 PetscErrorCode MatB200SetSpMVLayout(Mat A, PetscInt lanes_per_row, PetscInt rows_per_tile, PetscInt stages, PetscInt ctas_per_sm); /* -mat_b200_spmv_* */
+PetscErrorCode MatB200SetSpMVOrdered(Mat A, PetscBool ordered); /* -mat_b200_spmv_ordered: reference-order row sums for every layout (bit-exact MatMult) */
 
 /* ---- PC (src/ksp/pc/interface/precon.c) ---- */
 PetscErrorCode PCCreate(MPI_Comm comm, PC *newpc);

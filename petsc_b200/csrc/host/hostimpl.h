@@ -210,6 +210,7 @@ struct _p_Mat {
   COOEntry *coo;
   size_t    ncoo, coocap;
   int       spmv_layout[4];
+  int       spmv_ordered; /* -mat_b200_spmv_ordered: row sums in the reference's order for every lane count (bit-exact MatMult) */
   int64_t   coo_n; /* length of the arrays given to MatSetPreallocationCOO */
 };
 PetscErrorCode MatCreate_SeqAIJB200(Mat A);

@@ -101,6 +101,11 @@ PetscErrorCode MatSetFromOptions(Mat B)
   PetscCall(PetscOptionsGetInt(NULL, B->hdr.prefix, "-mat_b200_spmv_stages", &v[2], NULL));
   PetscCall(PetscOptionsGetInt(NULL, B->hdr.prefix, "-mat_b200_spmv_ctas_per_sm", &v[3], NULL));
   for (int i = 0; i < 4; i++) B->spmv_layout[i] = v[i];
+  {
+    PetscBool ordered = (PetscBool)B->spmv_ordered;
+    PetscCall(PetscOptionsGetBool(NULL, B->hdr.prefix, "-mat_b200_spmv_ordered", &ordered, NULL));
+    B->spmv_ordered = ordered ? 1 : 0;
+  }
   return PETSC_SUCCESS;
 }
 PetscErrorCode MatGetType(Mat mat, MatType *type)
@@ -395,6 +400,25 @@ PetscErrorCode MatGetInfo(Mat mat, MatInfoType flag, MatInfo *info)
   return PETSC_SUCCESS;
 }
 
+/* -mat_b200_spmv_ordered: MatMult / MatMultAdd / MatMultTranspose row sums in the reference's left-to-right FMA-free order for
+   every lane count (bit-identical to MatMult_SeqAIJ); default off = fastest association (equal to rounding) */
+PetscErrorCode MatB200SetSpMVOrdered(Mat A, PetscBool ordered)
+{
+  A->spmv_ordered = ordered ? 1 : 0;
+  if (!strcmp(A->hdr.type_name, MATSEQAIJB200) && A->data) {
+    Mat_SeqAIJB200 *a = (Mat_SeqAIJB200 *)A->data;
+    if (a->plan) PetscCallB200(b200CsrPlanSetSummation(a->plan, ordered ? 0 : 1));
+    if (a->T) {
+      b200CsrPlan tp;
+      PetscCallB200(b200CsrTransposeGetPlan(a->T, &tp));
+      PetscCallB200(b200CsrPlanSetSummation(tp, ordered ? 0 : 1));
+    }
+  } else if (!strcmp(A->hdr.type_name, MATMPIAIJB200) && A->data) {
+    Mat_MPIAIJB200 *a = (Mat_MPIAIJB200 *)A->data;
+    if (a->A) PetscCall(MatB200SetSpMVOrdered(a->A, ordered));
+  }
+  return PETSC_SUCCESS;
+}
 PetscErrorCode MatB200SetSpMVLayout(Mat A, PetscInt lanes, PetscInt rows, PetscInt stages, PetscInt ctas)
 {
   A->spmv_layout[0] = lanes; A->spmv_layout[1] = rows; A->spmv_layout[2] = stages; A->spmv_layout[3] = ctas;
@@ -477,6 +501,7 @@ static PetscErrorCode MatSetCSR_SeqAIJB200(Mat A, const PetscInt *ai, const Pets
   }
   PetscCallB200(b200CsrPlanCreate(H, m, A->n, nz, a->d_i, a->d_j, &a->plan));
   if (A->spmv_layout[0] || A->spmv_layout[1] || A->spmv_layout[2] || A->spmv_layout[3]) PetscCallB200(b200CsrPlanSetLayout(a->plan, A->spmv_layout[0], A->spmv_layout[1], A->spmv_layout[2], A->spmv_layout[3]));
+  if (A->spmv_ordered) PetscCallB200(b200CsrPlanSetSummation(a->plan, 0));
   {
     int cnt = 0;
     PetscCallB200(b200CsrCountNonemptyRows(H, m, a->d_i, &cnt));
@@ -555,10 +580,11 @@ static PetscErrorCode MatTransposeSync_SeqAIJB200(Mat A)
   if (!a->T) {
     PetscCallB200(b200CsrTransposeCreate(H, a->m, a->n, a->nz, a->d_i, a->d_j, &a->T));
     a->T_state = -1;
-    if (A->spmv_layout[0] || A->spmv_layout[1] || A->spmv_layout[2] || A->spmv_layout[3]) { /* -mat_b200_spmv_lanes etc. apply to A^T too */
+    if (A->spmv_ordered || A->spmv_layout[0] || A->spmv_layout[1] || A->spmv_layout[2] || A->spmv_layout[3]) { /* -mat_b200_spmv_* apply to A^T too */
       b200CsrPlan tp;
       PetscCallB200(b200CsrTransposeGetPlan(a->T, &tp));
       PetscCallB200(b200CsrPlanSetLayout(tp, A->spmv_layout[0], A->spmv_layout[1], A->spmv_layout[2], A->spmv_layout[3]));
+      if (A->spmv_ordered) PetscCallB200(b200CsrPlanSetSummation(tp, 0));
     }
   }
   if (a->T_state != A->hdr.state) {
@@ -887,6 +913,8 @@ static PetscErrorCode MatSetCSR_MPIAIJB200(Mat mat, const PetscInt *ai, const Pe
     PetscCall(MatSetSizes(a->A, m, mat->n, m, mat->n));
     PetscCall(MatSetType(a->A, MATSEQAIJB200));
     for (int i = 0; i < 4; i++) a->A->spmv_layout[i] = mat->spmv_layout[i];
+  a->A->spmv_ordered = mat->spmv_ordered;
+    a->A->spmv_ordered = mat->spmv_ordered;
     PetscCall(MatSetUp(a->A));
     PetscCall((*a->A->ops.setcsr)(a->A, dAi, dAj, dAa, 2)); /* adopts the device arrays */
     a->A->assembled = 1;
@@ -929,6 +957,7 @@ static PetscErrorCode MatSetCSR_MPIAIJB200(Mat mat, const PetscInt *ai, const Pe
   PetscCall(MatSetSizes(a->A, m, mat->n, m, mat->n));
   PetscCall(MatSetType(a->A, MATSEQAIJB200)); /* the MatMPIAIJSetPreallocation_C hook of mpiaijcupm.hpp:326-377 */
   for (int i = 0; i < 4; i++) a->A->spmv_layout[i] = mat->spmv_layout[i];
+  a->A->spmv_ordered = mat->spmv_ordered;
   PetscCall(MatSeqAIJSetPreallocationCSR(a->A, Ai, Aj, Aa));
   PetscCall(MatCreate(PETSC_COMM_SELF, &a->B));
   PetscCall(MatSetSizes(a->B, m, ec, m, ec));

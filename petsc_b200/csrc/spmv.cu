@@ -49,6 +49,9 @@ struct b200CsrPlan_s {
   int        max_tile_nnz[16]; /* for R = 8 << k */
   int        hints;            /* bit0: CSR streams evict_first, bit1: x evict_last, bit2: persisting L2 window on x */
   int        l2_persist_max;   /* of the device the plan was made on */
+  int        tree_sum;         /* 1 (default): FMA + shuffle tree for rows with several lanes (rounding differs from the reference in
+                                  the last bits; one lane per row is always exact); 0: the reference's left-to-right FMA-free
+                                  order for every lane count */
   int        hints_auto;
 };
 
@@ -117,7 +120,11 @@ __host__ __device__ inline StageLayout stage_layout(int R, int cap)
 }
 
 /* ------------------------------------------------------------------ the kernel */
-template <int G, int HINTS>
+/* ORD (G > 1 only): the G lanes of a row still load and multiply G consecutive entries at a time (coalesced), but the
+   products are then added into the row sum one after the other in column order (G width-G shuffles per chunk, every lane of
+   the group keeps the same running sum) -- MatMult_SeqAIJ's left-to-right, FMA-free association at full bandwidth.  ORD = 0
+   is the FMA + shuffle-tree variant (rounding differs from the reference in the last bits). */
+template <int G, int HINTS, int ORD>
 __global__ void __launch_bounds__(SPMV_TPB) csr_spmv_tile_kernel(int m, int R, int cap, int S, const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ val, const double *__restrict__ x, const double *yin, const double *__restrict__ dinv, double *yout, double *yplain)
 {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -224,6 +231,32 @@ __global__ void __launch_bounds__(SPMV_TPB) csr_spmv_tile_kernel(int m, int R, i
           for (; k < ke - k0a; k++) sum = __dadd_rn(sum, __dmul_rn(vs[k], ldx(x + cs[k])));
         } else {
           for (int k = ks; k < ke; k++) sum = __dadd_rn(sum, __dmul_rn(__ldg(val + k), __ldg(x + __ldg(colidx + k))));
+        }
+      } else if (ORD) {
+        sum = (act && yin) ? yin[r] : 0.0;
+        const int len = ke - ks; /* 0 for lanes without a row */
+        int       nch = (len + G - 1) / G;
+#pragma unroll
+        for (int o = 16; o >= G; o >>= 1) nch = max(nch, __shfl_xor_sync(0xffffffffu, nch, o)); /* warp-uniform trip count */
+        const int kb = staged ? ks - k0a : ks;
+        for (int c = 0; c < nch; c += 4) { /* four chunks of G entries: four independent gathers in flight per lane */
+          double p[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int  kk = (c + u) * G + gl;
+            const bool v  = kk < len;
+            if (staged) p[u] = v ? __dmul_rn(vs[kb + kk], ldx(x + cs[kb + kk])) : 0.0;
+            else p[u] = v ? __dmul_rn(__ldg(val + kb + kk), __ldg(x + __ldg(colidx + kb + kk))) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int cnt = len - (c + u) * G; /* entries of this chunk that exist (<= 0: none) */
+#pragma unroll
+            for (int l = 0; l < G; l++) {
+              const double pl = __shfl_sync(0xffffffffu, p[u], l, G);
+              if (l < cnt) sum = __dadd_rn(sum, pl);
+            }
+          }
         }
       } else {
         sum = 0.0;
@@ -400,6 +433,9 @@ extern "C" int b200CsrPlanCreate(b200Handle h, int m, int n, int64_t nnz, const 
   B200_CHECK(p, B200_ERR_MEM, "out of host memory");
   p->m = m; p->n = n; p->nnz = nnz; p->d_rowptr = d_rowptr; p->d_colidx = d_colidx; p->num_sms = h->num_sms; p->l2_persist_max = h->l2_persist_max;
   p->hints = -1; /* auto, see plan_configure */
+  /* measured (profiles/round1_notes.md): the ordered sums cost 1.0x (d <= 128 random), 1.4x (d = 512) and 1.7x (27-point) of the
+     tree variant, so the fast variant stays the default and the exact one is a switch (b200CsrPlanSetSummation(plan, 0)) */
+  p->tree_sum = 1;
   if (m > 0) {
     int *d_stats;
     int  hstats[17];
@@ -446,6 +482,14 @@ extern "C" int b200CsrPlanSetCacheHints(b200CsrPlan p, int hints)
   return 0;
 }
 
+extern "C" int b200CsrPlanSetSummation(b200CsrPlan p, int tree)
+{
+  B200_CHECK(p, B200_ERR_ARG_NULL, "null plan");
+  B200_CHECK(tree == 0 || tree == 1, B200_ERR_ARG_OUTOFRANGE, "summation mode must be 0 (reference order) or 1 (tree)");
+  p->tree_sum = tree;
+  return 0;
+}
+
 extern "C" int b200CsrPlanGetLayout(b200CsrPlan p, int *lanes, int *rows, int *stages, int *grid, int *smem, int *maxrow)
 {
   B200_CHECK(p, B200_ERR_ARG_NULL, "null plan");
@@ -458,18 +502,24 @@ extern "C" int b200CsrPlanGetLayout(b200CsrPlan p, int *lanes, int *rows, int *s
   return 0;
 }
 
-template <int G, int HINTS>
-static int spmv_launch_gh(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
+template <int G, int HINTS, int ORD>
+static int spmv_launch_gho(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
 {
   static int configured = 0;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(csr_spmv_tile_kernel<G, HINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    B200_CUDA(cudaFuncSetAttribute(csr_spmv_tile_kernel<G, HINTS, ORD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
     configured = 1;
   }
-  csr_spmv_tile_kernel<G, HINTS><<<p->grid, SPMV_TPB, p->smem, h->stream>>>(p->m, p->rows_tile, p->cap, p->stages, p->d_rowptr, p->d_colidx, val, x, yin, dinv, yout, yplain);
+  csr_spmv_tile_kernel<G, HINTS, ORD><<<p->grid, SPMV_TPB, p->smem, h->stream>>>(p->m, p->rows_tile, p->cap, p->stages, p->d_rowptr, p->d_colidx, val, x, yin, dinv, yout, yplain);
   B200_LAUNCHED(1);
   B200_KERNEL_CHECK();
   return 0;
+}
+template <int G, int HINTS>
+static int spmv_launch_gh(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
+{
+  if (G > 1 && !p->tree_sum) return spmv_launch_gho<G, HINTS, (G > 1) ? 1 : 0>(h, p, val, x, yin, dinv, yout, yplain);
+  return spmv_launch_gho<G, HINTS, 0>(h, p, val, x, yin, dinv, yout, yplain);
 }
 template <int G>
 static int spmv_launch_g(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)

@@ -398,6 +398,9 @@ class Mat:
     def set_spmv_layout(self, lanes=0, rows=0, stages=0, ctas=0):
         chk(lib().MatB200SetSpMVLayout(self.p, lanes, rows, stages, ctas))
 
+    def set_spmv_ordered(self, ordered=True):
+        chk(lib().MatB200SetSpMVOrdered(self.p, 1 if ordered else 0))
+
     def mpiaij_blocks(self):
         Ad, Ao, cm = vp(), vp(), C.POINTER(i32)()
         chk(lib().MatMPIAIJGetSeqAIJ(self.p, C.byref(Ad), C.byref(Ao), C.byref(cm)))

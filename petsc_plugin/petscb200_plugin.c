@@ -553,6 +553,12 @@ static PetscErrorCode PB_PlanSetFromOptions(Mat A, b200CsrPlan plan)
   PetscFunctionBegin;
   PetscCall(PetscOptionsGetInt(((PetscObject)A)->options, ((PetscObject)A)->prefix, "-mat_b200_spmv_lanes", &lanes, &set));
   if (set) PetscCallB200(b200CsrPlanSetLayout(plan, (int)lanes, 0, 0, 0));
+  {
+    /* -mat_b200_spmv_ordered: reference-order row sums for every lane count (bit-identical MatMult at 0.6-1.0x the speed) */
+    PetscBool ordered = PETSC_FALSE;
+    PetscCall(PetscOptionsGetBool(((PetscObject)A)->options, ((PetscObject)A)->prefix, "-mat_b200_spmv_ordered", &ordered, NULL));
+    if (ordered) PetscCallB200(b200CsrPlanSetSummation(plan, 0));
+  }
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 

@@ -26,7 +26,7 @@ def H():
 @pytest.fixture(scope="module")
 def P():
     from petsc_b200 import petsc
-    petsc.initialize(device=0)
+    petsc.initialize()
     return petsc
 
 

@@ -68,21 +68,34 @@ def test_spmv_bit_exact_parity_mode(H, oracle):
         assert np.array_equal(d_z.download(), oracle.matmultadd(ai, aj, aa, x, y0)), name
 
 
-def test_spmv_auto_layout_tolerance(H, oracle):
+def test_spmv_every_layout_is_bit_exact_tree_mode_within_tolerance(H, oracle):
+    """b200CsrPlanSetSummation(plan, 0): the reference's left-to-right FMA-free row sums for EVERY lanes-per-row (automatic
+    layout included), so MatMult / MatMultAdd / the fused Jacobi epilogue are bit-identical to the CPU path on every matrix
+    class.  The default (1) is the FMA + shuffle-tree variant for rows with several lanes: north_star tolerance."""
+    from petsc_b200 import _capi
+    L = _capi.lib()
     rng = np.random.default_rng(8)
     for name, (ai, aj, aa) in matrices(oracle):
         m = len(ai) - 1
         ncol = max(int(aj.max()) + 1 if len(aj) else m, m)
-        x = rng.uniform(-1, 1, ncol)
+        x = rng.uniform(-1, 1, ncol); y0 = rng.uniform(-1, 1, m); dinv = rng.uniform(0.5, 2.0, m)
         d_ai, d_aj, d_aa, plan = upload_csr(H, ai, aj, aa)
         lay = H.csr_plan_layout(plan)
-        d_x, d_y = H.array(x), H.empty(m)
-        H.spmv(plan, d_aa, d_x, d_y)
+        d_x, d_y, d_y0, d_dinv, d_w = H.array(x), H.empty(m), H.array(y0), H.array(dinv), H.empty(m)
         ref = oracle.matmult(ai, aj, aa, x)
-        got = d_y.download()
+        refadd = oracle.matmultadd(ai, aj, aa, x, y0)
         scale = np.abs(ref).max() if m else 1.0
-        assert np.abs(got - ref).max() <= RTOL * max(scale, 1e-300), (name, lay)
-        for lanes in (2, 4, 8, 16, 32):
+        _capi.check(L.b200CsrPlanSetSummation(plan, 0))
+        for lanes in (0, 2, 4, 8, 16, 32):
+            H.csr_plan_set_layout(plan, lanes=lanes)
+            H.spmv(plan, d_aa, d_x, d_y)
+            assert np.array_equal(d_y.download(), ref), (name, lanes, lay)
+            H.spmv_add(plan, d_aa, d_x, d_y0, d_y)
+            assert np.array_equal(d_y.download(), refadd), (name, lanes)
+            H.spmv_jacobi(plan, d_aa, d_x, d_dinv, d_w, d_y)
+            assert np.array_equal(d_y.download(), ref) and np.array_equal(d_w.download(), ref * dinv), (name, lanes)
+        _capi.check(L.b200CsrPlanSetSummation(plan, 1))
+        for lanes in (0, 2, 4, 8, 16, 32):
             H.csr_plan_set_layout(plan, lanes=lanes)
             H.spmv(plan, d_aa, d_x, d_y)
             assert np.abs(d_y.download() - ref).max() <= RTOL * max(scale, 1e-300), (name, lanes)

@@ -116,7 +116,7 @@ def test_ex2_bicg_uses_device_transpose():
 
 @pytest.mark.skipif(not (have() and os.path.exists(os.path.join(BIN, "plugin_driver"))), reason="oracle/_ref/petsc/bin/plugin_driver not built")
 def test_plugin_driver_device_coo_transpose_bindtocpu():
-    out = run("plugin_driver", B200 + ["-mat_b200_spmv_lanes", "1"])  # parity mode: the products are compared bit for bit
+    out = run("plugin_driver", B200 + ["-mat_b200_spmv_ordered"])  # reference-order row sums: the products are compared bit for bit
     assert "all ok" in out and "FAILED" not in out, out
     for name in ("coo_device_insert_equals_reference", "coo_device_add_equals_reference", "coo_host_values_equals_reference", "matmult_bit_exact",
                  "matmulttranspose_bit_exact", "matmulttransposeadd_bit_exact", "matmulttransposeadd_inplace_bit_exact", "matmulttranspose_after_matscale",

@@ -83,6 +83,12 @@ def main():
             for hints in (3, 7):
                 _capi.check(L.b200CsrPlanSetCacheHints(plan, hints))
                 hint_ms[str(hints)] = timed(lambda: _capi.check(L.b200CsrSpMV(H, plan, d_a.ptr, x.ptr, y.ptr)), 10)
+            # row-sum association: default = reference order for every lane count; 1 = FMA + shuffle tree
+            _capi.check(L.b200CsrPlanSetCacheHints(plan, 3))
+            _capi.check(L.b200CsrPlanSetSummation(plan, 1))
+            hint_ms["tree_sum"] = timed(lambda: _capi.check(L.b200CsrSpMV(H, plan, d_a.ptr, x.ptr, y.ptr)), 10)
+            _capi.check(L.b200CsrPlanSetSummation(plan, 0))
+            hint_ms["ordered_sum"] = timed(lambda: _capi.check(L.b200CsrSpMV(H, plan, d_a.ptr, x.ptr, y.ptr)), 10)
             alg = nnz * 12 + n * 20
             row = dict(n=n, d=d, nnz=nnz, auto=auto, best=best, hints_ms=hint_ms, algorithmic_bytes=alg, gbs_auto=alg / auto["ms"] / 1e6, gbs_best=alg / best["ms"] / 1e6,
                        frac_auto=alg / auto["ms"] / 1e6 / peak, gflops_auto=(2 * nnz - n) / auto["ms"] / 1e6,
@@ -197,6 +203,8 @@ def main():
             plan = C.c_void_p()
             _capi.check(L.b200CsrPlanCreate(H, N, N, C.c_int64(nnz), d_i.ptr, d_j.ptr, C.byref(plan)))
             fwd_ms = timed(lambda: _capi.check(L.b200CsrSpMV(H, plan, d_a.ptr, x.ptr, y.ptr)), 20)
+            _capi.check(L.b200CsrPlanSetSummation(plan, 1))
+            out["forward_spmv_ms_tree_sum"] = timed(lambda: _capi.check(L.b200CsrSpMV(H, plan, d_a.ptr, x.ptr, y.ptr)), 20)
             L.b200CsrPlanDestroy(plan)
             alg = nnz * 12 + N * 20
             res["transpose_27pt"] = dict(n=n, rows=N, nnz=nnz, create_s=create_s, gather_ms=gather_ms, gather_gbs=nnz * 20 / gather_ms / 1e6, forward_spmv_ms=fwd_ms,
