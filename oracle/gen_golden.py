@@ -84,7 +84,8 @@ def main():
             d, pos = O.getdiagonal(ai, aj, aa)
             aa = aa.copy(); aa[pos] = 12.0
         x, y, V, alpha = vecs(len(ai) - 1, nv)
-        out = run_case(exe, ai, aj, aa, x, y, V, alpha, ["-vec_mdot_use_gemv", "0"])
+        sym = ["-icc"] if meta["gen"] != "stored" else []   # the generated Laplacians are symmetric: record PCApply_ICC too
+        out = run_case(exe, ai, aj, aa, x, y, V, alpha, ["-vec_mdot_use_gemv", "0"] + sym)
         out2 = run_case(exe, ai, aj, aa, x, y, V, alpha, [])
         out["ref_mdot_gemv"] = out2["ref_mdot"]
         rec = dict(x=x, y=y, V=V, alpha=alpha, gen=meta["gen"], args=np.array(meta.get("args", []), dtype=np.int64), **out)
@@ -148,6 +149,10 @@ def main():
         # BASELINE config 3 shape: 27-pt, CG + ILU(0)
         "ksp_lap27_10_cg_ilu": ("lap27", [10], ["-ksp_type", "cg", "-pc_type", "ilu", "-ksp_rtol", "1e-8"]),
         "ksp_lap27_10_gmres_ilu": ("lap27", [10], ["-ksp_type", "gmres", "-pc_type", "ilu", "-ksp_rtol", "1e-8"]),
+        # ICC(0) (ex2's default PC because ex2 marks its matrix symmetric), oracle first
+        "ksp_lap27_10_cg_icc": ("lap27", [10], ["-ksp_type", "cg", "-pc_type", "icc", "-ksp_rtol", "1e-8"]),
+        "ksp_lap5_30_cg_icc": ("lap5", [30, 30], ["-ksp_type", "cg", "-pc_type", "icc", "-ksp_rtol", "1e-8"]),
+        "ksp_lap7_12_gmres_icc": ("lap7", [12, 11, 10], ["-ksp_type", "gmres", "-pc_type", "icc", "-ksp_rtol", "1e-8"]),
     }
     for name, (gen, args, opts) in ksp.items():
         ai, aj, aa = getattr(O, gen)(*args)

@@ -564,6 +564,17 @@ static int pc_setup(ora_pc *pc, int n, const int *ai, const int *aj, const doubl
       if (ora_lu_numeric(ml, li, lj, la, pc->bi[b], pc->bj[b], pc->bdiag[b], pc->ba[b], 100.0 * 2.220446049250313e-16, 100.0 * 2.220446049250313e-16) < 0) return -2;
       free(li); free(lj); free(la);
     }
+  } else if (o->pc_type == ORA_PC_ICC0) {
+    /* icc.c PCCreate_ICC defaults: levels 0, natural ordering, shifttype POSITIVE_DEFINITE, zeropivot 100 eps */
+    pc->nblk   = 1;
+    pc->rstart = (int64_t *)malloc(sizeof(int64_t) * 2);
+    pc->rstart[0] = 0; pc->rstart[1] = n;
+    pc->bi = (int **)calloc(1, sizeof(int *)); pc->bj = (int **)calloc(1, sizeof(int *));
+    pc->bdiag = (int **)calloc(1, sizeof(int *)); pc->ba = (double **)calloc(1, sizeof(double *));
+    pc->bi[0] = (int *)malloc(sizeof(int) * ((size_t)n + 1)); pc->bdiag[0] = (int *)malloc(sizeof(int) * ((size_t)n + 1));
+    pc->bj[0] = (int *)malloc(sizeof(int) * ((size_t)ai[n] + 1)); pc->ba[0] = (double *)calloc((size_t)ai[n] + 1, sizeof(double));
+    if (ora_icc0_symbolic(n, ai, aj, pc->bi[0], pc->bj[0], pc->bdiag[0])) return -1;
+    if (ora_icc0_numeric(n, ai, aj, aa, pc->bi[0], pc->bj[0], pc->bdiag[0], pc->ba[0], 100.0 * 2.220446049250313e-16)) return -2;
   }
   return 0;
 }
@@ -572,6 +583,7 @@ static void pc_apply(const ora_pc *pc, const double *x, double *y)
 {
   if (pc->type == ORA_PC_NONE) memcpy(y, x, sizeof(double) * (size_t)pc->n);
   else if (pc->type == ORA_PC_JACOBI) ora_vecpointwisemult(pc->n, x, pc->dinv, y); /* jacobi.c:354-362 */
+  else if (pc->type == ORA_PC_ICC0) ora_matsolve_icc(pc->n, pc->bi[0], pc->bj[0], pc->bdiag[0], pc->ba[0], x, y);
   else
     for (int b = 0; b < pc->nblk; b++) {
       int r0 = (int)pc->rstart[b], ml = (int)(pc->rstart[b + 1] - pc->rstart[b]);
@@ -917,5 +929,105 @@ void ora_coo_setvalues(int64_t nnz, const int64_t *jmap, const int64_t *perm, co
     double sum = 0.0;
     for (int64_t k = jmap[q]; k < jmap[q + 1]; k++) sum += v[perm[k]];
     Aa[q] = (insert ? 0.0 : Aa[q]) + sum;
+  }
+}
+
+/* ================================================================================================================== */
+/* ICC(0), natural ordering                                                                                           */
+/* ================================================================================================================== */
+int ora_icc0_symbolic(int n, const int *ai, const int *aj, int *ui, int *uj, int *udiag)
+{
+  ui[0] = 0;
+  for (int i = 0; i < n; i++) {
+    int d = -1;
+    for (int k = ai[i]; k < ai[i + 1]; k++)
+      if (aj[k] == i) { d = k; break; }
+    if (d < 0) return -(i + 1);
+    int q = ui[i];
+    for (int k = d + 1; k < ai[i + 1]; k++) uj[q++] = aj[k]; /* strictly upper part, column order */
+    uj[q]     = i;                                           /* the diagonal is the last entry of the row */
+    udiag[i]  = q;
+    ui[i + 1] = q + 1;
+  }
+  return 0;
+}
+
+int ora_icc0_numeric(int n, const int *ai, const int *aj, const double *aa, const int *ui, const int *uj, const int *udiag, double *ua, double zeropivot)
+{
+  double *rtmp = (double *)calloc((size_t)n + 1, sizeof(double));
+  int    *il = (int *)malloc(sizeof(int) * ((size_t)n + 1)), *c2r = (int *)malloc(sizeof(int) * ((size_t)n + 1));
+  int     rc = 0;
+  /* c2r[col]: head of the list of finished rows whose first not-yet-used entry lies in column col (and, for a row that is in
+     such a list, the next row of that list); il[i]: position of that entry in row i */
+  for (int i = 0; i < n; i++) c2r[i] = n;
+  if (n) il[0] = 0;
+  for (int k = 0; k < n; k++) {
+    for (int j = ui[k]; j < ui[k + 1]; j++) rtmp[uj[j]] = 0.0;
+    {
+      double *bval = ua + ui[k];
+      for (int j = ai[k]; j < ai[k + 1]; j++)
+        if (aj[j] >= k) { /* upper triangle of A only */
+          rtmp[aj[j]] = aa[j];
+          *bval++     = 0.0;
+        }
+    }
+    double dk = rtmp[k];
+    int    i  = c2r[k];
+    while (i < k) {
+      const int    nexti = c2r[i];
+      const int    ili   = il[i];
+      const double uikdi = -ua[ili] * ua[udiag[i]];
+      dk += uikdi * ua[ili];
+      ua[ili] = uikdi;
+      const int jmin = ili + 1, jmax = ui[i + 1]; /* through the diagonal slot, exactly as the reference's loop runs */
+      if (jmin < jmax) {
+        for (int j = jmin; j < jmax; j++) rtmp[uj[j]] += uikdi * ua[j];
+        il[i] = jmin;
+        const int j = uj[jmin];
+        c2r[i]      = c2r[j];
+        c2r[j]      = i;
+      }
+      i = nexti;
+    }
+    double    rs   = 0.0;
+    const int jmin = ui[k], jmax = ui[k + 1] - 1;
+    if (jmin < jmax) {
+      for (int j = jmin; j < jmax; j++) {
+        ua[j] = rtmp[uj[j]];
+        rs += fabs(ua[j]);
+      }
+      il[k]        = jmin;
+      const int c  = uj[jmin];
+      c2r[k]       = c2r[c];
+      c2r[c]       = k;
+    }
+    if (dk <= zeropivot * rs) { /* MatPivotCheck_pd would start shifting here */
+      rc = -(k + 1);
+      break;
+    }
+    ua[udiag[k]] = 1.0 / dk;
+  }
+  free(rtmp); free(il); free(c2r);
+  return rc;
+}
+
+void ora_matsolve_icc(int n, const int *ui, const int *uj, const int *udiag, const double *ua, const double *b, double *x)
+{
+  (void)udiag;
+  memcpy(x, b, sizeof(double) * (size_t)n);
+  for (int i = 0; i < n; i++) { /* U^T D y = b */
+    const double xi = x[i];
+    const int    nz = ui[i + 1] - ui[i] - 1;
+    const int   *vj = uj + ui[i];
+    const double *v = ua + ui[i];
+    for (int j = 0; j < nz; j++) x[vj[j]] += v[j] * xi;
+    x[i] = xi * v[nz];
+  }
+  for (int i = n - 2; i >= 0; i--) { /* U x = y, entries from the end of the row backwards */
+    double     xi = x[i];
+    const int  nz = ui[i + 1] - ui[i] - 1;
+    const int  e  = ui[i + 1] - 2; /* last off-diagonal entry */
+    for (int j = 0; j < nz; j++) xi += ua[e - j] * x[uj[e - j]];
+    x[i] = xi;
   }
 }

@@ -46,7 +46,7 @@ class KspResult(C.Structure):
     _fields_ = [("its", C.c_int), ("reason", C.c_int), ("rnorm", C.c_double), ("nhist", C.c_int)]
 
 
-PC = {"none": 0, "jacobi": 1, "ilu": 2, "bjacobi": 3}
+PC = {"none": 0, "jacobi": 1, "ilu": 2, "bjacobi": 3, "icc": 4}
 REFINE = {"never": 0, "ifneeded": 1, "always": 2}
 
 
@@ -227,6 +227,28 @@ def ksp_solve(ksp_type, ai, aj, aa, b, pc="ilu", restart=30, refine="never", max
     if rc:
         raise RuntimeError("oracle KSP setup failed rc=%d" % rc)
     return x, dict(its=res.its, reason=res.reason, rnorm=res.rnorm, hist=hist[:min(res.nhist, cap)].copy())
+
+
+def icc0(ai, aj, aa, zeropivot=100 * 2.220446049250313e-16):
+    """MatICCFactorSymbolic_SeqAIJ (levels 0, natural ordering) + MatCholeskyFactorNumeric_SeqAIJ -> (ui, uj, udiag, ua)."""
+    ai, aj, aa = _i32(ai), _i32(aj), _f64(aa)
+    n = len(ai) - 1
+    ui = np.empty(n + 1, np.int32); udiag = np.empty(n, np.int32); uj = np.empty(len(aj) + 1, np.int32); ua = np.zeros(len(aj) + 1)
+    rc = lib().ora_icc0_symbolic(n, _p(ai), _p(aj), _p(ui), _p(uj), _p(udiag))
+    if rc:
+        raise ValueError("matrix is missing the diagonal entry of row %d" % (-rc - 1))
+    rc = lib().ora_icc0_numeric(n, _p(ai), _p(aj), _p(aa), _p(ui), _p(uj), _p(udiag), _p(ua), C.c_double(zeropivot))
+    if rc:
+        raise ArithmeticError("non-positive pivot in row %d (the reference would shift)" % (-rc - 1))
+    nz = int(ui[-1])
+    return ui, uj[:nz].copy(), udiag, ua[:nz].copy()
+
+
+def matsolve_icc(ui, uj, udiag, ua, b):
+    n = len(ui) - 1
+    x = np.empty(n)
+    lib().ora_matsolve_icc(n, _p(_i32(ui)), _p(_i32(uj)), _p(_i32(udiag)), _p(_f64(ua)), _p(_f64(b)), _p(x))
+    return x
 
 
 def matmulttranspose(ai, aj, aa, x, n=None, z=None):

@@ -228,6 +228,19 @@ int main(int argc, char **argv)
     PetscCall(PCApply(pc, vx, vz));
     PetscCall(VecGetArrayRead(vz, &z)); wr(dir, "ref_ilusolve.f64", z, sizeof(PetscScalar) * m); PetscCall(VecRestoreArrayRead(vz, &z));
     PetscCall(PCDestroy(&pc));
+    {
+      PetscBool doicc = PETSC_FALSE; /* -icc: the matrix is symmetric, also record PCApply of PCICC (ICC(0), natural ordering) */
+      PetscCall(PetscOptionsGetBool(NULL, NULL, "-icc", &doicc, NULL));
+      if (doicc) {
+        PetscCall(PCCreate(PETSC_COMM_SELF, &pc));
+        PetscCall(PCSetType(pc, PCICC));
+        PetscCall(PCSetOperators(pc, A, A));
+        PetscCall(PCSetUp(pc));
+        PetscCall(PCApply(pc, vx, vz));
+        PetscCall(VecGetArrayRead(vz, &z)); wr(dir, "ref_iccsolve.f64", z, sizeof(PetscScalar) * m); PetscCall(VecRestoreArrayRead(vz, &z));
+        PetscCall(PCDestroy(&pc));
+      }
+    }
     PetscCall(PCCreate(PETSC_COMM_SELF, &pc));
     PetscCall(PCSetType(pc, PCJACOBI));
     PetscCall(PCSetOperators(pc, A, A));

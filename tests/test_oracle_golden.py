@@ -105,6 +105,10 @@ def test_ops_bit_exact_vs_reference(oracle, path):
     # PCApply_ILU: ILU(0) numeric + natural-ordering solve
     bi, bj, bdiag, ba = O.ilu0(ai, aj, aa)
     assert np.array_equal(O.matsolve(bi, bj, bdiag, ba, x), g["ref_ilusolve"])
+    # PCApply_ICC: ICC(0) natural ordering (MatCholeskyFactorNumeric_SeqAIJ + MatSolve_SeqSBAIJ_1_NaturalOrdering), symmetric cases
+    if "ref_iccsolve" in g.files:
+        ui, uj, udiag, ua = O.icc0(ai, aj, aa)
+        assert np.array_equal(O.matsolve_icc(ui, uj, udiag, ua, x), g["ref_iccsolve"])
     # MatMultTranspose / MatMultTransposeAdd: increasing-row accumulation into y
     assert np.array_equal(O.matmulttranspose(ai, aj, aa, x), g["ref_multtr"])
     assert np.array_equal(O.matmulttranspose(ai, aj, aa, x, z=y), g["ref_multtradd"])
