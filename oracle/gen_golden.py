@@ -153,6 +153,9 @@ def main():
         "ksp_lap27_10_cg_icc": ("lap27", [10], ["-ksp_type", "cg", "-pc_type", "icc", "-ksp_rtol", "1e-8"]),
         "ksp_lap5_30_cg_icc": ("lap5", [30, 30], ["-ksp_type", "cg", "-pc_type", "icc", "-ksp_rtol", "1e-8"]),
         "ksp_lap7_12_gmres_icc": ("lap7", [12, 11, 10], ["-ksp_type", "gmres", "-pc_type", "icc", "-ksp_rtol", "1e-8"]),
+        # single-reduction CG, oracle first
+        "ksp_lap5_30_pipecg_jacobi": ("lap5", [30, 30], ["-ksp_type", "pipecg", "-pc_type", "jacobi", "-ksp_rtol", "1e-8"]),
+        "ksp_lap27_10_pipecg_icc": ("lap27", [10], ["-ksp_type", "pipecg", "-pc_type", "icc", "-ksp_rtol", "1e-8"]),
     }
     for name, (gen, args, opts) in ksp.items():
         ai, aj, aa = getattr(O, gen)(*args)

@@ -802,6 +802,68 @@ int ora_ksp_cg(int n, const int *ai, const int *aj, const double *aa, const doub
   return 0;
 }
 
+/* KSPSolve_PIPECG (cg/pipecg/pipecg.c:19-160), zero initial guess, KSP_NORM_PRECONDITIONED: the three reductions of an
+   iteration (|u|, r.u, w.u) are posted together and collected after the PCApply + MatMult they overlap with -- the
+   single-reduction CG of SURVEY 8f.3.  Restated for the next round's fused-reduction device KSP. */
+int ora_ksp_pipecg(int n, const int *ai, const int *aj, const double *aa, const double *b, double *x, const ora_ksp_opts *o,
+                   ora_ksp_result *res, double *hist, int histcap)
+{
+  ora_pc pc;
+  g_omp = o->use_omp;
+  int rc = pc_setup(&pc, n, ai, aj, aa, o);
+  if (rc) return rc;
+  const size_t sz = sizeof(double) * (size_t)n;
+  double *R = (double *)malloc(sz), *Z = (double *)malloc(sz), *P = (double *)malloc(sz), *N = (double *)malloc(sz), *W = (double *)malloc(sz);
+  double *Q = (double *)malloc(sz), *U = (double *)malloc(sz), *M = (double *)malloc(sz), *S = (double *)malloc(sz);
+  conv_ctx cv = {0, 0, o->rtol, o->abstol, o->dtol};
+  double   dp, gamma = 0.0, gammaold = 0.0, delta, alpha = 0.0, beta;
+  int      i = 0, reason = 0, nh = 0, its = 0;
+  memset(x, 0, sz);
+  memcpy(R, b, sz);                 /* r <- b (x is 0) */
+  pc_apply(&pc, R, U);              /* u <- Br */
+  dp = ora_vecnorm2(n, U);
+  k_matmult(&pc, U, W);             /* w <- Au */
+  LOGRES(dp);
+  reason = converged_default(&cv, 0, dp);
+  if (!reason) {
+    do {
+      if (i > 0) dp = ora_vecnorm2(n, U);
+      gamma = ora_vecdot(n, R, U);
+      delta = ora_vecdot(n, W, U);
+      pc_apply(&pc, W, M);          /* m <- Bw */
+      k_matmult(&pc, M, N);         /* n <- Am */
+      if (i > 0) {
+        LOGRES(dp);
+        reason = converged_default(&cv, i, dp);
+        if (reason) break;
+      }
+      if (i == 0) {
+        alpha = gamma / delta;
+        memcpy(Z, N, sz); memcpy(Q, M, sz); memcpy(P, U, sz); memcpy(S, W, sz);
+      } else {
+        beta  = gamma / gammaold;
+        alpha = gamma / (delta - beta / alpha * gamma);
+        ora_vecaypx(n, beta, N, Z); /* z <- n + beta z */
+        ora_vecaypx(n, beta, M, Q);
+        ora_vecaypx(n, beta, U, P);
+        ora_vecaypx(n, beta, W, S);
+      }
+      ora_vecaxpy(n, alpha, P, x);
+      ora_vecaxpy(n, -alpha, Q, U);
+      ora_vecaxpy(n, -alpha, Z, W);
+      ora_vecaxpy(n, -alpha, S, R);
+      gammaold = gamma;
+      i++;
+      its = i;
+    } while (i <= o->max_it);
+    if (!reason) reason = -3;
+  }
+  res->its = its; res->reason = reason; res->rnorm = dp; res->nhist = nh;
+  free(R); free(Z); free(P); free(N); free(W); free(Q); free(U); free(M); free(S);
+  pc_destroy(&pc);
+  return 0;
+}
+
 /* ================================================================================================================== */
 /* widening rows: transposed product and COO assembly                                                                 */
 /* ================================================================================================================== */
