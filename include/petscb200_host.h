@@ -67,6 +67,7 @@ typedef const char *KSPType;
 #define PCILU     "ilu"
 #define KSPGMRES   "gmres"
 #define KSPCG      "cg"
+#define KSPPIPECG  "pipecg" /* cg/pipecg/pipecg.c: the three reductions of an iteration fused into one kernel + one synchronisation */
 #define KSPPREONLY "preonly"
 
 typedef enum { NORM_1 = 0, NORM_2 = 1, NORM_FROBENIUS = 2, NORM_INFINITY = 3 } NormType;   /* include/petscvec.h */

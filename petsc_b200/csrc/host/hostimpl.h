@@ -267,6 +267,7 @@ PetscErrorCode KSPConvergedDefault(KSP ksp, PetscInt n, PetscReal rnorm, KSPConv
 PetscErrorCode KSPInitialResidual(KSP ksp, Vec vsoln, Vec vt1, Vec vt2, Vec vres, Vec vb);
 PetscErrorCode KSPCreate_GMRES(KSP ksp);
 PetscErrorCode KSPCreate_CG(KSP ksp);
+PetscErrorCode KSPCreate_PIPECG(KSP ksp);
 PetscErrorCode KSPCreate_PREONLY(KSP ksp);
 PetscErrorCode PCCreate_None(PC pc);
 PetscErrorCode PCCreate_Jacobi(PC pc);

@@ -13,6 +13,7 @@ static PetscErrorCode KSPRegisterAll(void)
   KSPRegisterAllCalled = 1;
   PetscCall(KSPRegister(KSPGMRES, KSPCreate_GMRES));
   PetscCall(KSPRegister(KSPCG, KSPCreate_CG));
+  PetscCall(KSPRegister(KSPPIPECG, KSPCreate_PIPECG));
   PetscCall(KSPRegister(KSPPREONLY, KSPCreate_PREONLY));
   return PETSC_SUCCESS;
 }
@@ -696,6 +697,95 @@ PetscErrorCode KSPCreate_CG(KSP ksp)
 {
   ksp->ops.setup = KSPSetUp_CG;
   ksp->ops.solve = KSPSolve_CG;
+  return PETSC_SUCCESS;
+}
+
+/* ================================================================== PIPECG (cg/pipecg/pipecg.c:19-160), preconditioned norm
+   The single-reduction CG of SURVEY 8f.3: |u|^2, r.u and w.u of an iteration come out of ONE kernel (VecMDot of u against
+   {u, r, w}: one pass over the three vectors, one result transfer, one all-reduce of three numbers on several GPUs) instead of
+   the three separate reductions -- and three host synchronisations -- of KSPCG.  The PCApply and MatMult that do not depend on
+   those numbers are enqueued first, so the device works through them while the host waits for the reduction (the overlap
+   the reference gets from VecNormBegin/VecDotBegin + PetscCommSplitReductionBegin). */
+static PetscErrorCode KSPSetUp_PIPECG(KSP ksp)
+{
+  ksp->nwork = 9; /* pipecg.c KSPSetUp_PIPECG: KSPSetWorkVecs(ksp, 9) */
+  PetscCall(VecDuplicateVecs(ksp->vec_rhs, 9, &ksp->work));
+  return PETSC_SUCCESS;
+}
+static PetscErrorCode KSPSolve_PIPECG(KSP ksp)
+{
+  PetscInt    i;
+  PetscScalar alpha = 0.0, beta = 0.0, gamma = 0.0, gammaold = 0.0, delta = 0.0, red[3];
+  PetscReal   dp = 0.0;
+  Vec         X = ksp->vec_sol, B = ksp->vec_rhs, R = ksp->work[0], Z = ksp->work[1], P = ksp->work[2], N = ksp->work[3], W = ksp->work[4];
+  Vec         Q = ksp->work[5], U = ksp->work[6], M = ksp->work[7], S = ksp->work[8], ys[3];
+  Mat         Amat = ksp->pc->mat;
+  ksp->its = 0;
+  if (!ksp->guess_zero) {
+    PetscCall(MatMult(Amat, X, R));
+    PetscCall(VecAYPX(R, -1.0, B));
+  } else PetscCall(VecCopy(B, R));
+  PetscCall(PCApply(ksp->pc, R, U)); /* u <- Br */
+  PetscCall(MatMult(Amat, U, W));    /* w <- Au */
+  PetscCall(VecNorm(U, NORM_2, &dp));
+  if (isnan(dp) || isinf(dp)) {
+    ksp->reason = KSP_DIVERGED_NANORINF;
+    return PETSC_SUCCESS;
+  }
+  PetscCall(KSPLogResidualHistory(ksp, dp));
+  PetscCall(KSPMonitor(ksp, 0, dp));
+  ksp->rnorm = dp;
+  PetscCall(KSPConvergedDefault(ksp, 0, dp, &ksp->reason));
+  if (ksp->reason) return PETSC_SUCCESS;
+  ys[0] = U; ys[1] = R; ys[2] = W;
+  i = 0;
+  do {
+    PetscCall(PCApply(ksp->pc, W, M));   /* m <- Bw   (independent of the reduction below) */
+    PetscCall(MatMult(Amat, M, N));      /* n <- Am */
+    PetscCall(VecMDot(U, 3, ys, red));   /* |u|^2, r.u, w.u: one kernel, one synchronisation */
+    gamma = red[1];
+    delta = red[2];
+    if (i > 0) {
+      dp = sqrt(fabs(red[0]));
+      if (isnan(dp) || isinf(dp)) {
+        ksp->reason = KSP_DIVERGED_NANORINF;
+        return PETSC_SUCCESS;
+      }
+      ksp->rnorm = dp;
+      PetscCall(KSPLogResidualHistory(ksp, dp));
+      PetscCall(KSPMonitor(ksp, i, dp));
+      PetscCall(KSPConvergedDefault(ksp, i, dp, &ksp->reason));
+      if (ksp->reason) return PETSC_SUCCESS;
+    }
+    if (i == 0) {
+      alpha = gamma / delta;
+      PetscCall(VecCopy(N, Z)); /* z <- n */
+      PetscCall(VecCopy(M, Q)); /* q <- m */
+      PetscCall(VecCopy(U, P)); /* p <- u */
+      PetscCall(VecCopy(W, S)); /* s <- w */
+    } else {
+      beta  = gamma / gammaold;
+      alpha = gamma / (delta - beta / alpha * gamma);
+      PetscCall(VecAYPX(Z, beta, N)); /* z <- n + beta z */
+      PetscCall(VecAYPX(Q, beta, M));
+      PetscCall(VecAYPX(P, beta, U));
+      PetscCall(VecAYPX(S, beta, W));
+    }
+    PetscCall(VecAXPY(X, alpha, P));  /* x <- x + alpha p */
+    PetscCall(VecAXPY(U, -alpha, Q)); /* u <- u - alpha q */
+    PetscCall(VecAXPY(W, -alpha, Z)); /* w <- w - alpha z */
+    PetscCall(VecAXPY(R, -alpha, S)); /* r <- r - alpha s */
+    gammaold = gamma;
+    i++;
+    ksp->its = i;
+  } while (i <= ksp->max_it);
+  if (!ksp->reason) ksp->reason = KSP_DIVERGED_ITS;
+  return PETSC_SUCCESS;
+}
+PetscErrorCode KSPCreate_PIPECG(KSP ksp)
+{
+  ksp->ops.setup = KSPSetUp_PIPECG;
+  ksp->ops.solve = KSPSolve_PIPECG;
   return PETSC_SUCCESS;
 }
 
