@@ -96,6 +96,14 @@ int b200CsrPlanSetLayout(b200CsrPlan plan, int lanes_per_row, int rows_per_tile,
        products are then added in column order): y is bit-identical to MatMult_SeqAIJ for every layout, at 0.6-1.0x the
        speed of the tree variant (5x faster than forcing one lane per row on 27-entry rows) */
 int b200CsrPlanSetSummation(b200CsrPlan plan, int tree);
+/* column-blocked layout for matrices whose gathered vector does not stay in the L2 (random CSR with n*8 bytes >> L2/2): the
+   columns are cut into nblocks ranges and y = A x runs as nblocks passes y += A_b x in column order, each touching only
+   8*n/nblocks bytes of x; every pass continues the row sum of the previous one, so an exact summation stays exact.
+   nblocks <= 1 removes the blocked copy.  The blocked SpMV multiplies with a PACKED copy of the values:
+   b200CsrPlanPackValues must be called after b200CsrPlanSetColumnBlocks and after every change of the values; the d_val
+   argument of b200CsrSpMV* is then ignored.  Costs 16 B/nnz of extra device memory. */
+int b200CsrPlanSetColumnBlocks(b200Handle h, b200CsrPlan plan, int nblocks);
+int b200CsrPlanPackValues(b200Handle h, b200CsrPlan plan, const double *d_val);
 /* L2 hints: bit0 = stream val/col/rowptr as evict_first, bit1 = keep x as evict_last, bit2 = persisting access-policy
    window on x for the launch (default: 2 for one lane per row, else 3, plus bit2 when x fits the L2 set-aside) */
 int b200CsrPlanSetCacheHints(b200CsrPlan plan, int hints);
@@ -152,6 +160,13 @@ int b200VecMDot(b200Handle h, int64_t n, int nv, const double *d_x, const double
 int b200VecMAXPY(b200Handle h, int64_t n, int nv, const double *alpha, const double *const *y, double *d_x, double *norm2_out);
 /* y += alpha x and dot = y_new . z in one pass (fused AXPY+dot; z may be y for the squared norm) */
 int b200VecAXPYDot(b200Handle h, int64_t n, double alpha, const double *d_x, double *d_y, const double *d_z, double *result);
+/* the eight vector recurrences of one KSPPIPECG iteration in one pass (cg/pipecg/pipecg.c:124-141):
+     first != 0:  z = n, q = m, p = u, s = w                       (VecCopy x4)
+     else      :  z = n + beta z, q = m + beta q, p = u + beta p, s = w + beta s   (VecAYPX x4)
+     then      :  x += alpha p, u -= alpha q, w -= alpha z, r -= alpha s             (VecAXPY x4)
+   bit-identical to the eight separate calls; all ten vectors must be distinct */
+int b200VecPipeCGUpdate(b200Handle h, int64_t n, double alpha, double beta, int first, const double *d_n, const double *d_m, double *d_u, double *d_w,
+                        double *d_z, double *d_q, double *d_p, double *d_s, double *d_x, double *d_r);
 /* device-result variants (no host sync): results land in d_result[nv]; used by the MPI vector type, which all-reduces
    them before the single device->host copy (pvecimpl.h:97-172) */
 int b200VecMDotAsync(b200Handle h, int64_t n, int nv, const double *d_x, const double *const *y, double *d_result);

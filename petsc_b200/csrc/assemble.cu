@@ -15,7 +15,8 @@
  *   b200CsrTranspose*     MatMultTranspose_SeqAIJ / MatMultTransposeAdd_SeqAIJ (aij.c:1383-1440): y[c] accumulates x[i]*a[k] in
  *                         increasing row order.  An explicit transposed pattern (column-major order of A's entries, stable in
  *                         the row index) turns this into the row-ordered FMA-free sum the SpMV kernel already computes, so the
- *                         result is bit-identical to the reference and runs at the SpMV roofline; the value permutation is
+ *                         result is bit-identical to the reference with the SpMV plan's exact summation (one lane per row, or
+ *                         b200CsrPlanSetSummation(plan, 0)) and equal to rounding at the SpMV roofline otherwise; the value permutation is
  *                         re-applied (one gather pass) only when A's values change.
  *
  * Setup-time helpers use cub (CUDA toolkit header library) for sort / scan.

@@ -689,6 +689,73 @@ extern "C" int b200VecMAXPY(b200Handle h, int64_t n, int nv, const double *alpha
   return 0;
 }
 
+/* ------------------------------------------------------------------ KSPPIPECG vector recurrences in one pass
+   pipecg.c:124-141: four VecAYPX (or VecCopy in the first iteration) and four VecAXPY, here one kernel: 10 vectors read,
+   8 written (18 n doubles of traffic instead of 24 n, one launch instead of eight).  Every entry goes through exactly the
+   expressions of the separate kernels (x + a*y, y + a*x, same contraction), so the result is bit-identical to them. */
+template <bool VEC2>
+__global__ void __launch_bounds__(TPB) pipecg_update_kernel(int64_t n, double alpha, double beta, int first, const double *__restrict__ vn, const double *__restrict__ vm, double *u, double *w, double *z, double *q, double *p, double *s, double *x, double *r)
+{
+  const int64_t stride = (int64_t)gridDim.x * TPB;
+  const double  na     = -alpha;
+  auto one = [&](double nn, double mm, double &uu, double &ww, double &zz, double &qq, double &pp, double &ss, double &xx, double &rr) {
+    if (first) {
+      zz = nn; qq = mm; pp = uu; ss = ww;
+    } else {
+      zz = nn + beta * zz; /* VecAYPX(Z, beta, N) */
+      qq = mm + beta * qq;
+      pp = uu + beta * pp;
+      ss = ww + beta * ss;
+    }
+    xx = xx + alpha * pp;  /* VecAXPY(X, alpha, P) */
+    uu = uu + na * qq;     /* VecAXPY(U, -alpha, Q) */
+    ww = ww + na * zz;
+    rr = rr + na * ss;
+  };
+  if (VEC2) {
+    const int64_t  nvec = n >> 1;
+    const double2 *n2 = reinterpret_cast<const double2 *>(vn), *m2 = reinterpret_cast<const double2 *>(vm);
+    double2       *u2 = reinterpret_cast<double2 *>(u), *w2 = reinterpret_cast<double2 *>(w), *z2 = reinterpret_cast<double2 *>(z), *q2 = reinterpret_cast<double2 *>(q);
+    double2       *p2 = reinterpret_cast<double2 *>(p), *s2 = reinterpret_cast<double2 *>(s), *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < nvec; i += stride) {
+      const double2 nn = n2[i], mm = m2[i];
+      double2       uu = u2[i], ww = w2[i], xx = x2[i], rr = r2[i], zz, qq, pp, ss;
+      if (first) zz = qq = pp = ss = make_double2(0.0, 0.0);
+      else { zz = z2[i]; qq = q2[i]; pp = p2[i]; ss = s2[i]; }
+      one(nn.x, mm.x, uu.x, ww.x, zz.x, qq.x, pp.x, ss.x, xx.x, rr.x);
+      one(nn.y, mm.y, uu.y, ww.y, zz.y, qq.y, pp.y, ss.y, xx.y, rr.y);
+      z2[i] = zz; q2[i] = qq; p2[i] = pp; s2[i] = ss; x2[i] = xx; u2[i] = uu; w2[i] = ww; r2[i] = rr;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+      const int64_t i = n - 1;
+      double        uu = u[i], ww = w[i], xx = x[i], rr = r[i], zz = first ? 0.0 : z[i], qq = first ? 0.0 : q[i], pp = first ? 0.0 : p[i], ss = first ? 0.0 : s[i];
+      one(vn[i], vm[i], uu, ww, zz, qq, pp, ss, xx, rr);
+      z[i] = zz; q[i] = qq; p[i] = pp; s[i] = ss; x[i] = xx; u[i] = uu; w[i] = ww; r[i] = rr;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
+      double uu = u[i], ww = w[i], xx = x[i], rr = r[i], zz = first ? 0.0 : z[i], qq = first ? 0.0 : q[i], pp = first ? 0.0 : p[i], ss = first ? 0.0 : s[i];
+      one(vn[i], vm[i], uu, ww, zz, qq, pp, ss, xx, rr);
+      z[i] = zz; q[i] = qq; p[i] = pp; s[i] = ss; x[i] = xx; u[i] = uu; w[i] = ww; r[i] = rr;
+    }
+  }
+}
+
+extern "C" int b200VecPipeCGUpdate(b200Handle h, int64_t n, double alpha, double beta, int first, const double *d_n, const double *d_m, double *d_u, double *d_w, double *d_z, double *d_q, double *d_p, double *d_s, double *d_x, double *d_r)
+{
+  B200_CHECK(h, B200_ERR_ARG_NULL, "null handle");
+  B200_CHECK(n >= 0, B200_ERR_ARG_OUTOFRANGE, "negative length");
+  if (!n) return 0;
+  B200_CHECK(d_n && d_m && d_u && d_w && d_z && d_q && d_p && d_s && d_x && d_r, B200_ERR_ARG_NULL, "null vector");
+  const bool vec2 = aligned16(d_n) && aligned16(d_m) && aligned16(d_u) && aligned16(d_w) && aligned16(d_z) && aligned16(d_q) && aligned16(d_p) && aligned16(d_s) && aligned16(d_x) && aligned16(d_r);
+  const int  g    = ew_grid(h, vec2 ? (n >> 1) : n);
+  if (vec2) pipecg_update_kernel<true><<<g, TPB, 0, h->stream>>>(n, alpha, beta, first, d_n, d_m, d_u, d_w, d_z, d_q, d_p, d_s, d_x, d_r);
+  else pipecg_update_kernel<false><<<g, TPB, 0, h->stream>>>(n, alpha, beta, first, d_n, d_m, d_u, d_w, d_z, d_q, d_p, d_s, d_x, d_r);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  return 0;
+}
+
 /* ------------------------------------------------------------------ fused AXPY + dot */
 template <bool VEC2>
 __global__ void __launch_bounds__(TPB) axpy_dot_kernel(int64_t n, double a, const double *__restrict__ x, double *y, const double *z, double *partials, unsigned int *counter, double *d_result, double *h_result)

@@ -720,6 +720,8 @@ static PetscErrorCode KSPSolve_PIPECG(KSP ksp)
   Vec         X = ksp->vec_sol, B = ksp->vec_rhs, R = ksp->work[0], Z = ksp->work[1], P = ksp->work[2], N = ksp->work[3], W = ksp->work[4];
   Vec         Q = ksp->work[5], U = ksp->work[6], M = ksp->work[7], S = ksp->work[8], ys[3];
   Mat         Amat = ksp->pc->mat;
+  PetscBool   fuse = PETSC_TRUE; /* -ksp_pipecg_b200_fuse_update <bool>: the eight vector recurrences as one kernel */
+  PetscCall(PetscOptionsGetBool(NULL, ksp->hdr.prefix, "-ksp_pipecg_b200_fuse_update", &fuse, NULL));
   ksp->its = 0;
   if (!ksp->guess_zero) {
     PetscCall(MatMult(Amat, X, R));
@@ -757,24 +759,52 @@ static PetscErrorCode KSPSolve_PIPECG(KSP ksp)
       PetscCall(KSPConvergedDefault(ksp, i, dp, &ksp->reason));
       if (ksp->reason) return PETSC_SUCCESS;
     }
-    if (i == 0) {
-      alpha = gamma / delta;
-      PetscCall(VecCopy(N, Z)); /* z <- n */
-      PetscCall(VecCopy(M, Q)); /* q <- m */
-      PetscCall(VecCopy(U, P)); /* p <- u */
-      PetscCall(VecCopy(W, S)); /* s <- w */
-    } else {
+    if (i == 0) alpha = gamma / delta;
+    else {
       beta  = gamma / gammaold;
       alpha = gamma / (delta - beta / alpha * gamma);
-      PetscCall(VecAYPX(Z, beta, N)); /* z <- n + beta z */
-      PetscCall(VecAYPX(Q, beta, M));
-      PetscCall(VecAYPX(P, beta, U));
-      PetscCall(VecAYPX(S, beta, W));
     }
-    PetscCall(VecAXPY(X, alpha, P));  /* x <- x + alpha p */
-    PetscCall(VecAXPY(U, -alpha, Q)); /* u <- u - alpha q */
-    PetscCall(VecAXPY(W, -alpha, Z)); /* w <- w - alpha z */
-    PetscCall(VecAXPY(R, -alpha, S)); /* r <- r - alpha s */
+    if (fuse) {
+      /* the four VecCopy/VecAYPX and four VecAXPY below as ONE kernel (b200VecPipeCGUpdate): same arithmetic per entry */
+      const double *dn, *dm;
+      double       *du, *dw, *dz, *dq, *dp, *ds, *dx, *dr;
+      PetscInt      nloc;
+      PetscCall(VecGetLocalSize(X, &nloc));
+      PetscCall(VecB200GetArrayRead(N, &dn));
+      PetscCall(VecB200GetArrayRead(M, &dm));
+      PetscCall(VecB200GetArray(U, &du));
+      PetscCall(VecB200GetArray(W, &dw));
+      if (i == 0) {
+        PetscCall(VecB200GetArrayWrite(Z, &dz));
+        PetscCall(VecB200GetArrayWrite(Q, &dq));
+        PetscCall(VecB200GetArrayWrite(P, &dp));
+        PetscCall(VecB200GetArrayWrite(S, &ds));
+      } else {
+        PetscCall(VecB200GetArray(Z, &dz));
+        PetscCall(VecB200GetArray(Q, &dq));
+        PetscCall(VecB200GetArray(P, &dp));
+        PetscCall(VecB200GetArray(S, &ds));
+      }
+      PetscCall(VecB200GetArray(X, &dx));
+      PetscCall(VecB200GetArray(R, &dr));
+      PetscCallB200(b200VecPipeCGUpdate(PetscB200.h, nloc, alpha, beta, i == 0, dn, dm, du, dw, dz, dq, dp, ds, dx, dr));
+    } else {
+      if (i == 0) {
+        PetscCall(VecCopy(N, Z)); /* z <- n */
+        PetscCall(VecCopy(M, Q)); /* q <- m */
+        PetscCall(VecCopy(U, P)); /* p <- u */
+        PetscCall(VecCopy(W, S)); /* s <- w */
+      } else {
+        PetscCall(VecAYPX(Z, beta, N)); /* z <- n + beta z */
+        PetscCall(VecAYPX(Q, beta, M));
+        PetscCall(VecAYPX(P, beta, U));
+        PetscCall(VecAYPX(S, beta, W));
+      }
+      PetscCall(VecAXPY(X, alpha, P));  /* x <- x + alpha p */
+      PetscCall(VecAXPY(U, -alpha, Q)); /* u <- u - alpha q */
+      PetscCall(VecAXPY(W, -alpha, Z)); /* w <- w - alpha z */
+      PetscCall(VecAXPY(R, -alpha, S)); /* r <- r - alpha s */
+    }
     gammaold = gamma;
     i++;
     ksp->its = i;

@@ -63,16 +63,6 @@ __device__ __forceinline__ void wait_ready(const int *flag, int row, int epoch)
   }
 }
 
-/* Dynamic CTA index: CTAs are numbered in the order they actually start, so a CTA only ever waits on rows owned by
-   CTAs that are already running or finished. */
-__device__ __forceinline__ int take_ticket(int *ticket)
-{
-  __shared__ int s_t;
-  if (threadIdx.x == 0) s_t = atomicAdd(ticket, 1);
-  __syncthreads();
-  return s_t;
-}
-
 #define ILU_BATCH 4
 __device__ __forceinline__ int warp_ticket(int *ticket)
 {

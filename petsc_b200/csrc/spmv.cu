@@ -26,6 +26,7 @@
  * Algorithmic bytes per call: nnz*(8+4) + m*(4+8+8).
  */
 #include "b200_internal.h"
+#include <cub/device/device_scan.cuh>
 #include <stdlib.h>
 #include <string.h>
 
@@ -53,6 +54,25 @@ struct b200CsrPlan_s {
                                   the last bits; one lane per row is always exact); 0: the reference's left-to-right FMA-free
                                   order for every lane count */
   int        hints_auto;
+  struct CsrBlocks *blk;       /* column-blocked copy (b200CsrPlanSetColumnBlocks) or NULL */
+};
+
+/* Column-blocked layout for matrices whose gathered vector does not stay in the L2 (random CSR, SURVEY config 5): the columns
+   are cut into nb ranges, every range is a CSR matrix of its own over ALL rows (entries of a row inside a range are
+   contiguous because rows are sorted), and y = A x becomes nb passes y += A_b x that each touch only 8 n / nb bytes of x.
+   The passes run in column order and each pass continues the row sum where the previous one stopped, so with an exact
+   per-pass summation the result is still the reference's left-to-right sum.  Values are kept packed in block order
+   (b200CsrPlanPackValues after every value change). */
+#define SPMV_MAX_BLOCKS 64
+struct CsrBlocks {
+  int         nb, ms;                    /* blocks; row-pointer stride (m+1 rounded up to 4) */
+  int        *d_rowptr;                  /* nb * ms */
+  int        *d_col, *d_perm;            /* blocked columns; original position of every blocked entry */
+  double     *d_val;                     /* packed values */
+  int64_t     off[SPMV_MAX_BLOCKS + 1];  /* element offset of every block (multiples of 4) */
+  int64_t     tot;                       /* allocated elements */
+  b200CsrPlan sub[SPMV_MAX_BLOCKS];
+  int         packed;
 };
 
 /* ------------------------------------------------------------------ PTX helpers: mbarrier + 1-D TMA bulk copy */
@@ -457,8 +477,21 @@ extern "C" int b200CsrPlanCreate(b200Handle h, int m, int n, int64_t nnz, const 
   return 0;
 }
 
+static void csr_blocks_free(struct CsrBlocks *B)
+{
+  if (!B) return;
+  for (int b = 0; b < B->nb; b++)
+    if (B->sub[b]) b200CsrPlanDestroy(B->sub[b]);
+  cudaFree(B->d_rowptr);
+  cudaFree(B->d_col);
+  cudaFree(B->d_perm);
+  cudaFree(B->d_val);
+  free(B);
+}
+
 extern "C" int b200CsrPlanDestroy(b200CsrPlan plan)
 {
+  if (plan) csr_blocks_free(plan->blk);
   free(plan);
   return 0;
 }
@@ -470,6 +503,11 @@ extern "C" int b200CsrPlanSetLayout(b200CsrPlan p, int lanes, int rows_per_tile,
   B200_CHECK(rows_per_tile == 0 || (rows_per_tile >= 8 && rows_per_tile <= 2048 && (rows_per_tile & (rows_per_tile - 1)) == 0), B200_ERR_ARG_OUTOFRANGE, "rows_per_tile must be 0 or a power of two in [8,2048]");
   B200_CHECK(stages >= 0 && stages <= SPMV_MAX_STAGES && ctas_per_sm >= 0 && ctas_per_sm <= 8, B200_ERR_ARG_OUTOFRANGE, "stages/ctas out of range");
   p->user_lanes = lanes; p->user_rows = rows_per_tile; p->user_stages = stages; p->user_ctas = ctas_per_sm;
+  if (p->blk) /* the column blocks follow the lane choice; their tiles are sized from their own row lengths */
+    for (int b = 0; b < p->blk->nb; b++) {
+      int rc = b200CsrPlanSetLayout(p->blk->sub[b], lanes, 0, 0, 0);
+      if (rc) return rc;
+    }
   return plan_configure(p);
 }
 
@@ -487,6 +525,134 @@ extern "C" int b200CsrPlanSetSummation(b200CsrPlan p, int tree)
   B200_CHECK(p, B200_ERR_ARG_NULL, "null plan");
   B200_CHECK(tree == 0 || tree == 1, B200_ERR_ARG_OUTOFRANGE, "summation mode must be 0 (reference order) or 1 (tree)");
   p->tree_sum = tree;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ column-blocked layout (set-up kernels) */
+__global__ void blk_count_kernel(int m, int ms, int nb, int cw, const int *__restrict__ rowptr, const int *__restrict__ colidx, int *brow)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < ms; r += stride) {
+    int k = r < m ? rowptr[r] : 0;
+    const int ke = r < m ? rowptr[r + 1] : 0;
+    for (int b = 0; b < nb; b++) {
+      const int64_t bound = b == nb - 1 ? (int64_t)1 << 40 : (int64_t)(b + 1) * cw;
+      int           cnt   = 0;
+      while (k < ke && colidx[k] < bound) { k++; cnt++; }
+      brow[(int64_t)b * ms + r] = cnt; /* rows >= m count 0: the exclusive scan leaves the block total at index m */
+    }
+  }
+}
+__global__ void blk_fill_kernel(int m, int ms, int nb, const int *__restrict__ rowptr, const int *__restrict__ colidx, const int *__restrict__ brow, const long long *__restrict__ off, int *col, int *perm)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
+    int k = rowptr[r];
+    for (int b = 0; b < nb; b++) {
+      const int     s = brow[(int64_t)b * ms + r], e = brow[(int64_t)b * ms + r + 1];
+      const int64_t base = off[b] + s;
+      for (int t = 0; t < e - s; t++, k++) {
+        col[base + t]  = colidx[k];
+        perm[base + t] = k;
+      }
+    }
+  }
+}
+__global__ void blk_pack_kernel(int64_t tot, const int *__restrict__ perm, const double *__restrict__ val, double *out)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < tot; k += stride) out[k] = val[perm[k]];
+}
+
+/* nblocks <= 1 removes the blocked copy.  The plan keeps using the caller's rowptr/colidx for its own (unblocked) layout. */
+extern "C" int b200CsrPlanSetColumnBlocks(b200Handle h, b200CsrPlan p, int nblocks)
+{
+  B200_CHECK(h && p, B200_ERR_ARG_NULL, "null argument");
+  B200_CHECK(nblocks >= 0 && nblocks <= SPMV_MAX_BLOCKS, B200_ERR_ARG_OUTOFRANGE, "number of column blocks must be in [0,%d]", SPMV_MAX_BLOCKS);
+  csr_blocks_free(p->blk);
+  p->blk = NULL;
+  if (nblocks <= 1 || p->m == 0 || p->nnz == 0) return 0;
+  struct CsrBlocks *B = (struct CsrBlocks *)calloc(1, sizeof(*B));
+  B200_CHECK(B, B200_ERR_MEM, "out of host memory");
+  const int m = p->m, ms = (m + 1 + 3) & ~3, nb = nblocks, cw = (p->n + nb - 1) / nb;
+  B->nb = nb; B->ms = ms;
+  int        rc = 0;
+  void      *tmp = NULL;
+  long long *d_off = NULL;
+  int       *tot = (int *)malloc(sizeof(int) * (size_t)nb);
+#define BLK_CUDA(call) \
+  do { \
+    cudaError_t e_ = (call); \
+    if (e_ != cudaSuccess) { \
+      b200_set_error(B200_ERR_GPU, "cuda error %d (%s) : %s at %s:%d", (int)e_, cudaGetErrorName(e_), cudaGetErrorString(e_), __FILE__, __LINE__); \
+      rc = B200_ERR_GPU; \
+      goto done; \
+    } \
+  } while (0)
+  {
+    int64_t g = ((int64_t)ms + 255) / 256;
+    if (g > (int64_t)h->num_sms * 16) g = (int64_t)h->num_sms * 16;
+    BLK_CUDA(cudaMalloc(&B->d_rowptr, sizeof(int) * (size_t)nb * ms));
+    blk_count_kernel<<<(int)g, 256, 0, h->stream>>>(m, ms, nb, cw, p->d_rowptr, p->d_colidx, B->d_rowptr);
+    B200_LAUNCHED(1);
+    BLK_CUDA(cudaPeekAtLastError());
+    size_t tmp_bytes = 0;
+    BLK_CUDA(cub::DeviceScan::ExclusiveSum(NULL, tmp_bytes, B->d_rowptr, B->d_rowptr, m + 1, h->stream));
+    BLK_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    for (int b = 0; b < nb; b++) {
+      BLK_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, B->d_rowptr + (size_t)b * ms, B->d_rowptr + (size_t)b * ms, m + 1, h->stream));
+      BLK_CUDA(cudaMemcpyAsync(&tot[b], B->d_rowptr + (size_t)b * ms + m, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
+    B200_LAUNCHED(nb);
+    BLK_CUDA(cudaStreamSynchronize(h->stream));
+    B->off[0] = 0;
+    for (int b = 0; b < nb; b++) B->off[b + 1] = B->off[b] + (((int64_t)tot[b] + 3) & ~(int64_t)3) + 4; /* 16-byte aligned starts, slack for the kernel's 16-byte over-read */
+    B->tot = B->off[nb];
+    BLK_CUDA(cudaMalloc(&B->d_col, sizeof(int) * (size_t)B->tot + B200_ALLOC_PAD));
+    BLK_CUDA(cudaMalloc(&B->d_perm, sizeof(int) * (size_t)B->tot + B200_ALLOC_PAD));
+    BLK_CUDA(cudaMalloc(&B->d_val, sizeof(double) * (size_t)B->tot + B200_ALLOC_PAD));
+    BLK_CUDA(cudaMemsetAsync(B->d_col, 0, sizeof(int) * (size_t)B->tot, h->stream));
+    BLK_CUDA(cudaMemsetAsync(B->d_perm, 0, sizeof(int) * (size_t)B->tot, h->stream));
+    BLK_CUDA(cudaMalloc(&d_off, sizeof(long long) * (size_t)(nb + 1)));
+    {
+      long long hoff[SPMV_MAX_BLOCKS + 1];
+      for (int b = 0; b <= nb; b++) hoff[b] = (long long)B->off[b];
+      BLK_CUDA(cudaMemcpyAsync(d_off, hoff, sizeof(long long) * (size_t)(nb + 1), cudaMemcpyHostToDevice, h->stream));
+      blk_fill_kernel<<<(int)g, 256, 0, h->stream>>>(m, ms, nb, p->d_rowptr, p->d_colidx, B->d_rowptr, d_off, B->d_col, B->d_perm);
+      B200_LAUNCHED(1);
+      BLK_CUDA(cudaPeekAtLastError());
+      BLK_CUDA(cudaStreamSynchronize(h->stream)); /* hoff is on this stack frame */
+    }
+    for (int b = 0; b < nb && !rc; b++) {
+      rc = b200CsrPlanCreate(h, m, p->n, (int64_t)tot[b], B->d_rowptr + (size_t)b * ms, B->d_col + B->off[b], &B->sub[b]);
+      if (!rc && p->user_lanes) rc = b200CsrPlanSetLayout(B->sub[b], p->user_lanes, 0, 0, 0);
+    }
+  }
+done:
+  cudaFree(tmp);
+  cudaFree(d_off);
+  free(tot);
+  if (rc) {
+    csr_blocks_free(B);
+    return rc;
+  }
+  p->blk = B;
+  return 0;
+#undef BLK_CUDA
+}
+
+/* gathers the values into block order; call after every change of the matrix values (the blocked SpMV uses this copy) */
+extern "C" int b200CsrPlanPackValues(b200Handle h, b200CsrPlan p, const double *d_val)
+{
+  B200_CHECK(h && p, B200_ERR_ARG_NULL, "null argument");
+  if (!p->blk) return 0;
+  B200_CHECK(d_val, B200_ERR_ARG_NULL, "null value array");
+  int64_t g = (p->blk->tot + 255) / 256;
+  if (g > (int64_t)h->num_sms * 16) g = (int64_t)h->num_sms * 16;
+  blk_pack_kernel<<<(int)g, 256, 0, h->stream>>>(p->blk->tot, p->blk->d_perm, d_val, p->blk->d_val);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  p->blk->packed = 1;
   return 0;
 }
 
@@ -536,9 +702,33 @@ static int spmv_launch_lanes(b200Handle h, b200CsrPlan p, const double *val, con
 
 /* hints bit 2: the gathered vector x is given a persisting access-policy window for the duration of the launch (the CSR
    streams then miss as "streaming" and cannot push x out of the L2); the set-aside is raised once per handle */
+static int spmv_launch(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain);
+
+/* nb passes in column order; the partial row sums live in yplain (fused-Jacobi form) or in yout itself */
+static int spmv_launch_blocked(b200Handle h, b200CsrPlan p, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
+{
+  struct CsrBlocks *B = p->blk;
+  B200_CHECK(B->packed, B200_ERR_ORDER, "b200CsrPlanPackValues must be called after the matrix values changed");
+  B200_CHECK(yout && x, B200_ERR_ARG_NULL, "null vector pointer");
+  double *acc = yplain ? yplain : yout;
+  for (int b = 0; b < B->nb; b++) {
+    b200CsrPlan   s    = B->sub[b];
+    const double *in   = b == 0 ? yin : acc;
+    const double *vb   = B->d_val + B->off[b];
+    const bool    last = b == B->nb - 1;
+    int           rc;
+    s->tree_sum = p->tree_sum;
+    if (!last) rc = spmv_launch(h, s, vb, x, in, NULL, acc, NULL);
+    else rc = spmv_launch(h, s, vb, x, in, dinv, yout, dinv ? yplain : NULL);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 static int spmv_launch(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
 {
   B200_CHECK(h && p, B200_ERR_ARG_NULL, "null handle/plan");
+  if (p->blk && p->m) return spmv_launch_blocked(h, p, x, yin, dinv, yout, yplain);
   if (!(p->hints & 4) || h->l2_persist_max <= 0 || h->l2_window_max <= 0 || !x) return spmv_launch_lanes(h, p, val, x, yin, dinv, yout, yplain);
   if (!h->l2_persist_set) {
     B200_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)h->l2_persist_max));

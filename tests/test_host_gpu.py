@@ -302,3 +302,11 @@ def test_pipecg_single_reduction_matches_cg(P, oracle):
     _, o = oracle.ksp_solve("pipecg", ai, aj, aa, oracle.matmult(ai, aj, aa, np.ones(n)), pc="jacobi", rtol=1e-9)
     k = min(30, len(o["hist"]), len(pc["hist"]))
     assert abs(o["its"] - pc["its"]) <= 1 and np.allclose(pc["hist"][:k], o["hist"][:k], rtol=1e-9, atol=1e-12 * o["hist"][0])
+    # the one-kernel form of the eight vector recurrences (default) is the same arithmetic as the eight separate kernels
+    un = solve(P, ai, aj, aa, "-ksp_type pipecg -pc_type jacobi -ksp_rtol 1e-9 -ksp_pipecg_b200_fuse_update 0")
+    assert un["its"] == pc["its"] and np.array_equal(un["hist"], pc["hist"]) and np.array_equal(un["x"], pc["x"])
+    # an odd length exercises the scalar tail of the vectorised kernel
+    ai2, aj2, aa2 = oracle.lap5(13, 7)
+    a = solve(P, ai2, aj2, aa2, "-ksp_type pipecg -pc_type jacobi -ksp_rtol 1e-10")
+    b = solve(P, ai2, aj2, aa2, "-ksp_type pipecg -pc_type jacobi -ksp_rtol 1e-10 -ksp_pipecg_b200_fuse_update 0")
+    assert a["reason"] == 2 and a["its"] == b["its"] and np.array_equal(a["hist"], b["hist"]) and np.array_equal(a["x"], b["x"])

@@ -105,6 +105,58 @@ def test_spmv_every_layout_is_bit_exact_tree_mode_within_tolerance(H, oracle):
             assert np.array_equal(d_y.download(), ref), (name, rows, stages, ctas)
 
 
+def test_spmv_column_blocks_keep_the_reference_order(H, oracle):
+    """b200CsrPlanSetColumnBlocks: y = A x as nb passes over column ranges (x stays L2-resident per pass).  The passes continue
+    each other's row sums in column order, so with the exact summation every result is still bit-identical to MatMult_SeqAIJ /
+    MatMultAdd_SeqAIJ / the fused Jacobi form, for every lane count; the tree summation stays within tolerance."""
+    from petsc_b200 import _capi
+    L = _capi.lib()
+    rng = np.random.default_rng(18)
+    for name, (ai, aj, aa) in matrices(oracle):
+        m = len(ai) - 1
+        ncol = max(int(aj.max()) + 1 if len(aj) else m, m)
+        x = rng.uniform(-1, 1, ncol); y0 = rng.uniform(-1, 1, m); dinv = rng.uniform(0.5, 2.0, m)
+        d_ai, d_aj, d_aa = H.array(ai, np.int32), H.array(aj, np.int32), H.array(aa, np.float64)
+        plan = H.csr_plan(m, ncol, len(aj), d_ai, d_aj)
+        d_x, d_y, d_y0, d_z, d_dinv, d_w = H.array(x), H.empty(m), H.array(y0), H.empty(m), H.array(dinv), H.empty(m)
+        ref, refadd = oracle.matmult(ai, aj, aa, x), oracle.matmultadd(ai, aj, aa, x, y0)
+        scale = max(np.abs(ref).max() if m else 1.0, 1e-300)
+        for nb in (2, 3, 7):
+            _capi.check(L.b200CsrPlanSetColumnBlocks(H.h, plan, nb))
+            assert L.b200CsrSpMV(H.h, plan, d_aa.ptr, d_x.ptr, d_y.ptr) == 58, name   # PETSC_ERR_ORDER: values not packed yet
+            _capi.check(L.b200CsrPlanPackValues(H.h, plan, d_aa.ptr))
+            _capi.check(L.b200CsrPlanSetSummation(plan, 0))
+            for lanes in (0, 1, 4, 32):
+                H.csr_plan_set_layout(plan, lanes=lanes)
+                H.spmv(plan, d_aa, d_x, d_y)
+                assert np.array_equal(d_y.download(), ref), (name, nb, lanes)
+                H.spmv_add(plan, d_aa, d_x, d_y0, d_z)                      # z = y0 + A x, out of place
+                assert np.array_equal(d_z.download(), refadd), (name, nb, lanes)
+                d_z.upload(y0)
+                H.spmv_add(plan, d_aa, d_x, d_z, d_z)                       # in place
+                assert np.array_equal(d_z.download(), refadd), (name, nb, lanes)
+                H.spmv_jacobi(plan, d_aa, d_x, d_dinv, d_w, d_y)            # w = dinv .* (A x), y = A x
+                assert np.array_equal(d_y.download(), ref) and np.array_equal(d_w.download(), ref * dinv), (name, nb, lanes)
+                H.spmv_jacobi(plan, d_aa, d_x, d_dinv, d_w)                 # without the plain product
+                assert np.array_equal(d_w.download(), ref * dinv), (name, nb, lanes)
+            _capi.check(L.b200CsrPlanSetSummation(plan, 1))
+            H.csr_plan_set_layout(plan, lanes=8)
+            H.spmv(plan, d_aa, d_x, d_y)
+            assert np.abs(d_y.download() - ref).max() <= RTOL * scale, (name, nb)
+        # new values: pack again; then drop the blocks
+        aa2 = aa * 0.5
+        d_aa.upload(aa2)
+        _capi.check(L.b200CsrPlanPackValues(H.h, plan, d_aa.ptr))
+        _capi.check(L.b200CsrPlanSetSummation(plan, 0))
+        H.spmv(plan, d_aa, d_x, d_y)
+        assert np.array_equal(d_y.download(), oracle.matmult(ai, aj, aa2, x)), name
+        _capi.check(L.b200CsrPlanSetColumnBlocks(H.h, plan, 0))
+        H.csr_plan_set_layout(plan, lanes=1)
+        H.spmv(plan, d_aa, d_x, d_y)
+        assert np.array_equal(d_y.download(), oracle.matmult(ai, aj, aa2, x)), name
+        L.b200CsrPlanDestroy(plan)
+
+
 def test_spmv_fixture_vs_reference(H, oracle):
     """Committed outputs of the reference's own MatMult_SeqAIJ / MatMultAdd / GetDiagonal / PCApply_Jacobi."""
     from petsc_b200 import _capi

@@ -89,6 +89,18 @@ def main():
             hint_ms["tree_sum"] = timed(lambda: _capi.check(L.b200CsrSpMV(H, plan, d_a.ptr, x.ptr, y.ptr)), 10)
             _capi.check(L.b200CsrPlanSetSummation(plan, 0))
             hint_ms["ordered_sum"] = timed(lambda: _capi.check(L.b200CsrSpMV(H, plan, d_a.ptr, x.ptr, y.ptr)), 10)
+            # column-blocked passes (x block stays in the L2): nb = 2, 4, 8; values packed once (timed separately)
+            blocked = {}
+            if d > 5 and "nb" in what:
+                y_ref = y.download()
+                for nb in (2, 4, 8):
+                    _capi.check(L.b200CsrPlanSetColumnBlocks(H, plan, nb))
+                    pack_ms = timed(lambda: _capi.check(L.b200CsrPlanPackValues(H, plan, d_a.ptr)), 3, warm=1)
+                    ms = timed(lambda: _capi.check(L.b200CsrSpMV(H, plan, d_a.ptr, x.ptr, y.ptr)), 10)
+                    err = float(np.abs(y.download() - y_ref).max() / max(np.abs(y_ref).max(), 1e-300))
+                    blocked[str(nb)] = dict(ms=ms, pack_ms=pack_ms, rel_diff_vs_unblocked=err)
+                _capi.check(L.b200CsrPlanSetColumnBlocks(H, plan, 0))
+            hint_ms["column_blocks"] = blocked
             alg = nnz * 12 + n * 20
             row = dict(n=n, d=d, nnz=nnz, auto=auto, best=best, hints_ms=hint_ms, algorithmic_bytes=alg, gbs_auto=alg / auto["ms"] / 1e6, gbs_best=alg / best["ms"] / 1e6,
                        frac_auto=alg / auto["ms"] / 1e6 / peak, gflops_auto=(2 * nnz - n) / auto["ms"] / 1e6,
@@ -175,6 +187,40 @@ def main():
                                                    rows_per_group=os.environ.get("PETSCB200_ILU_ROWS_PER_GROUP", "auto"))
         print("config4", res["config4_block_gmres_ilu0_7pt"], flush=True)
         ksp.destroy(); A.destroy()
+
+    if "p" in what:
+        # fused-reduction CG (KSPPIPECG: 1 synchronisation per iteration) against KSPCG (3) on the 27-point operator, Jacobi
+        res["pipecg_vs_cg_27pt"] = []
+        for n in (48, 128, 256):
+            N = n ** 3
+            nnz = C.c_int64()
+            _capi.check(L.b200GenLaplace27Nnz(n, C.byref(nnz)))
+            nnz = nnz.value
+            d_i, d_j, d_a = _capi.DeviceArray(Hh, N + 1, np.int32), _capi.DeviceArray(Hh, nnz, np.int32), _capi.DeviceArray(Hh, nnz, np.float64)
+            _capi.check(L.b200GenLaplace27(H, n, d_i.ptr, d_j.ptr, d_a.ptr))
+            A = petsc.Mat.create(m=N, n=N, M=N, N=N, comm=petsc.COMM_SELF)
+            A.set_csr_device(d_i.ptr, d_j.ptr, d_a.ptr)
+            for o in (d_i, d_j, d_a):
+                o.free()
+            x, b = A.create_vecs()
+            u = x.duplicate(); u.set(1.0); A.mult(u, b)
+            row = dict(n=n, rows=N, nnz=nnz)
+            for kt in ("cg", "pipecg", "pipecg_unfused"):
+                petsc.options_clear()
+                petsc.options_insert("-ksp_type %s -pc_type jacobi -ksp_rtol 1e-8%s" % (kt.split("_")[0], " -ksp_pipecg_b200_fuse_update 0" if kt.endswith("unfused") else ""))
+                ksp = petsc.KSP.create(petsc.COMM_SELF)
+                ksp.set_operators(A); ksp.set_from_options()
+                ksp.solve(b, x)
+                t = _capi.Timer(Hh)
+                t.start(); ksp.solve(b, x); t.stop()
+                row[kt] = dict(iterations=ksp.its(), reason=ksp.reason(), solve_ms=t.ms(), us_per_iteration=1e3 * t.ms() / max(ksp.its(), 1))
+                ksp.destroy()
+            res["pipecg_vs_cg_27pt"].append(row)
+            print("pipecg", row, flush=True)
+            for o in (x, b, u):
+                o.destroy()
+            A.destroy()
+        petsc.options_clear()
 
     if "tr" in what or "coo" in what:
         # widening rows: transposed product and COO assembly on the 27-point operator (n = --nasm)
