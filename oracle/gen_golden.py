@@ -156,6 +156,10 @@ def main():
         # single-reduction CG, oracle first
         "ksp_lap5_30_pipecg_jacobi": ("lap5", [30, 30], ["-ksp_type", "pipecg", "-pc_type", "jacobi", "-ksp_rtol", "1e-8"]),
         "ksp_lap27_10_pipecg_icc": ("lap27", [10], ["-ksp_type", "pipecg", "-pc_type", "icc", "-ksp_rtol", "1e-8"]),
+        # pipelined GMRES (one reduction per iteration, used one iteration later), with restarts and without
+        "ksp_lap5_30_pgmres_jacobi": ("lap5", [30, 30], ["-ksp_type", "pgmres", "-pc_type", "jacobi", "-ksp_rtol", "1e-8"]),
+        "ksp_lap7_12_pgmres_ilu": ("lap7", [12, 11, 10], ["-ksp_type", "pgmres", "-pc_type", "ilu", "-ksp_rtol", "1e-8"]),
+        "ksp_lap5_30_pgmres5_none": ("lap5", [30, 30], ["-ksp_type", "pgmres", "-ksp_gmres_restart", "5", "-pc_type", "none", "-ksp_rtol", "1e-3"]),
     }
     for name, (gen, args, opts) in ksp.items():
         ai, aj, aa = getattr(O, gen)(*args)

@@ -802,6 +802,141 @@ int ora_ksp_cg(int n, const int *ai, const int *aj, const double *aa, const doub
   return 0;
 }
 
+/* KSPSolve_PGMRES / KSPPGMRESCycle (gmres/pgmres/pgmres.c:17-206, update :226-301, build :176-206): pipelined GMRES with one
+   reduction per iteration, posted one iteration before it is used.  The reference's split reductions (VecNormBegin /
+   VecMDotBegin) compute their local part when they are BEGUN, so the values below are taken at those points.  Left
+   preconditioning, preconditioned norm; restated for the next round's pipelined device KSP. */
+int ora_ksp_pgmres(int n, const int *ai, const int *aj, const double *aa, const double *b, double *x, const ora_ksp_opts *o,
+                   ora_ksp_result *res, double *hist, int histcap)
+{
+  const int max_k = o->restart;
+  ora_pc    pc;
+  g_omp = o->use_omp;
+  int rc = pc_setup(&pc, n, ai, aj, aa, o);
+  if (rc) return rc;
+  const int nvv = max_k + 3;
+  double  **vv  = (double **)malloc(sizeof(double *) * (size_t)nvv);
+  for (int i = 0; i < nvv; i++) vv[i] = (double *)malloc(sizeof(double) * (size_t)n);
+  double *temp = (double *)malloc(sizeof(double) * (size_t)n), *tmat = (double *)malloc(sizeof(double) * (size_t)n);
+  double *hh  = (double *)calloc((size_t)(max_k + 2) * (max_k + 2), sizeof(double));
+  double *hes = (double *)calloc((size_t)(max_k + 2) * (max_k + 2), sizeof(double));
+  double *grs = (double *)calloc((size_t)max_k + 3, sizeof(double)), *cc = (double *)calloc((size_t)max_k + 3, sizeof(double));
+  double *ss = (double *)calloc((size_t)max_k + 3, sizeof(double)), *nrs = (double *)calloc((size_t)max_k + 3, sizeof(double));
+  double *work = (double *)calloc((size_t)max_k + 3, sizeof(double));
+#define PHH(a, b)  (hh + (size_t)(b) * (max_k + 2) + (a))
+#define PHES(a, b) (hes + (size_t)(b) * (max_k + 2) + (a))
+  conv_ctx cv = {0, 0, o->rtol, o->abstol, o->dtol};
+  int      its = 0, reason = 0, nh = 0, guess_zero = 1, itcount = 0;
+  double   rnorm = -1.0;
+  vzero(n, x);
+  while (!reason) {
+    /* KSPInitialResidual, left PC */
+    if (!guess_zero) {
+      k_matmult(&pc, x, temp);
+      vcopy(n, b, tmat);
+      ora_vecaxpy(n, -1.0, temp, tmat);
+      pc_apply(&pc, tmat, vv[0]);
+    } else pc_apply(&pc, b, vv[0]);
+    /* ---- KSPPGMRESCycle ---- */
+    int    it = 0, hapend = 0;
+    double resn = ora_vecnorm2(n, vv[0]), pending_norm = 0.0;
+    if (resn != 0.0) ora_vecscale(n, 1.0 / resn, vv[0]);
+    grs[0] = resn;
+    rnorm  = resn;
+    LOGRES(rnorm);
+    if (!resn) { reason = 3; break; }
+    reason = converged_default(&cv, its, rnorm);
+    for (; !reason; it++) {
+      double *Zcur = vv[it], *Znext = vv[it + 1];
+      if (it < max_k + 1 && its + 1 < (o->max_it > 2 ? o->max_it : 2)) { /* Znext <- B A Zcur */
+        k_matmult(&pc, Zcur, tmat);
+        pc_apply(&pc, tmat, Znext);
+      }
+      if (it > 1) *PHH(it - 1, it - 2) = pending_norm;  /* VecNormEnd of the norm begun one iteration ago */
+      /* (the VecMDotEnd of this point delivers column it-1 of H: written when it was begun, below) */
+      if (it > 1) {
+        ora_vecscale(n, 1.0 / *PHH(it - 1, it - 2), vv[it - 1]);
+        { /* KSPPGMRESUpdateHessenberg(ksp, it - 2, ...) */
+          const int c  = it - 2;
+          double   *h  = PHH(0, c);
+          for (int j = 0; j <= c + 1; j++) *PHES(j, c) = h[j];
+          double hapbnd = fabs(h[c + 1] / grs[c]);
+          if (hapbnd > 1.0e-30) hapbnd = 1.0e-30;
+          if (fabs(h[c + 1]) < hapbnd) hapend = 1;
+          for (int j = 0; j < c; j++) {
+            const double hhj = h[j];
+            h[j]     = cc[j] * hhj + ss[j] * h[j + 1];
+            h[j + 1] = -ss[j] * hhj + cc[j] * h[j + 1];
+          }
+          if (!hapend) {
+            const double delta = sqrt(h[c] * h[c] + h[c + 1] * h[c + 1]);
+            if (delta == 0.0) { reason = -2; break; }
+            cc[c]      = h[c] / delta;
+            ss[c]      = h[c + 1] / delta;
+            h[c]       = cc[c] * h[c] + ss[c] * h[c + 1];
+            grs[c + 1] = -ss[c] * grs[c];
+            grs[c]     = cc[c] * grs[c];
+            resn       = fabs(grs[c + 1]);
+          } else resn = 0.0;
+        }
+        its++;
+        rnorm  = resn;
+        reason = converged_default(&cv, its, rnorm);
+        if (reason) break;
+        if (it < max_k + 1) LOGRES(rnorm);
+        if (hapend) { reason = -5; break; }
+        if (!(it < max_k + 1 && its < o->max_it)) break;
+        {
+          const double sc = *PHH(it - 1, it - 2);
+          ora_vecscale(n, 1.0 / sc, Zcur);
+          ora_vecscale(n, 1.0 / sc, Znext);
+          for (int k = 0; k < it; k++) *PHH(k, it - 1) /= sc;
+          *PHH(it - 1, it - 1) /= sc;
+        }
+      }
+      if (it > 0) {
+        for (int k = 0; k < it + 1; k++) {
+          work[k] = 0;
+          for (int j = (k - 1 > 0 ? k - 1 : 0); j < it - 1; j++) work[k] -= *PHES(k, j) * *PHH(j, it - 1);
+        }
+        ora_vecmaxpy(n, it + 1, work, (const double *const *)vv, Znext);
+        ora_vecaxpy(n, -*PHH(it - 1, it - 1), Zcur, Znext);
+        for (int k = 0; k < it; k++) work[k] = -*PHH(k, it - 1);
+        ora_vecmaxpy(n, it, work, (const double *const *)vv, Zcur);
+        pending_norm = ora_vecnorm2(n, vv[it]); /* VecNormBegin(VEC_VV(it)) */
+      }
+      ora_vecmdot(n, it + 1, Znext, (const double *const *)vv, PHH(0, it)); /* VecMDotBegin(Znext, it+1, VV, HH(0,it)) */
+    }
+    itcount += it - 1 > 0 ? it - 1 : 0;
+    /* KSPPGMRESBuildSoln(RS, x, x, ksp, it - 2) */
+    {
+      const int k = it - 2;
+      if (k >= 0) {
+        nrs[k] = *PHH(k, k) != 0.0 ? grs[k] / *PHH(k, k) : 0.0;
+        for (int kk = k - 1; kk >= 0; kk--) {
+          double tt = grs[kk];
+          for (int j = kk + 1; j <= k; j++) tt -= *PHH(kk, j) * nrs[j];
+          nrs[kk] = tt / *PHH(kk, kk);
+        }
+        vzero(n, temp);
+        ora_vecmaxpy(n, k + 1, nrs, (const double *const *)vv, temp);
+        ora_vecaxpy(n, 1.0, temp, x);
+      }
+    }
+    if (!reason && its == o->max_it) reason = -3;
+    if (reason) LOGRES(rnorm);
+    if (itcount >= o->max_it) { if (!reason) reason = -3; break; }
+    guess_zero = 0;
+  }
+#undef PHH
+#undef PHES
+  res->its = its; res->reason = reason; res->rnorm = rnorm; res->nhist = nh;
+  for (int i = 0; i < nvv; i++) free(vv[i]);
+  free(vv); free(temp); free(tmat); free(hh); free(hes); free(grs); free(cc); free(ss); free(nrs); free(work);
+  pc_destroy(&pc);
+  return 0;
+}
+
 /* KSPSolve_PIPECG (cg/pipecg/pipecg.c:19-160), zero initial guess, KSP_NORM_PRECONDITIONED: the three reductions of an
    iteration (|u|, r.u, w.u) are posted together and collected after the PCApply + MatMult they overlap with -- the
    single-reduction CG of SURVEY 8f.3.  Restated for the next round's fused-reduction device KSP. */

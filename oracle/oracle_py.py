@@ -222,7 +222,7 @@ def ksp_solve(ksp_type, ai, aj, aa, b, pc="ilu", restart=30, refine="never", max
     cap = max_it + max_it // max(restart, 1) + 8
     hist = np.zeros(cap, np.float64)
     x = np.zeros(n, np.float64)
-    f = {"gmres": lib().ora_ksp_gmres, "cg": lib().ora_ksp_cg, "pipecg": lib().ora_ksp_pipecg}[ksp_type]
+    f = {"gmres": lib().ora_ksp_gmres, "cg": lib().ora_ksp_cg, "pipecg": lib().ora_ksp_pipecg, "pgmres": lib().ora_ksp_pgmres}[ksp_type]
     rc = f(n, _p(ai), _p(aj), _p(aa), _p(_f64(b)), _p(x), C.byref(o), C.byref(res), _p(hist), cap)
     if rc:
         raise RuntimeError("oracle KSP setup failed rc=%d" % rc)

@@ -131,9 +131,13 @@ def test_vec_ops_offload_and_norm_cache(P, oracle):
 
 OPS = sorted(glob.glob(golden_path("ops_*.npz")))
 def _device_path_exists(path):
-    """ICC(0) fixtures pin the ORACLE only so far (tests/test_oracle_golden.py; the device factorisation is the next round's):
-    they are not run through the host mirror."""
-    return "icc" not in [str(s) for s in np.load(path)["opts"]]
+    """ICC(0) and pipelined-GMRES fixtures pin the ORACLE only so far (tests/test_oracle_golden.py; their device paths are the
+    next round's): they are not run through the host mirror.  Whitelist, so that a new oracle-only fixture can never turn
+    into a failing device test by accident."""
+    opts = [str(s) for s in np.load(path)["opts"]]
+    ksp = opts[opts.index("-ksp_type") + 1] if "-ksp_type" in opts else "gmres"
+    pc = opts[opts.index("-pc_type") + 1] if "-pc_type" in opts else "ilu"
+    return ksp in ("gmres", "cg", "pipecg", "preonly") and pc in ("none", "jacobi", "ilu", "bjacobi")
 
 
 KSPF = [p for p in sorted(glob.glob(golden_path("ksp_*.npz"))) if _device_path_exists(p)]
