@@ -267,6 +267,20 @@ def run_e2e(a, D, petsc, _capi, L, H, Hh, d_i, d_j, d_a, nloc, nnz, comm, K):
         _capi.check(L.b200MallocHost(C.byref(p), C.c_size_t(nbytes)))
         return p
 
+    # the user's pinned host buffers (12.9 GB per rank): if any rank cannot get them (host memory / cgroup limit with many
+    # ranks on one node), every rank skips the e2e leg together instead of one rank failing inside a collective
+    bufs, fail = [], 0.0
+    try:
+        for nb in (8 * nloc, 8 * nloc, 4 * (nloc + 1), 4 * nnz, 8 * nnz):
+            bufs.append(pinned(nb))
+    except Exception as e:  # noqa: BLE001
+        fail, why = 1.0, str(e).splitlines()[0][:200]
+    if D.max(fail) > 0:
+        for p in bufs:
+            L.b200FreeHost(p)
+        d_i.free(); d_j.free(); d_a.free()
+        return {"skipped": "pinned host buffers for the end-to-end leg could not be allocated on every rank" + (": " + why if fail else "")}
+    h_b, h_x, h_i, h_j, h_a = bufs
     # untimed prelude: b = A*1 from the device copy of the generator's CSR (global columns: x = ones of the global length)
     Nglob = nloc * D.size
     ones = _capi.DeviceArray(Hh, Nglob, np.float64)
@@ -275,11 +289,9 @@ def run_e2e(a, D, petsc, _capi, L, H, Hh, d_i, d_j, d_a, nloc, nnz, comm, K):
     plan0 = vp()
     _capi.check(L.b200CsrPlanCreate(H, nloc, Nglob, C.c_int64(nnz), d_i.ptr, d_j.ptr, C.byref(plan0)))
     _capi.check(L.b200CsrSpMV(H, plan0, d_a.ptr, ones.ptr, d_b.ptr))
-    h_b, h_x = pinned(8 * nloc), pinned(8 * nloc)
     _capi.check(L.b200MemcpyDtoH(H, h_b, d_b.ptr, C.c_size_t(8 * nloc)))
     L.b200CsrPlanDestroy(plan0)
     ones.free(); d_b.free()
-    h_i, h_j, h_a = pinned(4 * (nloc + 1)), pinned(4 * nnz), pinned(8 * nnz)
     _capi.check(L.b200MemcpyDtoH(H, h_i, d_i.ptr, C.c_size_t(4 * (nloc + 1))))
     _capi.check(L.b200MemcpyDtoH(H, h_j, d_j.ptr, C.c_size_t(4 * nnz)))
     _capi.check(L.b200MemcpyDtoH(H, h_a, d_a.ptr, C.c_size_t(8 * nnz)))
