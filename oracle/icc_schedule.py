@@ -48,6 +48,33 @@ def merge_schedule(ui, uj):
     return np.array(ptr, np.int64), np.array(rows, np.int64), np.array(pos, np.int64)
 
 
+def solve_gather(ui, uj, udiag, final, b):
+    """MatSolve_SeqSBAIJ_1_NaturalOrdering (sbaijfact2.c:2030-2065) without scatters, the form a level-scheduled device sweep
+    needs: the forward sweep's x[c] += v(i,c) * x_i over rows i in ascending order is a GATHER along column c of U (= row c
+    of the transposed pattern, ascending i) of the UNSCALED y_i, followed by one multiply with 1/D(c); the backward sweep
+    gathers along row i from its last off-diagonal entry to its first."""
+    n = len(ui) - 1
+    # transposed pattern of the strictly upper part: for column c the entries (i, c), i ascending (rows are visited in order)
+    tcols = [[] for _ in range(n)]
+    for i in range(n):
+        for t in range(int(ui[i]), int(ui[i + 1]) - 1):
+            tcols[int(uj[t])].append((i, t))
+    y = np.zeros(n)       # unscaled forward values
+    x = np.zeros(n)
+    for c in range(n):
+        s = b[c]
+        for i, t in tcols[c]:
+            s = s + final[t] * y[i]
+        y[c] = s
+        x[c] = s * final[udiag[c]]
+    for i in range(n - 2, -1, -1):
+        s = x[i]
+        for t in range(int(ui[i + 1]) - 2, int(ui[i]) - 1, -1):
+            s = s + final[t] * x[int(uj[t])]
+        x[i] = s
+    return x
+
+
 def levels(ptr, rows):
     n = len(ptr) - 1
     lev = np.zeros(n, np.int64)

@@ -32,6 +32,8 @@ def test_rowwise_icc_with_reference_merge_order_is_bit_exact(oracle, path):
     assert np.array_equal(final, ua)
     # and the factor solves to the reference's PCApply(PCICC) output
     assert np.array_equal(oracle.matsolve_icc(ui, uj, udiag, final, g["x"]), g["ref_iccsolve"])
+    # the scatter-free (gather) form of the two sweeps, as a level-scheduled device kernel will run them
+    assert np.array_equal(S.solve_gather(ui, uj, udiag, final, g["x"]), g["ref_iccsolve"])
     # the schedule's dependency levels: rows only wait for rows of strictly lower level
     lev = S.levels(ptr, rows)
     assert all(lev[rows[q]] < lev[k] for k in range(n) for q in range(ptr[k], ptr[k + 1]))
