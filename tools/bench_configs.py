@@ -147,7 +147,7 @@ def main():
         res["config3_cg_ilu0_27pt"] = dict(n=n, rows=N, nnz=nnz, iterations=its, reason=ksp.reason(), max_error=err, first_solve_incl_setup_s=first, solve_ms=solve_ms,
                                            ms_per_iteration=solve_ms / max(its, 1), iterations_per_sec=its / (solve_ms * 1e-3), spmv_ms=spmv_ms, spmv_gbs=alg_spmv / spmv_ms / 1e6,
                                            pcapply_ilu_ms=pcapply_ms, sptrsv_gbs=alg_sptrsv / pcapply_ms / 1e6, sptrsv_frac_of_peak=alg_sptrsv / pcapply_ms / 1e6 / peak,
-                                           levels=3 * n + 4 * (n - 1) - 2, rows_per_group=os.environ.get("PETSCB200_ILU_ROWS_PER_GROUP", "auto"))
+                                           levels=3 * n + 4 * (n - 1) - 2)
         print("config3", res["config3_cg_ilu0_27pt"], flush=True)
         ksp.destroy(); A.destroy()
 
@@ -183,8 +183,7 @@ def main():
         alg_sptrsv = nnz * 12 + N * (4 + 4 + 4 + 4 + 8 * 3)
         res["config4_block_gmres_ilu0_7pt"] = dict(n=n, rows=N, nnz=nnz, iterations=its, reason=ksp.reason(), first_solve_incl_setup_s=first, solve_ms=t.ms(),
                                                    ms_per_iteration=t.ms() / max(its, 1), pcapply_ilu_ms=pcapply_ms, levels=3 * (n - 1) + 1,
-                                                   sptrsv_gbs=alg_sptrsv / pcapply_ms / 1e6, sptrsv_frac_of_peak=alg_sptrsv / pcapply_ms / 1e6 / peak,
-                                                   rows_per_group=os.environ.get("PETSCB200_ILU_ROWS_PER_GROUP", "auto"))
+                                                   sptrsv_gbs=alg_sptrsv / pcapply_ms / 1e6, sptrsv_frac_of_peak=alg_sptrsv / pcapply_ms / 1e6 / peak)
         print("config4", res["config4_block_gmres_ilu0_7pt"], flush=True)
         ksp.destroy(); A.destroy()
 
