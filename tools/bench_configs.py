@@ -4,8 +4,10 @@
   config 3: 27-point 256^3, KSPCG + PCILU(0)  (ILU(0) numeric on device, sync-free sweeps)
   config 5: random CSR sweep n = 10 M (2.5 M for d = 512: 32-bit PetscInt), d in {5, 32, 128, 512}, MatMult only
   config 1: ex2 100x100 GMRES(30)+Jacobi (latency-bound small case)
+  4       : the per-rank block of config 4 (7-point ILU(0) PCApply);  nb (with 5): column-blocked passes;
+  tr / coo: transposed product and COO assembly on the 27-point operator (--nasm);  p: KSPPIPECG vs KSPCG
 
-usage: python tools/bench_configs.py [--what 3,5,1] [--n27 256] [--out gpurun_out/configs.json]
+usage: python tools/bench_configs.py [--what 3,5,1,4,nb,tr,coo,p] [--n27 256] [--out gpurun_out/configs.json]
 """
 import argparse
 import ctypes as C
