@@ -244,6 +244,15 @@ PetscErrorCode KSPGMRESSetRestart(KSP ksp, PetscInt restart);
 PetscErrorCode KSPGMRESSetCGSRefinementType(KSP ksp, KSPGMRESCGSRefinementType type);
 PetscErrorCode KSPDestroy(KSP *ksp);
 
+/* ---- ICC(0): host-side symbolic phase of the planned device factorisation (csrc/host/iccsym.c) ----------
+   Index work only, caller-allocated outputs; the numeric kernels that consume these schedules are the next round's. */
+/* MatICCFactorSymbolic_SeqAIJ levels 0, natural ordering (aijfact.c:2078-2094): ui[n+1], uj[<= ai[n]], udiag[n] */
+PetscErrorCode PetscB200ICC0Symbolic(PetscInt n, const PetscInt *ai, const PetscInt *aj, PetscInt *ui, PetscInt *uj, PetscInt *udiag);
+/* merge order of MatCholeskyFactorNumeric_SeqAIJ (aijfact.c:1750-1800) + dependency levels: mptr[n+1], mrow/mpos[ui[n]-n], level[n] */
+PetscErrorCode PetscB200ICC0MergeSchedule(PetscInt n, const PetscInt *ui, const PetscInt *uj, PetscInt *mptr, PetscInt *mrow, PetscInt *mpos, PetscInt *level, PetscInt *nlevels);
+/* column view for the scatter-free forward sweep of MatSolve_SeqSBAIJ_1_NaturalOrdering: tptr[n+1], trow/tpos[ui[n]-n] */
+PetscErrorCode PetscB200ICC0ColumnView(PetscInt n, const PetscInt *ui, const PetscInt *uj, PetscInt *tptr, PetscInt *trow, PetscInt *tpos);
+
 #ifdef __cplusplus
 }
 #endif
