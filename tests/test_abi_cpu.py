@@ -16,6 +16,11 @@ def test_kernel_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
     assert b"sm_100a" in L.b200Version()
+    # and the other direction: the shared object exports no b200* entry point that include/petscb200.h does not declare
+    import subprocess
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _capi.LIB_PATH], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l and l.split()[-1].startswith("b200")}
+    assert exported == set(names), sorted(exported ^ set(names))
 
 
 def test_host_library_exports_every_declared_symbol():
