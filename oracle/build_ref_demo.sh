@@ -1,7 +1,6 @@
 #!/bin/bash
 # Builds the reference-side demo artefacts into oracle/_ref/ (git-ignored; they travel to the GPU box with gpurun):
-#   oracle/_ref/petsc/lib/libpetsc.so*     the reference library as configured by the survey stage from an UNMODIFIED copy of
-#                                          /root/reference (CPU-only, MPIUNI, -O2) -- copied, not rebuilt
+#   (oracle/_ref/petsc/lib/libpetsc.so*    the reference library, built by oracle/build_ref.sh from /root/reference: CPU-only, MPIUNI, -O2)
 #   oracle/_ref/petsc/bin/ex2              the reference's own tutorial programs, compiled from the sources where they lie
 #   oracle/_ref/petsc/bin/bench_kspsolve   under /root/reference/src/ksp/ksp/tutorials/ (never copied into the repo)
 #   oracle/_ref/ref_driver                 oracle/ref_driver.c (our driver against the reference's public API)
@@ -10,18 +9,18 @@
 # Only runs in the build container (needs /root/reference and the configured PETSc build).  No reference SOURCE is copied.
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"; ROOT="$(dirname "$HERE")"
-PETSC_DIR="${PETSC_DIR:-/tmp/petsc-probe}"; PETSC_ARCH="${PETSC_ARCH:-arch-probe}"; REF=/root/reference
+REF=/root/reference
 BLASDIR=/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs
-[ -d "$PETSC_DIR/$PETSC_ARCH/lib" ] || { echo "no configured PETSc at $PETSC_DIR/$PETSC_ARCH: skipping the reference demo build"; exit 0; }
-OUT="$HERE/_ref/petsc"; mkdir -p "$OUT/lib" "$OUT/bin"
-cp -aL "$PETSC_DIR/$PETSC_ARCH/lib/libpetsc.so.3.025" "$OUT/lib/"; ln -sf libpetsc.so.3.025 "$OUT/lib/libpetsc.so"
-INC="-I$PETSC_DIR/include -I$PETSC_DIR/$PETSC_ARCH/include"
+OUT="$HERE/_ref/petsc"; mkdir -p "$OUT/bin"
+[ -e "$OUT/lib/libpetsc.so" ] && [ -e "$OUT/include/petscconf.h" ] && [ -d "$REF/include" ] || { echo "no reference library in $OUT (run oracle/build_ref.sh in the build container): skipping the reference demo build"; exit 0; }
+# headers: the reference's own include tree where it lies + the generated headers build_ref.sh installed next to the library
+INC="-I$REF/include -I$OUT/include"
 LNK="-L$OUT/lib -lpetsc -Wl,-rpath,\$ORIGIN/../lib -Wl,-rpath,$BLASDIR -Wl,-rpath-link,$BLASDIR -Wl,--allow-shlib-undefined -lm"
 for ex in ex2 bench_kspsolve; do
   /usr/bin/gcc -O2 -o "$OUT/bin/$ex" "$REF/src/ksp/ksp/tutorials/$ex.c" $INC $LNK
 done
 /usr/bin/gcc -O2 -ffp-contract=off -fopenmp -o "$HERE/_ref/ref_driver" "$HERE/ref_driver.c" "$HERE/oracle.c" -I"$HERE" $INC -L$OUT/lib -lpetsc -Wl,-rpath,\$ORIGIN/petsc/lib -Wl,-rpath,$BLASDIR -Wl,-rpath-link,$BLASDIR -Wl,--allow-shlib-undefined -lm
-make -s -C "$ROOT/petsc_plugin" PETSC_DIR="$PETSC_DIR" PETSC_ARCH="$PETSC_ARCH"
+make -s -C "$ROOT/petsc_plugin" PETSC_INC="$INC" PETSC_LIBDIR="$OUT/lib"
 # a PETSc program for the plugin paths the tutorials do not reach (device COO, MatMultTranspose, MatBindToCPU)
 /usr/bin/gcc -O2 -o "$OUT/bin/plugin_driver" "$ROOT/petsc_plugin/plugin_driver.c" $INC -I"$ROOT/include" $LNK -L"$ROOT/petsc_b200/lib" -lpetscb200 -Wl,-rpath,\$ORIGIN/../../../../petsc_b200/lib
 echo "reference demo built in $OUT"

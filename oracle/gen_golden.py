@@ -1,10 +1,14 @@
 #!/usr/bin/env python
 """Generate tests/golden/*.npz by running the REFERENCE's own CPU code on seeded inputs.
 
-Needs a PETSc build of /root/reference (PETSC_DIR / PETSC_ARCH, default /tmp/petsc-probe + arch-probe: the survey's
-configure of an unmodified copy of the reference, --with-mpi=0 --with-cuda=0 --with-debugging=0 COPTFLAGS=-O2, OpenBLAS
-0.3.15 for BLAS).  It only runs in the build container; the fixtures it writes are committed and are what the tests
-read.  ref_driver.c (this directory) is the program that calls the reference's public API.
+Needs the reference library that oracle/build_ref.sh builds from /root/reference into oracle/_ref/petsc (--with-mpi=0
+--with-cuda=0 --with-debugging=0 COPTFLAGS=-O2, OpenBLAS 0.3.15 for BLAS) and oracle/_ref/ref_driver (built by the same
+script from ref_driver.c, the program that calls the reference's public API).  It only runs in the build container; the
+fixtures it writes are committed and are what the tests read.
+
+    python oracle/gen_golden.py            # (re)write tests/golden/*.npz
+    python oracle/gen_golden.py --check    # re-derive every fixture into a scratch directory and compare it, array by array
+                                           # and bit for bit, with the committed file; exit status 1 on any difference
 
 Every case records inputs (or the generator parameters) together with the reference's outputs:
   ref_mult / ref_multadd / ref_diag  -- MatMult_SeqAIJ, MatMultAdd_SeqAIJ, MatGetDiagonal_SeqAIJ (bit-exact pins)
@@ -26,26 +30,22 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 from oracle import oracle_py as O  # noqa: E402
 
-PETSC_DIR = os.environ.get("PETSC_DIR", "/tmp/petsc-probe")
-PETSC_ARCH = os.environ.get("PETSC_ARCH", "arch-probe")
+REFLIB = os.path.join(HERE, "_ref", "petsc", "lib")
 BLASDIR = "/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs"
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
 def build_driver():
+    subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])   # no-op when the library is already there
     exe = os.path.join(HERE, "_ref", "ref_driver")
-    os.makedirs(os.path.dirname(exe), exist_ok=True)
-    cmd = ["/usr/bin/gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-o", exe, os.path.join(HERE, "ref_driver.c"), os.path.join(HERE, "oracle.c"), "-I" + HERE,
-           "-I%s/include" % PETSC_DIR, "-I%s/%s/include" % (PETSC_DIR, PETSC_ARCH),
-           "-L%s/%s/lib" % (PETSC_DIR, PETSC_ARCH), "-Wl,-rpath,%s/%s/lib" % (PETSC_DIR, PETSC_ARCH), "-lpetsc", "-lm",
-           "-Wl,-rpath,%s" % BLASDIR, "-Wl,-rpath-link,%s" % BLASDIR, "-Wl,--allow-shlib-undefined"]
-    subprocess.check_call(cmd)
+    if not os.path.exists(exe):
+        sys.exit("oracle/_ref/ref_driver missing: oracle/build_ref.sh needs /root/reference (build container only)")
     return exe
 
 
 def run_case(exe, ai, aj, aa, x, y, V, alpha, opts):
     env = dict(os.environ)
-    env["LD_LIBRARY_PATH"] = "%s/%s/lib:%s:%s" % (PETSC_DIR, PETSC_ARCH, BLASDIR, env.get("LD_LIBRARY_PATH", ""))
+    env["LD_LIBRARY_PATH"] = "%s:%s:%s" % (REFLIB, BLASDIR, env.get("LD_LIBRARY_PATH", ""))
     with tempfile.TemporaryDirectory() as d:
         m, nv = len(ai) - 1, V.shape[0]
         for name, arr in (("ai.i32", ai), ("aj.i32", aj), ("aa.f64", aa), ("x.f64", x), ("y.f64", y), ("V.f64", V),
@@ -61,6 +61,31 @@ def run_case(exe, ai, aj, aa, x, y, V, alpha, opts):
             its, reason, rnorm, nh = open(os.path.join(d, "ref_ksp.txt")).read().split()
             out["ref_its"] = np.int64(its); out["ref_reason"] = np.int64(reason); out["ref_rnorm"] = np.float64(rnorm)
         return out
+
+
+def check():
+    """Regenerate into a scratch directory and diff against the committed fixtures (bit for bit)."""
+    global OUT
+    committed = OUT
+    bad = 0
+    with tempfile.TemporaryDirectory() as scratch:
+        OUT = scratch
+        main()
+        names = sorted(f for f in os.listdir(committed) if f.endswith(".npz"))
+        fresh = sorted(f for f in os.listdir(scratch) if f.endswith(".npz"))
+        if names != fresh:
+            print("fixture sets differ:", sorted(set(names) ^ set(fresh))); bad += 1
+        for f in sorted(set(names) & set(fresh)):
+            a, b = np.load(os.path.join(committed, f)), np.load(os.path.join(scratch, f))
+            if sorted(a.files) != sorted(b.files):
+                print(f, "array names differ", sorted(set(a.files) ^ set(b.files))); bad += 1; continue
+            for k in a.files:
+                x, y = a[k], b[k]
+                same = x.shape == y.shape and x.dtype == y.dtype and (x.tobytes() == y.tobytes())
+                if not same:
+                    print(f, k, "DIFFERS"); bad += 1
+    print("gen_golden --check: %d fixtures compared, %d differences" % (len(names), bad))
+    return 1 if bad else 0
 
 
 def main():
@@ -121,7 +146,7 @@ def main():
                 ci = np.sort(ci[ci >= 0]).astype(np.int32); cj = cj[:len(ci)]; n = len(ci)
         v1, v2 = crng.uniform(-1, 1, n), crng.uniform(-1, 1, n)
         env = dict(os.environ)
-        env["LD_LIBRARY_PATH"] = "%s/%s/lib:%s:%s" % (PETSC_DIR, PETSC_ARCH, BLASDIR, env.get("LD_LIBRARY_PATH", ""))
+        env["LD_LIBRARY_PATH"] = "%s:%s:%s" % (REFLIB, BLASDIR, env.get("LD_LIBRARY_PATH", ""))
         with tempfile.TemporaryDirectory() as d:
             for fn, arr in (("coo_i.i32", ci), ("coo_j.i32", cj), ("v1.f64", v1), ("v2.f64", v2)):
                 np.ascontiguousarray(arr).tofile(os.path.join(d, fn))
@@ -172,4 +197,6 @@ def main():
 
 
 if __name__ == "__main__":
+    if "--check" in sys.argv:
+        sys.exit(check())
     main()
