@@ -117,6 +117,12 @@ int b200CsrSpMVJacobi(b200Handle h, b200CsrPlan plan, const double *d_val, const
 /* compressed-row z = y + A x for a block whose rows are mostly empty (off-diagonal block B of MATMPIAIJ):
    only the nrows_c rows listed in d_rindex are read/written   (MatMultAdd_SeqAIJ compressed branch, aij.c:1626-1640) */
 int b200CsrSpMVAddCompressed(b200Handle h, int nrows_c, const int *d_cr_i, const int *d_rindex, const int *d_colidx, const double *d_val, const double *d_x, const double *d_y, double *d_z);
+/* MatMult_MPIAIJ + PCApply_Jacobi fused on the rows that own off-diagonal entries: after b200CsrSpMVJacobi wrote
+   w = dinv .* (A_d x) on the diagonal block, this overwrites w[r] = dinv[r] * (A_d(r,:) x  +  B(r,:) lvec) for the nrows_c
+   rows of d_rindex, the row sum taken left to right through A_d's entries and then B's (mpiaij.c:1057-1060: the off-diagonal
+   multadd continues the diagonal block's y[r]; jacobi.c:354) -- the unfused result bit for bit, without a y vector */
+int b200CsrSpMVAddCompressedJacobi(b200Handle h, int nrows_c, const int *d_cr_i, const int *d_rindex, const int *d_bj, const double *d_ba, const double *d_lvec,
+                                   const int *d_ai, const int *d_aj, const double *d_aa, const double *d_x, const double *d_dinv, double *d_w);
 /* MatAssemblyEnd_SeqAIJ invariants checked on the device: *bad_row = -1 if valid, else an offending row and
    kind 1 = column out of range, 2 = columns not strictly increasing, 3 = decreasing row pointer */
 int b200CsrValidate(b200Handle h, int m, int n, const int *d_rowptr, const int *d_colidx, int *bad_row, int *kind);

@@ -984,6 +984,36 @@ static PetscErrorCode MatMult_MPIAIJB200(Mat mat, Vec x, Vec y)
   PetscCall((*a->B->ops.multadd)(a->B, a->lvec, y, y));
   return PETSC_SUCCESS;
 }
+/* PCApplyBAorAB with PCJACOBI on the row-partitioned matrix, fused: w = dinv .* (A_d x + B_o lvec) without the intermediate y
+   (mpiaij.c:1047-1061 + jacobi.c:354).  The diagonal block runs its fused kernel while the halo travels; the (few) rows that
+   own off-diagonal entries are then redone with both blocks in the reference's order. */
+static PetscErrorCode MatMultJacobi_MPIAIJB200(Mat mat, Vec x, Vec dinv, Vec w)
+{
+  Mat_MPIAIJB200 *a = (Mat_MPIAIJB200 *)mat->data;
+  Mat_SeqAIJB200 *A = (Mat_SeqAIJB200 *)a->A->data, *B = (Mat_SeqAIJB200 *)a->B->data;
+  const double   *dx, *dd, *dlr;
+  double         *dl, *dw;
+  if (!a->A->ops.multjacobi || (B->nz && !B->cr_use)) { /* off-diagonal block not in compressed-row form: unfused */
+    Vec work;
+    PetscCall(VecDuplicate(w, &work));
+    PetscCall(MatMult(mat, x, work));
+    PetscCall(VecPointwiseMult(w, work, dinv));
+    PetscCall(VecDestroy(&work));
+    return PETSC_SUCCESS;
+  }
+  PetscCall(VecB200GetArrayRead(x, &dx));
+  PetscCall(VecB200GetArrayWrite(a->lvec, &dl));
+  PetscCallB200(b200HaloBegin(H, a->Mvctx, dx, dl));
+  PetscCall((*a->A->ops.multjacobi)(a->A, x, dinv, w));
+  PetscCallB200(b200HaloEnd(H, a->Mvctx));
+  if (B->nz) {
+    PetscCall(VecB200GetArrayRead(a->lvec, &dlr));
+    PetscCall(VecB200GetArrayRead(dinv, &dd));
+    PetscCall(VecB200GetArray(w, &dw));
+    PetscCallB200(b200CsrSpMVAddCompressedJacobi(H, B->cr_nrows, B->d_cr_i, B->d_cr_rindex, B->d_j, B->d_a, dlr, A->d_i, A->d_j, A->d_a, dx, dd, dw));
+  }
+  return PETSC_SUCCESS;
+}
 static PetscErrorCode MatMultAdd_MPIAIJB200(Mat mat, Vec x, Vec y, Vec z)
 {
   Mat_MPIAIJB200 *a = (Mat_MPIAIJB200 *)mat->data; /* mpiaij.c:1072-1084 */
@@ -1029,6 +1059,7 @@ PetscErrorCode MatCreate_MPIAIJB200(Mat A)
   A->data                 = a;
   A->ops.mult             = MatMult_MPIAIJB200;
   A->ops.multadd          = MatMultAdd_MPIAIJB200;
+  A->ops.multjacobi       = MatMultJacobi_MPIAIJB200;
   A->ops.getdiagonal      = MatGetDiagonal_MPIAIJB200;
   A->ops.getdiagonalblock = MatGetDiagonalBlock_MPIAIJB200;
   A->ops.destroy          = MatDestroy_MPIAIJB200;

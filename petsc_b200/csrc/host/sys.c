@@ -276,13 +276,19 @@ PetscErrorCode PetscB200AllreduceHost(MPI_Comm comm, double *vals, int n, int op
 {
   if (PetscB200CommSize(comm) == 1 || n == 0) return PETSC_SUCCESS;
   PetscCall(PetscB200EnsureInit());
-  double *d;
-  PetscCallB200(b200Malloc(PetscB200.h, (void **)&d, sizeof(double) * (size_t)n));
+  /* persistent device scratch (grown on demand, never freed per call): a cudaMalloc/cudaFree pair synchronises the whole
+     device and would defeat the halo-stream overlap on the CG path (2 dots + 1 norm per iteration) */
+  static double *d     = NULL;
+  static size_t  d_cap = 0;
+  if ((size_t)n > d_cap) {
+    if (d) PetscCallB200(b200Free(PetscB200.h, d));
+    d_cap = (size_t)n < 1024 ? 1024 : (size_t)n;
+    PetscCallB200(b200Malloc(PetscB200.h, (void **)&d, sizeof(double) * d_cap));
+  }
   PetscCallB200(b200MemcpyHtoDAsync(PetscB200.h, d, vals, sizeof(double) * (size_t)n));
   if (op == 0) PetscCallB200(b200CommAllreduceSum(PetscB200.h, d, n));
   else PetscCallB200(b200CommAllreduceMax(PetscB200.h, d, n));
   PetscCallB200(b200MemcpyDtoH(PetscB200.h, vals, d, sizeof(double) * (size_t)n));
-  PetscCallB200(b200Free(PetscB200.h, d));
   return PETSC_SUCCESS;
 }
 

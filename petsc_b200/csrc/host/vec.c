@@ -885,13 +885,14 @@ PetscErrorCode VecCreate_SeqB200(Vec v)
 }
 
 /* ------------------------------------------------------------------ mpib200: local kernels + NCCL all-reduce (pvecimpl.h:97-172) */
+static double *d_red = NULL; /* device scratch for the fused local-reduce + all-reduce */
+static PetscErrorCode VecMDot_MPIB200(Vec x, PetscInt nv, const Vec y[], PetscScalar *val);
 static PetscErrorCode VecDot_MPIB200(Vec x, Vec y, PetscScalar *val)
 {
-  PetscCall(VecDot_Local(x, y, val));
-  PetscCall(PetscB200AllreduceHost(x->hdr.comm, val, 1, 0));
-  return PETSC_SUCCESS;
+  /* VecXDot_MPI_Default (pvecimpl.h:97-121): the local dot is the nv = 1 MDot kernel, its device result is all-reduced in
+     place on persistent scratch, one device-to-host copy */
+  return VecMDot_MPIB200(x, 1, &y, val);
 }
-static double *d_red = NULL; /* device scratch for the fused local-reduce + all-reduce */
 static PetscErrorCode VecMDot_MPIB200(Vec x, PetscInt nv, const Vec y[], PetscScalar *val)
 {
   /* VecMXDot_MPI_Default: local mdot then MPIU_Allreduce(nv). Here the local results never leave the device before the
@@ -899,11 +900,9 @@ static PetscErrorCode VecMDot_MPIB200(Vec x, PetscInt nv, const Vec y[], PetscSc
   RD(x, dx);
   if (!d_red) PetscCallB200(b200Malloc(H, (void **)&d_red, sizeof(double) * 4096));
   PetscCheck(nv <= 4096, x->hdr.comm, PETSC_ERR_SUP, "nv too large");
-  const double **yp = (const double **)malloc(sizeof(double *) * (size_t)nv);
+  const double *yp[4096];
   for (PetscInt j = 0; j < nv; j++) PetscCall(VecB200GetArrayRead(y[j], &yp[j]));
-  PetscErrorCode rc = b200VecMDotAsync(H, x->n, nv, dx, yp, d_red);
-  free(yp);
-  PetscCallB200(rc);
+  PetscCallB200(b200VecMDotAsync(H, x->n, nv, dx, yp, d_red));
   PetscCallB200(b200CommAllreduceSum(H, d_red, nv));
   PetscCallB200(b200MemcpyDtoH(H, val, d_red, sizeof(double) * (size_t)nv));
   return PETSC_SUCCESS;

@@ -899,6 +899,38 @@ extern "C" int b200CsrSpMVAddCompressed(b200Handle h, int nrows_c, const int *d_
   return 0;
 }
 
+/* MatMult_MPIAIJ + PCApply_Jacobi fused for the rows that own off-diagonal entries (mpiaij.c:1057-1060 + jacobi.c:354):
+   the diagonal-block kernel has already written w = dinv .* (A_d x) for every row; for the nrows_c halo rows this kernel
+   recomputes the diagonal-block row sum (left to right from 0.0, exactly as the diagonal-block product does), continues it
+   with the off-diagonal entries (the sum MatMultAdd_SeqAIJ starts at y[r], aij.c:1639-1652) and overwrites
+   w[r] = dinv[r] * sum -- the reference's association without ever materialising y. */
+__global__ void csr_multadd_compressed_jacobi_kernel(int nrows, const int *__restrict__ cr_i, const int *__restrict__ ridx, const int *__restrict__ bj, const double *__restrict__ ba, const double *__restrict__ lvec,
+                                                     const int *__restrict__ ai, const int *__restrict__ aj, const double *__restrict__ aa, const double *__restrict__ x, const double *__restrict__ dinv, double *w)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += stride) {
+    const int r   = ridx[i];
+    double    sum = 0.0;
+    for (int k = ai[r]; k < ai[r + 1]; k++) sum = __dadd_rn(sum, __dmul_rn(aa[k], __ldg(x + aj[k])));
+    for (int k = cr_i[i]; k < cr_i[i + 1]; k++) sum = __dadd_rn(sum, __dmul_rn(ba[k], __ldg(lvec + bj[k])));
+    w[r] = __dmul_rn(sum, dinv[r]);
+  }
+}
+
+extern "C" int b200CsrSpMVAddCompressedJacobi(b200Handle h, int nrows_c, const int *d_cr_i, const int *d_rindex, const int *d_bj, const double *d_ba, const double *d_lvec,
+                                              const int *d_ai, const int *d_aj, const double *d_aa, const double *d_x, const double *d_dinv, double *d_w)
+{
+  B200_CHECK(h, B200_ERR_ARG_NULL, "null handle");
+  if (nrows_c <= 0) return 0;
+  B200_CHECK(d_cr_i && d_rindex && d_bj && d_ba && d_lvec && d_ai && d_aj && d_aa && d_x && d_dinv && d_w, B200_ERR_ARG_NULL, "null pointer");
+  int g = (nrows_c + 127) / 128;
+  if (g > h->num_sms * 16) g = h->num_sms * 16;
+  csr_multadd_compressed_jacobi_kernel<<<g, 128, 0, h->stream>>>(nrows_c, d_cr_i, d_rindex, d_bj, d_ba, d_lvec, d_ai, d_aj, d_aa, d_x, d_dinv, d_w);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  return 0;
+}
+
 /* compressed-row analysis (MatCheckCompressedRow, src/mat/utils/compressedrow.c): list of non-empty rows */
 __global__ void count_nonempty_kernel(int m, const int *__restrict__ rowptr, int *count)
 {

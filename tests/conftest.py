@@ -21,3 +21,13 @@ def oracle():
 
 def golden_path(name):
     return os.path.join(ROOT, "tests", "golden", name)
+
+
+def assert_history_1e12(hist, ref, k, label=""):
+    """north_star tolerance for fp64 residuals: every entry of the first k (<= one restart cycle) within 1e-12 of the
+    reference RELATIVE TO THE INITIAL RESIDUAL.  Prints the measured margin (pytest -s / -rA shows it)."""
+    import numpy as np
+    h, r = np.asarray(hist[:k], dtype=float), np.asarray(ref[:k], dtype=float)
+    dev = float(np.max(np.abs(h - r))) / float(r[0]) if k else 0.0
+    print("history %s: max|h-ref|/r0 = %.2e over %d entries (bound 1e-12, margin %.0fx)" % (label, dev, k, 1e-12 / dev if dev else float("inf")))
+    assert dev <= 1e-12, (label, dev)
