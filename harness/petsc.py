@@ -1,4 +1,4 @@
-"""ctypes door to libpetscb200host.so, the C host mirror of PETSc's Mat/Vec/KSP/PC interface (include/petscb200_host.h).
+"""TEST HARNESS: ctypes door to harness/libb200harness.so, the C mini-PETSc of harness/host (harness/petscb200_host.h).
 
 Thin by design: every method is one call into the C library (which calls the sm_100a kernels).  Names follow petsc4py
 loosely so tests read like the reference's examples.  No CPU fallback: without the CUDA libraries this module raises.
@@ -8,7 +8,9 @@ import os
 
 import numpy as np
 
-from . import _capi
+from petsc_b200 import _capi
+
+_HARNESS_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200harness.so")
 
 _host = None
 vp, dbl, i32 = C.c_void_p, C.c_double, C.c_int
@@ -27,9 +29,9 @@ def lib():
     global _host
     if _host is None:
         _capi.lib()  # kernel library first (RTLD_GLOBAL)
-        if not os.path.exists(_capi.HOST_LIB_PATH):
-            raise ImportError("libpetscb200host.so is not built; run __graft_entry__.build()")
-        _host = C.CDLL(_capi.HOST_LIB_PATH, mode=C.RTLD_GLOBAL)
+        if not os.path.exists(_HARNESS_LIB):
+            raise ImportError("harness/libb200harness.so is not built; run __graft_entry__.build()")
+        _host = C.CDLL(_HARNESS_LIB, mode=C.RTLD_GLOBAL)
         _host.PetscB200GetLastErrorMessage.restype = C.c_char_p
     return _host
 
@@ -41,7 +43,7 @@ def chk(rc):
 
 def host_symbols():
     import re
-    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "petscb200_host.h")).read()
+    hdr = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "petscb200_host.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     return sorted(set(re.findall(r"\b(?:PetscErrorCode|const char\s*\*)\s*(\w+)\s*\(", hdr)))
 

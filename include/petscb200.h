@@ -58,6 +58,9 @@ const char *b200GetLastErrorString(void);
 const char *b200Version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
 long long   b200KernelLaunchCount(void);
+/* bytes moved host->device / device->host through b200Memcpy* since load (the PetscLogCpuToGpu / PetscLogGpuToCpu counters
+   of aijcusparse.cu:1563, veccupmimpl.h:430; results of reductions that arrive through mapped pinned memory are not copies) */
+int         b200TransferCounters(long long *h2d_bytes, long long *d2h_bytes);
 /* PetscGetMemType analogue: 1 if ptr is device (or managed) memory, 0 for host memory */
 int         b200PointerIsDevice(const void *ptr, int *is_device);
 
@@ -216,6 +219,23 @@ int b200HaloDestroy(b200Halo halo);
 int b200HaloBegin(b200Handle h, b200Halo halo, const double *d_x, double *d_lvec);
 /* make the main stream wait for the exchange */
 int b200HaloEnd(b200Handle h, b200Halo halo);
+
+/* reverse scatter = PetscSFReduceBegin/End(MPI_SUM) of VecScatter(ADD_VALUES, SCATTER_REVERSE) in MatMultTranspose_MPIAIJ
+   (mpiaij.c:1086-1097): every rank returns its lvec segments to their owners (halo stream), which add them into
+   y[send_idx] on the main stream, peer after peer in plan order (deterministic) */
+int b200HaloReduceBegin(b200Handle h, b200Halo halo, const double *d_lvec);
+int b200HaloReduceEnd(b200Handle h, b200Halo halo, double *d_y);
+/* MatSetUpMultiply_MPIAIJ host side, shared by the PETSc plugin and the test harness (index work, bit-exact):
+   b200MpiaijSplitHost: column split of a row block with GLOBAL columns into the diagonal block (local columns) and the
+     off-diagonal block (global columns); call with Aj == NULL first for the counts        (mpiaij.c MatSetValues_MPIAIJ routing)
+   b200MpiaijBuildGarray: garray = sorted distinct off-process columns, h_bj renumbered in place (mmaij.c:25-61);
+     *h_garray is malloc'ed: release with b200HostFree
+   b200HaloCreateFromGarray: ownership ranges (all-gather of m_local; ranges[nranks+1] is caller storage), owners of the
+     garray entries, the request exchange and the halo plan (mmaij.c:103-117 + PetscSFSetUp); collective */
+int b200MpiaijSplitHost(int m, int cstart, int cend, const int *ai, const int *aj, const double *aa, int64_t *nzA, int64_t *nzB, int *Ai, int *Aj, double *Aa, int *Bi, int *Bj, double *Ba);
+int b200MpiaijBuildGarray(int64_t nzB, int *h_bj, int **h_garray, int *ec);
+int b200HaloCreateFromGarray(b200Handle h, int m_local, int ec, const int *h_garray, int64_t *ranges, b200Halo *halo);
+int b200HostFree(void *p);
 
 /* ---- COO assembly ----------------------------------------------------------------------------------
  * replaces MatSetPreallocationCOO_SeqAIJ / MatSetValuesCOO_SeqAIJ (src/mat/impls/aij/seq/aij.c:4524-4732) and the value

@@ -10,7 +10,6 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpetscb200.so")
-HOST_LIB_PATH = os.path.join(_HERE, "lib", "libpetscb200host.so")
 
 _lib = None
 

@@ -1,4 +1,4 @@
-"""Builds libpetscb200.so (CUDA kernels + C ABI) and libpetscb200host.so (C host mirror) in-tree.
+"""Builds libpetscb200.so (CUDA kernels + C ABI) in-tree.
 
 nvcc cross-compiles for sm_100a without a GPU.  Called by __graft_entry__.build(); also runnable as
 ``python -m petsc_b200.build``.
@@ -52,16 +52,6 @@ def build(verbose=False, force=False, ptxas_info=False):
     so = os.path.join(LIBDIR, "libpetscb200.so")
     if force or _newer(so, objs):
         cmd = [NVCC, "-shared", "-o", so] + objs + ["-ccbin", GXX, "-Xcompiler", "-fPIC", "-ldl", "-lpthread"]
-        if verbose:
-            print(" ".join(cmd))
-        subprocess.check_call(cmd)
-    # host mirror (plain C, links the kernel library)
-    hsrc = sorted(glob.glob(os.path.join(CSRC, "host", "*.c")))
-    hso = os.path.join(LIBDIR, "libpetscb200host.so")
-    if hsrc and (force or _newer(hso, hsrc + headers + [so] + glob.glob(os.path.join(CSRC, "host", "*.h")))):
-        cmd = [GCC, "-O2", "-g", "-fPIC", "-std=c11", "-Wall", "-Wextra", "-Wno-unused-parameter", "-shared", "-o", hso] + hsrc + [
-            "-I", os.path.join(ROOT, "include"), "-I", os.path.join(CSRC, "host"), "-L", LIBDIR, "-lpetscb200",
-            "-Wl,-rpath,$ORIGIN", "-lm"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -240,3 +240,216 @@ extern "C" int b200CommAlltoallvInt(b200Handle h, const int *sendcounts, const i
   B200_NCCL(N.GroupEnd());
   return 0;
 }
+
+/* ------------------------------------------------------------------ reverse scatter: PetscSFReduceBegin/End with MPI_SUM
+   (VecScatterBegin/End(..., ADD_VALUES, SCATTER_REVERSE) in MatMultTranspose_MPIAIJ, mpiaij.c:1086-1097): every rank returns
+   its lvec segments to their owners, which add them into y[send_idx].  Same plan, roles swapped: what Bcast received
+   contiguously is now sent contiguously (no pack kernel); what Bcast packed is now unpacked with an add.  The adds of one
+   peer touch distinct entries (garray is duplicate-free); peers are applied one after the other in plan order, so the
+   result does not depend on timing. */
+__global__ void halo_unpack_add_kernel(int n, const int *__restrict__ idx, const double *__restrict__ buf, double *y)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[idx[i]] = __dadd_rn(y[idx[i]], buf[i]);
+}
+
+extern "C" int b200HaloReduceBegin(b200Handle h, b200Halo p, const double *d_lvec)
+{
+  B200_CHECK(h && p, B200_ERR_ARG_NULL, "null argument");
+  if (!p->npeers) return 0;
+  B200_CHECK(h->nccl_comm, B200_ERR_ORDER, "communicator not initialised");
+  B200_CUDA(cudaEventRecord(h->ev_main, h->stream));
+  B200_CUDA(cudaStreamWaitEvent(h->halo_stream, h->ev_main, 0));
+  B200_NCCL(N.GroupStart());
+  for (int i = 0; i < p->npeers; i++) {
+    if (p->recv_counts[i]) B200_NCCL(N.Send(d_lvec + p->recv_offsets[i], (size_t)p->recv_counts[i], NCCL_FLOAT64, p->peers[i], (nccl_comm_t)h->nccl_comm, h->halo_stream));
+    if (p->send_counts[i]) B200_NCCL(N.Recv(p->d_send_buf + p->send_offsets[i], (size_t)p->send_counts[i], NCCL_FLOAT64, p->peers[i], (nccl_comm_t)h->nccl_comm, h->halo_stream));
+  }
+  B200_NCCL(N.GroupEnd());
+  B200_CUDA(cudaEventRecord(h->ev_halo, h->halo_stream));
+  return 0;
+}
+
+extern "C" int b200HaloReduceEnd(b200Handle h, b200Halo p, double *d_y)
+{
+  B200_CHECK(h && p, B200_ERR_ARG_NULL, "null argument");
+  if (!p->npeers) return 0;
+  B200_CUDA(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
+  for (int i = 0; i < p->npeers; i++) {
+    const int n = p->send_counts[i];
+    if (!n) continue;
+    int g = (n + 255) / 256;
+    if (g > h->num_sms * 4) g = h->num_sms * 4;
+    halo_unpack_add_kernel<<<g, 256, 0, h->stream>>>(n, p->d_send_idx + p->send_offsets[i], p->d_send_buf + p->send_offsets[i], d_y);
+    B200_LAUNCHED(1);
+    B200_KERNEL_CHECK();
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------ MatSetUpMultiply_MPIAIJ, host side (mmaij.c:8-126)
+   Shared by the PETSc plugin (mpiaijb200) and the test harness, so the index work that must be bit-exact lives once. */
+static int cmp_int_(const void *a, const void *b)
+{
+  int x = *(const int *)a, y = *(const int *)b;
+  return (x > y) - (x < y);
+}
+
+/* garray = sorted distinct off-process columns (mmaij.c:25-51); h_bj is renumbered in place into positions in garray
+   (mmaij.c:55-61).  *h_garray is malloc'ed (free with b200HostFree). */
+extern "C" int b200MpiaijBuildGarray(int64_t nzB, int *h_bj, int **h_garray, int *ec)
+{
+  B200_CHECK(h_garray && ec && (h_bj || !nzB), B200_ERR_ARG_NULL, "null argument");
+  int *g = (int *)malloc(sizeof(int) * ((size_t)nzB + 1));
+  B200_CHECK(g, B200_ERR_MEM, "out of host memory");
+  int n = 0;
+  if (nzB) {
+    memcpy(g, h_bj, sizeof(int) * (size_t)nzB);
+    qsort(g, (size_t)nzB, sizeof(int), cmp_int_);
+    n = 1;
+    for (int64_t k = 1; k < nzB; k++)
+      if (g[k] != g[n - 1]) g[n++] = g[k];
+    for (int64_t k = 0; k < nzB; k++) {
+      int c = h_bj[k], lo = 0, hi = n - 1;
+      while (lo < hi) {
+        int mid = (lo + hi) / 2;
+        if (g[mid] < c) lo = mid + 1;
+        else hi = mid;
+      }
+      h_bj[k] = lo;
+    }
+  }
+  *h_garray = g;
+  *ec       = n;
+  return 0;
+}
+
+/* host column split of a row block (local rows, GLOBAL columns) into the diagonal block (columns [cstart,cend) renumbered
+   to local) and the off-diagonal block (global columns kept): two passes, call with Aj == NULL to get the counts first */
+extern "C" int b200MpiaijSplitHost(int m, int cstart, int cend, const int *ai, const int *aj, const double *aa, int64_t *nzA, int64_t *nzB, int *Ai, int *Aj, double *Aa, int *Bi, int *Bj, double *Ba)
+{
+  B200_CHECK(ai && (aj || !ai[m]) && nzA && nzB, B200_ERR_ARG_NULL, "null argument");
+  int64_t ka = 0, kb = 0;
+  if (!Aj) {
+    for (int r = 0; r < m; r++)
+      for (int k = ai[r]; k < ai[r + 1]; k++) {
+        if (aj[k] >= cstart && aj[k] < cend) ka++;
+        else kb++;
+      }
+    *nzA = ka;
+    *nzB = kb;
+    return 0;
+  }
+  Ai[0] = Bi[0] = 0;
+  for (int r = 0; r < m; r++) {
+    for (int k = ai[r]; k < ai[r + 1]; k++) {
+      const int c = aj[k];
+      if (c >= cstart && c < cend) {
+        Aj[ka]   = c - cstart;
+        Aa[ka++] = aa[k];
+      } else {
+        Bj[kb]   = c;
+        Ba[kb++] = aa[k];
+      }
+    }
+    Ai[r + 1] = (int)ka;
+    Bi[r + 1] = (int)kb;
+  }
+  *nzA = ka;
+  *nzB = kb;
+  return 0;
+}
+
+extern "C" int b200HostFree(void *p)
+{
+  free(p);
+  return 0;
+}
+
+/* host values through the device: setup-time collectives on <= a few thousand doubles */
+static int allreduce_host(b200Handle h, double *v, int n, int op)
+{
+  if (h->nranks == 1 || n == 0) return 0;
+  double *d = NULL;
+  B200_CUDA(cudaMalloc(&d, sizeof(double) * (size_t)n));
+  B200_CUDA(cudaMemcpyAsync(d, v, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  int rc = allreduce(h, d, n, op);
+  if (!rc) {
+    B200_CUDA(cudaMemcpyAsync(v, d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  cudaFree(d);
+  return rc;
+}
+
+/* The Mvctx scatter of MatSetUpMultiply_MPIAIJ (mmaij.c:103-117) from garray alone: all-gathers the local sizes into the
+   ownership ranges (ranges[nranks+1], caller storage), finds the owner of every garray entry (one contiguous lvec range
+   per owner), tells each owner which of its entries are wanted (the request exchange PetscSFSetUp does over MPI) and
+   creates the halo plan.  Collective over the handle's communicator. */
+extern "C" int b200HaloCreateFromGarray(b200Handle h, int m_local, int ec, const int *h_garray, int64_t *ranges, b200Halo *halo)
+{
+  B200_CHECK(h && halo && ranges && (h_garray || !ec), B200_ERR_ARG_NULL, "null argument");
+  const int size = h->nranks, rank = h->rank;
+  double   *v    = (double *)calloc((size_t)size * (size + 1), sizeof(double));
+  B200_CHECK(v, B200_ERR_MEM, "out of host memory");
+  v[rank] = (double)m_local; /* exact below 2^53 */
+  int rc  = allreduce_host(h, v, size, NCCL_SUM);
+  if (rc) { free(v); return rc; }
+  ranges[0] = 0;
+  for (int p = 0; p < size; p++) ranges[p + 1] = ranges[p] + (int64_t)v[p];
+  int *rcnt = (int *)calloc((size_t)size, sizeof(int)), *roff = (int *)calloc((size_t)size, sizeof(int)), *scnt = (int *)calloc((size_t)size, sizeof(int));
+  int  k = 0;
+  for (int p = 0; p < size; p++) {
+    roff[p] = k;
+    while (k < ec && h_garray[k] < ranges[p + 1]) k++;
+    rcnt[p] = k - roff[p];
+  }
+  if (k != ec || rcnt[rank]) {
+    free(v); free(rcnt); free(roff); free(scnt);
+    B200_CHECK(0, B200_ERR_ARG_OUTOFRANGE, "garray holds columns that are locally owned or outside the global range");
+  }
+  /* count matrix: row = requester, column = owner */
+  double *mat = v;
+  memset(mat, 0, sizeof(double) * (size_t)size * size);
+  for (int p = 0; p < size; p++) mat[(size_t)rank * size + p] = rcnt[p];
+  rc = allreduce_host(h, mat, size * size, NCCL_SUM);
+  if (rc) { free(v); free(rcnt); free(roff); free(scnt); return rc; }
+  size_t ns = 0;
+  for (int p = 0; p < size; p++) {
+    scnt[p] = (int)mat[(size_t)p * size + rank];
+    ns += (size_t)scnt[p];
+  }
+  free(v);
+  int *req = (int *)malloc(sizeof(int) * ((size_t)ec + 1)), *need = (int *)malloc(sizeof(int) * (ns + 1));
+  for (int p = 0, q = 0; q < ec; q++) {
+    while (h_garray[q] >= ranges[p + 1]) p++;
+    req[q] = (int)(h_garray[q] - ranges[p]); /* local index on the owner */
+  }
+  if (size > 1) {
+    int *d_s = NULL, *d_r = NULL;
+    B200_CUDA(cudaMalloc(&d_s, sizeof(int) * ((size_t)ec + 1)));
+    B200_CUDA(cudaMalloc(&d_r, sizeof(int) * (ns + 1)));
+    if (ec) B200_CUDA(cudaMemcpyAsync(d_s, req, sizeof(int) * (size_t)ec, cudaMemcpyHostToDevice, h->stream));
+    rc = b200CommAlltoallvInt(h, rcnt, d_s, scnt, d_r);
+    if (!rc && ns) B200_CUDA(cudaMemcpyAsync(need, d_r, sizeof(int) * ns, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(d_s); cudaFree(d_r);
+  }
+  int np = 0, *peers = (int *)malloc(sizeof(int) * (size_t)(size + 1)), *psc = (int *)malloc(sizeof(int) * (size_t)(size + 1)), *prc = (int *)malloc(sizeof(int) * (size_t)(size + 1)), *pro = (int *)malloc(sizeof(int) * (size_t)(size + 1));
+  int *sidx = (int *)malloc(sizeof(int) * (ns + 1)), nsi = 0, off = 0, bad = 0;
+  for (int p = 0; p < size && !rc; p++) {
+    if (p != rank && (scnt[p] || rcnt[p])) {
+      peers[np] = p; psc[np] = scnt[p]; prc[np] = rcnt[p]; pro[np] = roff[p];
+      for (int q = 0; q < scnt[p]; q++) {
+        if (need[off + q] < 0 || need[off + q] >= m_local) bad = 1;
+        sidx[nsi++] = need[off + q];
+      }
+      np++;
+    }
+    off += scnt[p];
+  }
+  if (!rc && bad) { b200_set_error(B200_ERR_ARG_OUTOFRANGE, "a peer requested an entry outside my row range"); rc = B200_ERR_ARG_OUTOFRANGE; }
+  if (!rc) rc = b200HaloCreate(h, np, peers, psc, sidx, prc, pro, halo);
+  free(rcnt); free(roff); free(scnt); free(req); free(need); free(peers); free(psc); free(prc); free(pro); free(sidx);
+  return rc;
+}

@@ -20,6 +20,15 @@ void b200_set_error(int code, const char *fmt, ...)
 extern "C" const char *b200GetLastErrorString(void) { return g_err; }
 extern "C" const char *b200Version(void) { return "petscb200 0.1 (sm_100a)"; }
 extern "C" long long   b200KernelLaunchCount(void) { return g_b200_launches; }
+/* bytes moved by b200Memcpy{HtoD,DtoH}[Async] since load: what a PETSc plugin reports through PetscLogCpuToGpu/GpuToCpu and
+   what the tests use to prove that a KSPSolve moves no vector over PCIe per iteration */
+static long long g_b200_h2d = 0, g_b200_d2h = 0;
+extern "C" int b200TransferCounters(long long *h2d_bytes, long long *d2h_bytes)
+{
+  if (h2d_bytes) *h2d_bytes = g_b200_h2d;
+  if (d2h_bytes) *d2h_bytes = g_b200_d2h;
+  return 0;
+}
 
 extern "C" int b200DeviceCount(int *n)
 {
@@ -131,6 +140,7 @@ extern "C" int b200FreeHost(void *p)
 extern "C" int b200MemcpyHtoD(b200Handle h, void *d, const void *s, size_t bytes)
 {
   if (!bytes) return 0;
+  g_b200_h2d += (long long)bytes;
   B200_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
@@ -138,6 +148,7 @@ extern "C" int b200MemcpyHtoD(b200Handle h, void *d, const void *s, size_t bytes
 extern "C" int b200MemcpyDtoH(b200Handle h, void *d, const void *s, size_t bytes)
 {
   if (!bytes) return 0;
+  g_b200_d2h += (long long)bytes;
   B200_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
@@ -145,12 +156,14 @@ extern "C" int b200MemcpyDtoH(b200Handle h, void *d, const void *s, size_t bytes
 extern "C" int b200MemcpyHtoDAsync(b200Handle h, void *d, const void *s, size_t bytes)
 {
   if (!bytes) return 0;
+  g_b200_h2d += (long long)bytes;
   B200_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream));
   return 0;
 }
 extern "C" int b200MemcpyDtoHAsync(b200Handle h, void *d, const void *s, size_t bytes)
 {
   if (!bytes) return 0;
+  g_b200_d2h += (long long)bytes;
   B200_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, h->stream));
   return 0;
 }

@@ -11,7 +11,8 @@ import torch.distributed as td
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import oracle_py as O  # noqa: E402
-from petsc_b200 import _capi, petsc  # noqa: E402
+from petsc_b200 import _capi
+from harness import petsc  # noqa: E402
 
 
 def sig6(v):

@@ -6,7 +6,8 @@ import os
 import numpy as np
 import pytest
 
-from petsc_b200 import _capi, petsc
+from petsc_b200 import _capi
+from harness import petsc
 
 
 def test_kernel_library_exports_every_declared_symbol():
@@ -48,11 +49,12 @@ def test_no_cpu_fallback_without_gpu():
 def test_package_does_not_import_oracle():
     import subprocess
     import sys
-    out = subprocess.check_output([sys.executable, "-c", "import sys; import petsc_b200, petsc_b200.petsc; print([m for m in sys.modules if 'oracle' in m])"],
+    out = subprocess.check_output([sys.executable, "-c", "import sys; import petsc_b200, petsc_b200._capi, harness.petsc; print([m for m in sys.modules if 'oracle' in m])"],
                                   cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert out.strip() == b"[]"
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for dirpath, _, files in os.walk(os.path.join(root, "petsc_b200")):
+    assert "oracle" not in open(os.path.join(root, "petsc_plugin", "petscb200_plugin.c")).read().lower()   # the PETSc binding of the product
+    for dirpath, _, files in list(os.walk(os.path.join(root, "petsc_b200"))) + list(os.walk(os.path.join(root, "include"))):
         for f in files:
             if f.endswith((".py", ".c", ".cu", ".h")):
                 assert "oracle" not in open(os.path.join(dirpath, f), errors="replace").read().lower(), f

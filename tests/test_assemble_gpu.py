@@ -25,7 +25,7 @@ def H():
 
 @pytest.fixture(scope="module")
 def P():
-    from petsc_b200 import petsc
+    from harness import petsc
     petsc.initialize()
     return petsc
 

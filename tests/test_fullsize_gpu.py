@@ -18,7 +18,7 @@ RTOL = 1e-12
 
 @pytest.fixture(scope="module")
 def P():
-    from petsc_b200 import petsc
+    from harness import petsc
     petsc.initialize()  # idempotent; the device was chosen by whichever module initialised first (cuda:0 by default)
     return petsc
 

@@ -17,7 +17,7 @@ RTOL = 1e-12
 
 @pytest.fixture(scope="module")
 def P():
-    from petsc_b200 import petsc
+    from harness import petsc
     petsc.initialize()
     yield petsc
     petsc.options_clear()

@@ -7,7 +7,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from petsc_b200 import petsc
+from harness import petsc
 
 vp = C.c_void_p
 

@@ -19,7 +19,8 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from petsc_b200 import _capi, petsc  # noqa: E402
+from petsc_b200 import _capi
+from harness import petsc  # noqa: E402
 
 
 def main():
