@@ -2,10 +2,14 @@
 """bench.py -- the measurement contract.
 
 Workload (BASELINE.json configs[1]): 3-D 7-point Laplacian 512^3 (n = 134 217 728, nnz = 937 951 232), MATSEQAIJ layout,
-KSPGMRES(30) + PCJACOBI, fp64, through the C host mirror (-mat_type aijb200 -vec_type b200).  A "step" is one GMRES(30)
-restart cycle = 30 Krylov iterations (initial residual, 30 x [SpMV+Jacobi, MDot, MAXPY, norm, scale], solution update).
-N > 1 is weak scaling: every rank owns a 512 x 512 x 512 slab of a 512 x 512 x (512 N) grid (row-partitioned MPIAIJ, NCCL
-halo + all-reduces); `value` counts iterations in units of one 512^3 problem so that it is extensive in N.
+KSPGMRES(30) + PCJACOBI, fp64.  The measured path is the REFERENCE'S OWN KSPSolve (gmres.c / borthog2.c of the unmodified
+libpetsc under baseline/_ref) with -mat_type aijb200 -vec_type b200 from petsc_plugin/libpetscb200plugin.so: every Mat / Vec /
+PC operation of the loop runs in the sm_100a kernels of libpetscb200.so, driven by petsc_plugin/b200_driver.c (a PETSc program,
+loaded into this process).  A "step" is one GMRES(30) restart cycle = 30 Krylov iterations (30 x [SpMV+Jacobi, MDot, MAXPY,
+norm, scale], solution update).  N > 1 is weak scaling: every rank owns a 512 x 512 x 512 slab of a 512 x 512 x (512 N) grid
+(row-partitioned mpiaijb200/mpib200, NCCL halo + all-reduces); `value` counts iterations in units of one 512^3 problem so
+that it is extensive in N.  Before the timed region an N > 1 run verifies the multi-rank path against the oracle
+(`parity_check`).  (Without a PETSc library to host the plugin the harness mini-PETSc drives the same kernels: "host":"harness".)
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 512]
 
@@ -28,6 +32,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 RESTART = 30
+# ONE unit string for both arms (the driver divides them): GMRES iterations per second on the 512^3-row problem; under weak
+# scaling the product arm multiplies by n_gpus (N problems' worth of rows advance per iteration) -- see "unit_note"
+UNIT = "iterations/s"
+UNIT_NOTE = "GMRES(30)+Jacobi iterations per second in units of one 512^3-row problem; x n_gpus under weak scaling"
+
+
+def _load_traffic():
+    """dram bytes per launch from the committed ncu captures (profiles/traffic.json: kernel -> bytes), or nothing"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
+TRAFFIC = _load_traffic()
 
 
 def env_int(k, d):
@@ -135,9 +154,165 @@ class Dist:
             self.td.destroy_process_group()
 
 
-# ---------------------------------------------------------------------------------------------- product arm
+# ---------------------------------------------------------------------------------------------- product arm (real PETSc + plugin)
+def _parity_block(D, drv, env):
+    """N > 1 only: the multi-rank path (mpiaijb200 split / garray, halo MatMult, fused Jacobi, all-reduced reductions, GMRES +
+    PCBJACOBI/ILU(0) vs ex2_2.out) through the real-PETSc driver AND through the harness, both against the oracle.  The oracle
+    is used here as the checker only (tools/plugin_parity.py, tests/_mpi_nccl_worker.py)."""
+    import tempfile
+    from oracle import oracle_py as O
+    sys.path.insert(0, os.path.join(ROOT, "tools")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import plugin_parity as PP
+
+    class Ck:
+        def __init__(self):
+            self.passed, self.failed = 0, []
+
+        def __call__(self, cond, what):
+            if bool(cond):
+                self.passed += 1
+            else:
+                self.failed.append(str(what))
+    ck = Ck()
+
+    def gather(a):
+        box = [None] * D.size
+        D.td.all_gather_object(box, np.asarray(a))
+        return np.concatenate(box)
+    d = D.bcast(tempfile.mkdtemp(prefix="b200parity_") if D.rank == 0 else None)
+    cs = PP.write(d, O, D.rank, D.size)
+    D.barrier()
+    try:
+        drv.run(["-parity", d], env=env)
+        D.barrier()
+        PP.check(cs, O, D.rank, D.size, ck, gather)
+    except Exception as e:  # noqa: BLE001
+        ck(False, "real-PETSc parity driver failed: %r" % (e,))
+    n_plugin = ck.passed
+    D.barrier()
+    if D.rank == 0:
+        PP.cleanup(d)
+    box = [None] * D.size
+    D.td.all_gather_object(box, (ck.passed, ck.failed))
+    passed = sum(b[0] for b in box)
+    failures = ["rank %d: %s" % (r, f) for r, b in enumerate(box) for f in b[1]]
+    return {"passed": passed, "failed": len(failures), "failures": failures[:20], "per_rank_checks_real_petsc_plugin": n_plugin,
+            "what": "garray/blocks index-exact vs MatSetUpMultiply_MPIAIJ restatement; rank-local MatMult bit-exact; fused Jacobi == unfused; MatMultTranspose (reverse scatter); "
+                    "MDot/Norm/Dot 1e-12; GMRES+BJACOBI/ILU(0), GMRES+Jacobi, CG+BJACOBI histories 1e-12*r0 (ex2_2.out digits at N=2); through the reference's own KSPSolve + plugin"}
+
+
 def run_product(a, D):
-    from petsc_b200 import _capi, petsc
+    from petsc_b200 import _capi, petsc_driver as drv
+    if not drv.available():
+        return run_product_harness(a, D)
+    K, W, n = a.steps, a.warmup, a.n
+    _capi.lib()
+    uid = D.bcast(drv.unique_id_hex() if (D.rank == 0 and D.size > 1) else None)
+    env = drv.rank_env(D.rank, D.size, uid, device=D.local)
+    peak, peak_src = measured_peak()
+    parity = _parity_block(D, drv, env) if (D.size > 1 and not a.no_parity) else None
+
+    clocks = ClockSampler(D.local)
+    clocks.start()
+    time.sleep(0.6)
+    clocks.mark()
+    args = ["-bench", "gmres7", "-n", n, "-steps", K, "-warmup", W, "-kernels", 1, "-e2e", 0 if a.no_e2e else 1, "-ksp_gmres_restart", RESTART] + (a.options.split() if a.options else [])
+    recs = drv.run(args, env=env)
+    clk = clocks.stop()
+    D.barrier()
+    if D.rank != 0:
+        # ranks > 0 still take part in the extra multi-rank configs below
+        if D.size == 8 and not a.no_configs:
+            drv.run(["-bench", "gmres7", "-nx", 1024, "-ny", 1024, "-nzl", 128, "-steps", 2, "-warmup", 1, "-kernels", 0, "-pc_type", "bjacobi", "-sub_pc_type", "ilu", "-sub_pc_factor_mat_solver_type", "b200"], env=env)
+        return None
+    solve = [r for r in recs if r["kind"] == "solve"][0]
+    kern = [r for r in recs if r["kind"] == "kernels"][0]
+    e2r = ([r for r in recs if r["kind"] == "e2e"] or [None])[0]
+    assert solve["sum_A_ones"] == solve["expected_sum_A_ones"], "operator checksum sum(A*1) != 7N - nnz"
+    its_per_s = solve["iterations_per_sec"]
+    value = its_per_s * D.size
+    nloc, nnz = solve["rows_per_rank"], solve["nnz_per_rank"]
+
+    def roof(name, ms, alg, extra=None):
+        ach = alg / (ms * 1e-3) / 1e9
+        r = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "frac_of_nominal_8TBs": round(ach / 8000.0, 4),
+             "ms": round(ms, 4), "algorithmic_bytes": int(alg), "traffic": TRAFFIC.get(name.split(" ")[0])}
+        r.update(extra or {})
+        return r
+    roofline = roof("csr_spmv_tile_kernel<1,2,0> (MatMult_SeqAIJB200)", kern["spmv_ms"], kern["spmv_algorithmic_bytes"],
+                    {"gflops": round(kern["spmv_flops"] / (kern["spmv_ms"] * 1e-3) / 1e9, 1), "peak_source": peak_src,
+                     "note": "timed alone with CUDA events through PETSc's MatMult on the diagonal block; reads >> writes, so it can exceed the read+write copy peak"})
+    kernels = [roofline,
+               roof("maxpy_kernel<30> (VecMAXPY_SeqB200, nv=30, fused |x|^2)", kern["maxpy_ms"], kern["maxpy_algorithmic_bytes"]),
+               roof("mdot_kernel<15,split> (VecMDot_SeqB200, nv=30)", kern["mdot_ms"], kern["mdot_algorithmic_bytes"]),
+               roof("csr_spmv_tile_kernel<1,2,0>+jacobi epilogue (PCApplyBAorAB, fused)", kern["pcapplyba_ms"], kern["spmv_algorithmic_bytes"] + 8 * nloc)]
+    alg_bytes = kern["spmv_algorithmic_bytes"]
+    it_bytes = nloc * (alg_bytes / nloc + 8 + sum(8 * (j + 2) + 8 * (j + 3) for j in range(RESTART)) / RESTART + 16)
+    iter_model = {"bytes_per_iteration": int(it_bytes), "achieved_gbs": round(it_bytes * its_per_s / 1e9, 1), "frac_of_peak": round(it_bytes * its_per_s / 1e9 / peak, 4),
+                  "spmv_bound_ratio": round((1.0 / its_per_s) / (it_bytes / (roofline["achieved"] * 1e9)), 3)}
+    e2e = None
+    if e2r:
+        e2e = {"value": round(e2r["iterations_per_sec"] * D.size, 3), "unit": UNIT, "h2d_bytes_per_step": int(e2r["h2d_bytes_per_step"]), "d2h_bytes_per_step": int(e2r["d2h_bytes_per_step"]),
+               "note": "PETSc public API on HOST buffers (pinned). Timed (CUDA events, max over ranks): K x [b modified in the user's host buffer -> H2D, KSPSolve = one GMRES(30) cycle in the reference's gmres.c, x device->host into "
+                       "the user's buffer]. One-time set-up is reported beside it, not inside (the reference arm times KSPSolve on a pre-assembled matrix too): MatCreateSeqAIJWithArrays + MatSetType(aijb200) "
+                       "[N>1: MatCreateMPIAIJB200WithSplitArrays] adopting the user's CSR arrays, MatCreateVecs + VecPlaceArray on the user's b/x, KSPSetUp, and a first solve that uploads the matrix. Bytes counted by the library.",
+               "ms_per_step": e2r["ms_per_step"], "ms_total": e2r["ms_total"], "phases_ms": e2r["phases_ms"], "setup_ms": e2r["setup_ms"],
+               "value_incl_one_time_setup_amortised_over_%d_steps" % K: round(e2r["iterations_per_sec_incl_one_time_setup"] * D.size, 3), "x_checksum": e2r["x_checksum"]}
+    out = {
+        "metric": "gmres30_jacobi_iterations_per_sec", "value": round(value, 3), "unit": UNIT, "unit_note": UNIT_NOTE,
+        "n_gpus": D.size, "steps": K, "warmup": W, "ms_per_step": round(solve["ms_per_step"], 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "host": "PETSc 3.25.4-dev (unmodified reference library, MPIUNI) + libpetscb200plugin.so: KSPSolve = the reference's gmres.c; -mat_type aijb200 -vec_type b200 -pc_type jacobi (fused sub-class)",
+        "config": {"workload": "3D 7-point Laplacian %d^3 per GPU (global %dx%dx%d), MATSEQAIJ/MATMPIAIJ CSR int32+fp64, KSPGMRES(30)+PCJACOBI left-preconditioned, b=A*1, x0=0" % (n, n, n, n * D.size),
+                   "rows_per_gpu": nloc, "nnz_per_gpu": nnz, "step": "one GMRES(30) restart cycle = 30 iterations", "parallelism": "row-partitioned x%d, NCCL halo + all-reduce" % D.size,
+                   "l2_policy": "inputs_larger_than_L2 (13.9 GB matrix + 36 GB Krylov basis vs 126 MB L2)", "final_preconditioned_residual": solve["rnorm"],
+                   "operator_checksum_sum_A_ones": solve["sum_A_ones"]},
+        "iterations_per_sec_global_problem": round(its_per_s, 3),
+        "spmv_gflops": roofline["gflops"], "roofline": roofline, "roofline_kernels": kernels, "iteration_model": iter_model,
+        "gpu_launches": int(solve["gpu_launches"]), "pcie_bytes_in_timed_region": {"h2d": solve["h2d_bytes_in_timed_region"], "d2h": solve["d2h_bytes_in_timed_region"]},
+        "clocks": clk, "e2e": e2e,
+    }
+    if parity is not None:
+        out["parity_check"] = parity
+    if not a.no_configs:
+        out["configs"] = other_configs(a, D, drv, env, peak)
+    if D.size == 1 and not a.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(a)
+    return out
+
+
+def other_configs(a, D, drv, env, peak):
+    """The BASELINE configs that are not the headline, through the same real-PETSc driver (rank 0 collects)."""
+    res = {}
+
+    def frac(alg, ms):
+        return {"gbs": round(alg / ms / 1e6, 1), "frac": round(alg / ms / 1e6 / peak, 4)}
+    try:
+        if D.size == 1:
+            r = drv.run(["-bench", "ex2", "-m", 100, "-n", 100, "-ksp_type", "gmres", "-pc_type", "jacobi"], env=env)[0]
+            res["c1_ex2_100"] = dict(r, reference="ex2 -m 100 -n 100 -ksp_type gmres -pc_type jacobi on the CPU types: 719 iterations, residual 4.918891918633e-06, error 0.00920721 (SURVEY 6)")
+            r = drv.run(["-bench", "cg27", "-n", 256], env=env)[0]
+            r["spmv"] = frac(r["spmv_algorithmic_bytes"], r["spmv_ms"]); r["sptrsv"] = frac(r["sptrsv_algorithmic_bytes"], r["pcapply_ilu_ms"])
+            res["c3_cg_ilu0_27pt_256"] = r
+            for d in (5, 32, 128, 512):
+                nr = 10_000_000 if d < 512 else 2_500_000   # 32-bit PetscInt: n*d < 2^31 (SURVEY 7 hard part 2)
+                r = drv.run(["-bench", "rand", "-rand_n", nr, "-rand_d", d], env=env)[0]
+                r.update(frac(r["algorithmic_bytes"], r["ms"])); r["gflops"] = round(r["flops"] / r["ms"] / 1e6, 1)
+                res["c5_random_d%d" % d] = r
+        if D.size == 8:
+            r = [x for x in drv.run(["-bench", "gmres7", "-nx", 1024, "-ny", 1024, "-nzl", 128, "-steps", 2, "-warmup", 1, "-kernels", 0, "-pc_type", "bjacobi", "-sub_pc_type", "ilu",
+                                     "-sub_pc_factor_mat_solver_type", "b200"], env=env) if x["kind"] == "solve"][0]
+            res["c4_gmres_bjacobi_1024cube"] = dict(r, note="BASELINE configs[3] as stated: 1024^3 cube, 1024x1024x128 slab per rank (8 MiB halos), GMRES(30)+PCBJACOBI/ILU(0), 2 cycles")
+    except Exception as e:  # noqa: BLE001
+        res["error"] = repr(e)[:500]
+    return res
+
+
+# ---------------------------------------------------------------------------------------------- harness fallback
+def run_product_harness(a, D):
+    """Fallback when no PETSc library is available to host the plugin: the harness mini-PETSc drives the same kernels."""
+    from petsc_b200 import _capi
+    from harness import petsc
     K, W, n = a.steps, a.warmup, a.n
     L = _capi.lib()
     petsc.initialize(device=D.local)
@@ -221,7 +396,7 @@ def run_product(a, D):
     achieved = alg_bytes / (spmv_ms * 1e-3) / 1e9
     roofline = {"kernel": "csr_spmv_tile_kernel<1> (MatMult_SeqAIJB200)", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4), "peak_source": peak_src,
-                "traffic": a.traffic, "ms": round(spmv_ms, 4), "gflops": round(flops / (spmv_ms * 1e-3) / 1e9, 1), "algorithmic_bytes": alg_bytes}
+                "traffic": TRAFFIC.get("csr_spmv_tile_kernel<1,2,0>"), "ms": round(spmv_ms, 4), "gflops": round(flops / (spmv_ms * 1e-3) / 1e9, 1), "algorithmic_bytes": alg_bytes}
     xs.destroy(); ys.destroy()
     # whole-iteration model: bytes/row/iteration averaged over a 30-cycle with Jacobi fused into the SpMV and the norm into MAXPY
     it_bytes = nloc * (alg_bytes / nloc + 8 + sum(8 * (j + 2) + 8 * (j + 3) for j in range(RESTART)) / RESTART + 16)
@@ -235,7 +410,8 @@ def run_product(a, D):
         e2e = run_e2e(a, D, petsc, _capi, L, H, Hh, d_i, d_j, d_a, nloc, nnz, comm, K)
 
     out = {
-        "metric": "gmres30_jacobi_iterations_per_sec", "value": round(value, 3), "unit": "iterations/s (per 512^3-row problem unit; x n_gpus under weak scaling)",
+        "host": "harness (no PETSc library under baseline/_ref to host the plugin)", "unit_note": UNIT_NOTE,
+        "metric": "gmres30_jacobi_iterations_per_sec", "value": round(value, 3), "unit": UNIT,
         "n_gpus": D.size, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "3D 7-point Laplacian %d^3 per GPU (global %dx%dx%d), MATSEQAIJ/MATMPIAIJ CSR int32+fp64, KSPGMRES(30)+PCJACOBI left-preconditioned, b=A*1, x0=0" % (n, n, n, nzg),
@@ -246,7 +422,7 @@ def run_product(a, D):
         "gpu_launches": int(launches), "clocks": clk, "e2e": e2e,
     }
     if D.rank == 0 and D.size == 1 and not a.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(a, quick=True)
+        out["cpu_baseline"] = cpu_baseline(a)
     return out
 
 
@@ -332,7 +508,7 @@ def run_e2e(a, D, petsc, _capi, L, H, Hh, d_i, d_j, d_a, nloc, nnz, comm, K):
         h2d += 8 * nloc; d2h += 8 * nloc
     timer.stop()
     ms = D.max(timer.ms())
-    res = {"value": round(RESTART * K / (ms * 1e-3) * D.size, 3), "unit": "iterations/s (same unit as value)", "h2d_bytes_per_step": int(h2d // K), "d2h_bytes_per_step": int(d2h // K),
+    res = {"value": round(RESTART * K / (ms * 1e-3) * D.size, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d // K), "d2h_bytes_per_step": int(d2h // K),
            "note": "user data (CSR, b, x) in pinned host buffers; timed region = MatCreate + Mat*AIJSetPreallocationCSR (host->device) + VecCreate*WithArray + K x [b host->device, KSPSolve 30 its, x device->host]; matrix upload amortised over %d steps" % K,
            "ms_total": round(ms, 2), "phases_ms": {k: round(v, 2) for k, v in phases.items()}, "x_checksum": float(sum(hx))}
     ksp.destroy(); x.destroy(); b.destroy(); A.destroy()
@@ -341,85 +517,128 @@ def run_e2e(a, D, petsc, _capi, L, H, Hh, d_i, d_j, d_a, nloc, nnz, comm, K):
     return res
 
 
-# ---------------------------------------------------------------------------------------------- CPU arms (oracle)
-def cpu_baseline(a, quick=False, steps=1, warmup=0):
-    """The reference's CPU algorithm (restated in oracle/, OpenMP over all host cores) on a bounded sample of the workload:
-    the same 7-point operator at 256^3 (1/8 of the rows), one GMRES(30)+Jacobi cycle per step, scaled to the 512^3 unit
-    (the path is bandwidth bound, cost is linear in the number of rows)."""
+# ---------------------------------------------------------------------------------------------- CPU arms
+BLASDIR = "/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs"
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")   # oracle/ref_driver.c linked against the reference library (baseline/_ref/petsc)
+
+
+def host_threads():
+    """Threads the CPU arms may use: min(logical CPUs, cgroup CPU quota).  (Round 1 ran 128 OpenMP threads on a 16-core quota
+    and saw a 5x run-to-run spread.)"""
+    n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        pass
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return max(1, int(min(n, quota) if quota else n)), quota
+
+
+def reference_run(ns, threads, timeout=3000):
+    """The REFERENCE ITSELF (PETSc built from /root/reference: MATSEQAIJ, VECSEQ, KSPGMRES(30)+PCJACOBI, gmres.c) on the 7-point
+    ns^3 operator: one restart cycle of 30 iterations, timed by the reference's own PetscTime around KSPSolve.  MPIUNI build: the
+    Krylov loop runs on one core, OpenBLAS (dgemv-based VecMDot, ddot, daxpy) may use `threads`.  None if the binary did not travel."""
+    if not os.path.exists(REF_DRIVER):
+        return None
+    env = dict(os.environ, LD_LIBRARY_PATH=BLASDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""), OMP_NUM_THREADS=str(threads), OPENBLAS_NUM_THREADS=str(threads), OMP_PROC_BIND="close")
+    t0 = time.time()
+    p = subprocess.run([REF_DRIVER, "-bench7", str(ns), "-ksp_type", "gmres", "-pc_type", "jacobi", "-ksp_gmres_restart", str(RESTART), "-ksp_max_it", str(RESTART),
+                        "-ksp_rtol", "1e-300", "-ksp_atol", "1e-300", "-ksp_divtol", "1e300", "-options_left", "0"], capture_output=True, text=True, timeout=timeout, env=env)
+    wall = time.time() - t0
+    line = [l for l in p.stdout.splitlines() if l.startswith("REFBENCH")]
+    if p.returncode != 0 or not line:
+        return {"error": "ref_driver failed (%d): %s" % (p.returncode, (p.stdout + p.stderr)[-400:])}
+    kv = dict(t.split("=") for t in line[0].split()[1:])
+    N, ks, ms_ = int(kv["rows"]), float(kv["ksp_s"]), float(kv["matmult_s"])
+    return {"rows": N, "nnz": int(kv["nnz"]), "ksp_its": int(kv["ksp_its"]), "ksp_seconds": ks, "matmult_seconds": ms_, "spmv_gflops": round((2 * int(kv["nnz"]) - N) / ms_ / 1e9, 3),
+            "process_wall_seconds": round(wall, 1), "blas_threads": threads}
+
+
+def port_run(a, ns, threads, steps=1):
+    """The oracle's OpenMP restatement of the same cycle (all allowed threads: MatMult, MDot, MAXPY, dots are threaded)."""
     from oracle import oracle_py as O
-    ns = a.cpu_n
+    O.set_num_threads(threads)
     ai, aj, aa = O.lap7(ns, omp=True)                # filled by all threads: NUMA first touch
     N = ns ** 3
     b = O.matmult(ai, aj, aa, np.ones(N), omp=True)
-    thr = O.max_threads()
     times = []
-    for s in range(warmup + steps):
+    for s in range(steps + 1):                        # first cycle = warm-up (page faults of the Krylov basis)
         t = time.time()
         x, r = O.ksp_solve("gmres", ai, aj, aa, b, pc="jacobi", restart=RESTART, max_it=RESTART, rtol=1e-300, abstol=1e-300, dtol=1e300, omp=True)
-        dt = time.time() - t
-        if s >= warmup:
-            times.append(dt)
+        if s:
+            times.append(time.time() - t)
         assert r["its"] == RESTART
-    dt = float(np.mean(times))
-    scale = N / float(a.n ** 3)
-    # CPU SpMV alone
-    t = time.time(); reps = 5
+    t = time.time(); reps = 3
     for _ in range(reps):
         O.matmult(ai, aj, aa, b, omp=True)
     spmv_s = (time.time() - t) / reps
-    port = {"value": round(RESTART / dt * scale, 4), "unit": "iterations/s (512^3 unit)", "cores": thr, "kind": "port",
-            "sample": "oracle GMRES(30)+Jacobi (OpenMP, all host cores), 7-pt %d^3 (%d rows), %d cycle(s) of 30 iterations, %.2f s per cycle, scaled by rows %d^3/%d^3" % (ns, N, steps, dt, ns, a.n),
-            "spmv_gflops": round((2 * len(aj) - N) / spmv_s / 1e9, 3), "seconds_per_step_sample": round(dt, 3)}
-    try:  # a container CPU quota (cgroup cpu.max) caps what "all host cores" can deliver: record it next to the number
-        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
-        port["cgroup_cpu_quota_cores"] = None if q == "max" else round(float(q) / float(per), 2)
-    except Exception:
-        pass
-    ref = reference_1core(a)
-    if ref is None:
-        return port
-    # the reference itself (real PETSc MATSEQAIJ/VECSEQ/KSPGMRES, MPIUNI => one core) next to the all-cores port; the faster
-    # of the two is the headline CPU number, the other is kept alongside
-    if ref["value"] > port["value"]:
-        ref["port_all_cores"] = port
-        return ref
-    port["reference_1core"] = ref
-    return port
+    dt = float(np.mean(times))
+    return {"rows": N, "seconds_per_cycle": round(dt, 3), "spread": [round(min(times), 3), round(max(times), 3)], "cycles_timed": steps, "threads": threads,
+            "spmv_gflops": round((2 * len(aj) - N) / spmv_s / 1e9, 3), "iterations_per_sec_sample": round(RESTART / dt, 4)}
 
 
-def reference_1core(a):
-    """oracle/_ref/ref_driver: the reference's own KSPSolve (built against the reference library in the build container,
-    see oracle/build_ref_demo.sh) on the same bounded sample.  None when the binaries did not travel."""
-    exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
-    if not os.path.exists(exe):
-        return None
-    env = dict(os.environ, LD_LIBRARY_PATH="/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs:" + os.environ.get("LD_LIBRARY_PATH", ""),
-               OMP_NUM_THREADS="1")
-    ns = min(a.cpu_n, 192)
+def cpu_baseline(a):
+    """Reported CPU baseline beside the product arm (rank 0, N = 1): a BOUNDED sample of the same workload, the 7-point operator at
+    cpu_n^3 (default 256^3 = 1/8 of the rows; ~20 s), one GMRES(30)+Jacobi cycle, by the reference itself (`kind` "reference") and
+    by the all-threads OpenMP port next to it.  value = iterations/s in 512^3 units = sample iterations/s x rows_sample/rows_512^3
+    (the cycle is bandwidth bound: cost linear in the rows) -- the raw sample numbers are kept alongside."""
+    thr, quota = host_threads()
+    ns = a.cpu_n
+    scale = (ns ** 3) / float(a.n ** 3)
+    ref = reference_run(ns, thr)
+    port = None
     try:
-        out = subprocess.run([exe, "-bench7", str(ns), "-ksp_type", "gmres", "-pc_type", "jacobi", "-ksp_gmres_restart", str(RESTART), "-ksp_max_it", str(RESTART),
-                              "-ksp_rtol", "1e-300", "-ksp_atol", "1e-300", "-ksp_divtol", "1e300"], capture_output=True, text=True, timeout=600, env=env).stdout
-        line = [l for l in out.splitlines() if l.startswith("REFBENCH")][0]
-        kv = dict(t.split("=") for t in line.split()[1:])
-        N, ks, ms_ = int(kv["rows"]), float(kv["ksp_s"]), float(kv["matmult_s"])
-        scale = N / float(a.n ** 3)
-        return {"value": round(int(kv["ksp_its"]) / ks * scale, 5), "unit": "iterations/s (512^3 unit)", "cores": 1, "kind": "reference",
-                "sample": "PETSc 3.25.4-dev KSPSolve (MATSEQAIJ, VECSEQ, KSPGMRES(30)+PCJACOBI, MPIUNI build: 1 core), 7-pt %d^3, one cycle of 30 iterations in %.2f s, scaled by rows" % (ns, ks),
-                "spmv_gflops": round((2 * int(kv["nnz"]) - N) / ms_ / 1e9, 3), "seconds_per_step_sample": round(ks, 3)}
-    except Exception as e:  # the reference binaries are optional
-        return {"value": 0.0, "unit": "iterations/s (512^3 unit)", "cores": 1, "kind": "reference", "sample": "ref_driver failed: %r" % (e,)}
+        port = port_run(a, ns, thr, steps=2)
+    except Exception as e:  # noqa: BLE001
+        port = {"error": repr(e)[:300]}
+    out = {"unit": UNIT, "cores": thr, "cgroup_cpu_quota_cores": quota, "logical_cpus": os.cpu_count()}
+    if ref and "error" not in ref:
+        out.update(value=round(ref["ksp_its"] / ref["ksp_seconds"] * scale, 5), kind="reference",
+                   sample="PETSc 3.25.4-dev built from the reference sources (MATSEQAIJ, VECSEQ, KSPGMRES(30)+PCJACOBI; MPIUNI: one rank, OpenBLAS threads = %d): 7-pt %d^3, one cycle of 30 iterations in %.2f s; scaled by rows %d^3/%d^3"
+                          % (thr, ns, ref["ksp_seconds"], ns, a.n), raw_sample=ref)
+        out["port_all_threads"] = port
+    else:
+        pv = port.get("iterations_per_sec_sample", 0.0) * scale
+        out.update(value=round(pv, 5), kind="port", sample="oracle OpenMP restatement, %d threads, 7-pt %d^3, scaled by rows" % (thr, ns), raw_sample=port, reference_error=ref)
+    return out
 
 
 def run_reference(a, D):
+    """--impl reference: the reference's own CPU implementation on this box's host cores, on the SAME config (7-point 512^3,
+    GMRES(30)+Jacobi).  The real reference needs ~2.5 min per step at 512^3, so whatever --steps/--warmup ask for, exactly ONE
+    step is run and timed (reported as steps = 1, warmup = 0: the numbers describe what ran).  Fallback when the reference binary
+    is absent: the OpenMP port on the bounded cpu_n^3 sample, scaled by rows, flagged kind = "port"."""
     if D.rank != 0:
         return None
-    cb = cpu_baseline(a, steps=a.steps, warmup=min(a.warmup, 1))
-    ms_step = RESTART / cb["value"] * 1e3
-    return {"impl": "reference", "metric": "gmres30_jacobi_iterations_per_sec", "value": cb["value"], "unit": "iterations/s (per 512^3-row problem unit)", "n_gpus": D.size,
-            "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": round(ms_step, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": "3D 7-point Laplacian %d^3, KSPGMRES(30)+PCJACOBI on the host cores (bounded sample: %d^3, scaled by rows)" % (a.n, a.cpu_n),
+    thr, quota = host_threads()
+    ref = reference_run(a.n, thr) if not a.ref_sample else None
+    if ref and "error" not in ref:
+        ms_step = ref["ksp_seconds"] * 1e3
+        value = ref["ksp_its"] / ref["ksp_seconds"]
+        cb = {"value": round(value, 5), "unit": UNIT, "cores": thr, "kind": "reference", "cgroup_cpu_quota_cores": quota,
+              "sample": "the full workload, not a sample: PETSc 3.25.4-dev built from the reference sources, 7-pt %d^3 (%d rows, %d nnz), MATSEQAIJ/VECSEQ, KSPGMRES(30)+PCJACOBI, one restart cycle = 30 iterations in %.1f s "
+                        "(MPIUNI: the Krylov loop is one rank; OpenBLAS threads = %d)" % (a.n, ref["rows"], ref["nnz"], ref["ksp_seconds"], thr), "raw": ref}
+        steps, warm = 1, 0
+    else:
+        port = port_run(a, a.cpu_n, thr, steps=max(1, min(a.steps, 3)))
+        scale = (a.cpu_n ** 3) / float(a.n ** 3)
+        value = port["iterations_per_sec_sample"] * scale
+        ms_step = RESTART / value * 1e3
+        cb = {"value": round(value, 5), "unit": UNIT, "cores": thr, "kind": "port", "cgroup_cpu_quota_cores": quota,
+              "sample": "reference binary absent: oracle OpenMP restatement on a %d^3 sample, %d cycle(s), scaled by rows to the %d^3 unit (ms_per_step is the scaled figure, not a measured wall time)" % (a.cpu_n, port["cycles_timed"], a.n),
+              "raw": port, "reference_error": ref}
+        steps, warm = port["cycles_timed"], 1
+    return {"impl": "reference", "metric": "gmres30_jacobi_iterations_per_sec", "value": round(value, 5), "unit": UNIT, "unit_note": UNIT_NOTE, "n_gpus": D.size,
+            "steps": steps, "warmup": warm, "requested": {"steps": a.steps, "warmup": a.warmup}, "ms_per_step": round(ms_step, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": "3D 7-point Laplacian %d^3, MATSEQAIJ, KSPGMRES(30)+PCJACOBI left-preconditioned, b=A*1, x0=0, on the host cores (reference CPU types)" % a.n,
                                             "step": "one GMRES(30) restart cycle = 30 iterations"},
-            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "cpu_baseline": cb, "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
 
 
 def main():
@@ -433,13 +652,10 @@ def main():
     ap.add_argument("--options", default="")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--traffic", type=float, default=None, help="dram bytes/launch of the SpMV kernel from the committed ncu capture")
+    ap.add_argument("--ref-sample", action="store_true", help="--impl reference: use the bounded sample + port instead of the full-size reference run")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-rank parity block (N > 1)")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 1/3/5 (N = 1) and 4 (N = 8)")
     a = ap.parse_args()
-    if a.traffic is None:
-        try:
-            a.traffic = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json")))["dram_bytes_per_launch"]
-        except Exception:
-            a.traffic = None
     # stdout carries exactly ONE line (the JSON): anything libraries print while we run (NCCL's version banner, ...) goes to stderr
     sys.stdout.flush()
     real_stdout = os.dup(1)

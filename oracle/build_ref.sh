@@ -1,12 +1,16 @@
 #!/bin/bash
-# Self-contained build of the REFERENCE (PETSc, /root/reference) into oracle/_ref/petsc  --  test infrastructure only.
+# Self-contained build of the UNMODIFIED REFERENCE (PETSc, /root/reference) into baseline/_ref/petsc (git-ignored, travels to the
+# GPU box).  It serves three roles: the reference arm of bench.py and the golden-fixture generator run it with its own CPU types
+# (-mat_type aij -vec_type standard); and it is the HOST APPLICATION the product is a plugin for: the product arm loads
+# petsc_plugin/libpetscb200plugin.so into this same library (-mat_type aijb200 -vec_type b200), so KSPSolve is the
+# reference's own gmres.c/cg.c while every Mat/Vec/PC operation of the hot path runs in the sm_100a kernels.
 #
-#   oracle/_ref/petsc/lib/libpetsc.so*     the reference library: CPU-only, MPIUNI (no MPI in this image), -O2, no -march
+#   baseline/_ref/petsc/lib/libpetsc.so*     the reference library: CPU-only, MPIUNI (no MPI in this image), -O2, no -march
 #                                          (so PetscSparseDensePlusDot stays the generic FMA-free loop, aij.h:609-614),
 #                                          BLAS/LAPACK = the OpenBLAS 0.3.15 bundled with the opencv wheel of this image
-#   oracle/_ref/petsc/include/             the GENERATED headers of that build (petscconf.h, petscfix.h, ...): what the
+#   baseline/_ref/petsc/include/             the GENERATED headers of that build (petscconf.h, petscfix.h, ...): what the
 #                                          plugin needs beside /root/reference/include to be ABI-locked to this library
-#   oracle/_ref/petsc/build.env            PETSC_DIR / PETSC_ARCH of the scratch build tree (kept for gen_golden.py)
+#   baseline/_ref/petsc/build.env            PETSC_DIR / PETSC_ARCH of the scratch build tree (kept for gen_golden.py)
 #
 # /root/reference is read-only and PETSc configures in-tree, so the tree is copied to a scratch directory under /tmp
 # (never into the repo), configured and built there (~1.5 min + ~1 min on 8 cores), and only the products above are
@@ -16,7 +20,7 @@
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF=/root/reference
-OUT="$HERE/_ref/petsc"
+OUT="$(dirname "$HERE")/baseline/_ref/petsc"
 SCRATCH="${PETSC_SCRATCH:-/tmp/petsc-ref-build}"
 ARCH=arch-ref
 BLASDIR=/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs

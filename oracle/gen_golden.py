@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Generate tests/golden/*.npz by running the REFERENCE's own CPU code on seeded inputs.
 
-Needs the reference library that oracle/build_ref.sh builds from /root/reference into oracle/_ref/petsc (--with-mpi=0
+Needs the reference library that oracle/build_ref.sh builds from /root/reference into baseline/_ref/petsc (--with-mpi=0
 --with-cuda=0 --with-debugging=0 COPTFLAGS=-O2, OpenBLAS 0.3.15 for BLAS) and oracle/_ref/ref_driver (built by the same
 script from ref_driver.c, the program that calls the reference's public API).  It only runs in the build container; the
 fixtures it writes are committed and are what the tests read.
@@ -30,7 +30,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 from oracle import oracle_py as O  # noqa: E402
 
-REFLIB = os.path.join(HERE, "_ref", "petsc", "lib")
+REFLIB = os.path.join(ROOT, "baseline", "_ref", "petsc", "lib")
 BLASDIR = "/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs"
 OUT = os.path.join(ROOT, "tests", "golden")
 

@@ -19,6 +19,15 @@
 static int g_omp = 0;
 #define OMP_FOR _Pragma("omp parallel for schedule(static) if (g_omp && n > 65536)")
 
+void ora_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int ora_max_threads(void)
 {
 #ifdef _OPENMP

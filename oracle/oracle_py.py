@@ -283,5 +283,9 @@ def coo_setvalues(jmap, perm, v, Aa=None):
     return out
 
 
+def set_num_threads(n):
+    lib().ora_set_num_threads(int(n))
+
+
 def max_threads():
     return lib().ora_max_threads()

@@ -311,6 +311,7 @@ static PetscErrorCode VecSet_SeqB200(Vec x, PetscScalar a)
 {
   double *d;
   PetscFunctionBegin;
+  if (!x->map->n) PetscFunctionReturn(PETSC_SUCCESS);
   PetscCall(PB_VecWrite(x, &d));
   PetscCallB200(b200VecSet(PB_h, N_(x), a, d));
   PetscFunctionReturn(PETSC_SUCCESS);
@@ -1032,6 +1033,10 @@ static PetscErrorCode MatMultAdd_SeqAIJB200(Mat A, Vec x, Vec y, Vec z)
   double       *dz;
   PetscFunctionBegin;
   if (PB_BoundToCPU(A) || !PB_IsB200(x) || !PB_IsB200(y) || !PB_IsB200(z)) PetscFunctionReturn((*m->multadd_seqaij)(A, x, y, z));
+  if (!a->nz) { /* no entries (e.g. the off-diagonal block of a one-rank mpiaijb200): z = y */
+    if (z != y) PetscCall(VecCopy(y, z));
+    PetscFunctionReturn(PETSC_SUCCESS);
+  }
   PetscCall(PB_MatSync(A));
   PetscCall(PB_VecRead(x, &dx));
   PetscCall(PB_LogTimeBegin());
@@ -1098,6 +1103,10 @@ static PetscErrorCode MatMultTranspose_SeqAIJB200(Mat A, Vec x, Vec y)
   double       *dy;
   PetscFunctionBegin;
   if (PB_BoundToCPU(A) || !PB_IsB200(x) || !PB_IsB200(y)) PetscFunctionReturn((*m->multtranspose_seqaij)(A, x, y));
+  if (!((Mat_SeqAIJ *)A->data)->nz || !A->cmap->n) {
+    PetscCall(VecSet(y, 0.0));
+    PetscFunctionReturn(PETSC_SUCCESS);
+  }
   PetscCall(PB_MatSyncTranspose(A));
   PetscCall(PB_VecRead(x, &dx));
   PetscCall(PB_VecWrite(y, &dy));
@@ -1715,6 +1724,7 @@ typedef struct {
   PetscObjectState matstate;
   Mat              mat;
   PetscBool        fuse, usable;
+  PetscErrorCode (*apply_parent)(PC, Vec, Vec);
 } PC_JacobiB200;
 
 static PetscErrorCode PB_JacobiCtx(PC pc, PC_JacobiB200 **jac)
@@ -1768,6 +1778,19 @@ static PetscErrorCode PB_JacobiRefresh(PC pc, PC_JacobiB200 *jac)
   jac->usable = PETSC_TRUE;
   PetscFunctionReturn(PETSC_SUCCESS);
 }
+/* PCApply: with the device diagonal at hand it is one VecPointwiseMult (jacobi.c:354).  The parent's lazy set-up
+   (PCSetUp_Jacobi_NonSymmetric -> PCSetUp_Jacobi, jacobi.c:172-270) scans the diagonal for zeros in a HOST loop -- a device ->
+   host -> device round trip of the vector plus n host iterations -- which the device inversion already did (nzero == 0). */
+static PetscErrorCode PCApply_JacobiB200(PC pc, Vec x, Vec y)
+{
+  PC_JacobiB200 *jac;
+  PetscFunctionBegin;
+  PetscCall(PB_JacobiCtx(pc, &jac));
+  PetscCall(PB_JacobiRefresh(pc, jac));
+  if (jac->usable && PB_IsB200(x) && PB_IsB200(y)) PetscCall(VecPointwiseMult(y, x, jac->dinv));
+  else PetscCall((*jac->apply_parent)(pc, x, y));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
 static PetscErrorCode PCApplyBA_JacobiB200(PC pc, PCSide side, Vec x, Vec y, Vec work)
 {
   PC_JacobiB200 *jac;
@@ -1797,7 +1820,7 @@ static PetscErrorCode PCApplyBA_JacobiB200(PC pc, PCSide side, Vec x, Vec y, Vec
     const double   *dx, *dd, *dlr;
     double         *dy, *dl;
     PetscCall(PB_MatSync(mp->A));
-    PetscCall(PB_MatSync(mp->B));
+    if (sB->nz) PetscCall(PB_MatSync(mp->B));
     if (sB->nz && !mB->cr_nrows) { /* off-diagonal block not in compressed-row form: unfused */
       PetscCall(MatMult(A, x, work));
       PetscCall(VecPointwiseMult(y, work, jac->dinv));
@@ -1845,7 +1868,10 @@ PETSC_EXTERN PetscErrorCode PCCreate_JacobiB200(PC pc)
   PetscCall(PetscContainerSetCtxDestroy(c, PB_JacobiCtxDestroy));
   PetscCall(PetscObjectCompose((PetscObject)pc, "PCJacobiB200_ctx", (PetscObject)c));
   PetscCall(PetscContainerDestroy(&c));
-  pc->ops->applyBA = PCApplyBA_JacobiB200;
+  jac->apply_parent       = pc->ops->apply;
+  pc->ops->apply          = PCApply_JacobiB200;
+  pc->ops->applytranspose = PCApply_JacobiB200;
+  pc->ops->applyBA        = PCApplyBA_JacobiB200;
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 

@@ -11,7 +11,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-BIN = os.path.join(ROOT, "oracle", "_ref", "petsc", "bin")
+BIN = os.path.join(ROOT, "baseline", "_ref", "petsc", "bin")
 PLUGIN = os.path.join(ROOT, "petsc_plugin", "libpetscb200plugin.so")
 BLASDIR = "/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs"
 B200 = ["-dll_append", PLUGIN, "-mat_type", "aijb200", "-vec_type", "b200"]
@@ -40,7 +40,7 @@ def history(out):
     return np.array([float(m.group(1)) for m in re.finditer(r"KSP Residual norm ([0-9.eE+-]+)", out)])
 
 
-@pytest.mark.skipif(not have(), reason="oracle/_ref/petsc not built (needs the build container)")
+@pytest.mark.skipif(not have(), reason="baseline/_ref/petsc not built (needs the build container)")
 def test_ex2_golden_through_plugin():
     """ex2_1.out reproduced (all printed digits) by the reference's own ex2 running on the b200 types."""
     out = run("ex2", ["-m", "5", "-n", "5", "-ksp_monitor", "-ksp_gmres_cgs_refinement_type", "refine_always"] + B200)
@@ -55,7 +55,7 @@ def test_ex2_golden_through_plugin():
     assert "seqaijb200" in view and re.search(r"package used to perform factorization: *b200", view), view
 
 
-@pytest.mark.skipif(not have(), reason="oracle/_ref/petsc not built (needs the build container)")
+@pytest.mark.skipif(not have(), reason="baseline/_ref/petsc not built (needs the build container)")
 @pytest.mark.parametrize("opts", [
     ["-m", "100", "-n", "100", "-ksp_type", "gmres", "-pc_type", "jacobi"],          # BASELINE config 1
     ["-m", "60", "-n", "50", "-ksp_type", "cg", "-pc_type", "ilu"],
@@ -76,7 +76,7 @@ def test_ex2_plugin_matches_reference_cpu_types(opts):
     assert np.isclose(ea, eb, rtol=1e-3)
 
 
-@pytest.mark.skipif(not have(), reason="oracle/_ref/petsc not built (needs the build container)")
+@pytest.mark.skipif(not have(), reason="baseline/_ref/petsc not built (needs the build container)")
 def test_bench_kspsolve_through_plugin():
     """The reference's own benchmark driver (27-point stencil, COO assembly path falls back to the parent) on the b200 types."""
     common = ["-n", "24", "-ksp_monitor", "-print_timing", "false", "-ksp_type", "cg", "-pc_type", "ilu"]
@@ -88,7 +88,7 @@ def test_bench_kspsolve_through_plugin():
     assert "Number of nonzeros = %d" % ((3 * 32 - 2) ** 3) in mm
 
 
-@pytest.mark.skipif(not have(), reason="oracle/_ref/petsc not built (needs the build container)")
+@pytest.mark.skipif(not have(), reason="baseline/_ref/petsc not built (needs the build container)")
 def test_ex2_fused_jacobi_pc_matches_pcjacobi():
     """-pc_type jacobib200 (PCRegister'ed by the plugin; ops->applyBA = one fused SpMV+Jacobi kernel) gives the residual history
     of the reference's PCJACOBI on the same types to the last digit printed, and of the CPU types to 1e-10."""
@@ -104,7 +104,7 @@ def test_ex2_fused_jacobi_pc_matches_pcjacobi():
     assert "jacobib200" in view
 
 
-@pytest.mark.skipif(not have(), reason="oracle/_ref/petsc not built (needs the build container)")
+@pytest.mark.skipif(not have(), reason="baseline/_ref/petsc not built (needs the build container)")
 def test_ex2_bicg_uses_device_transpose():
     """KSPBICG needs MatMultTranspose and PCApplyTranspose: the plugin's explicit-transpose product vs the CPU types."""
     opts = ["-m", "40", "-n", "40", "-ksp_type", "bicg", "-pc_type", "jacobi", "-ksp_monitor"]
@@ -114,7 +114,7 @@ def test_ex2_bicg_uses_device_transpose():
     assert np.allclose(ha[:k], hb[:k], rtol=1e-8, atol=1e-12 * hb[0])
 
 
-@pytest.mark.skipif(not (have() and os.path.exists(os.path.join(BIN, "plugin_driver"))), reason="oracle/_ref/petsc/bin/plugin_driver not built")
+@pytest.mark.skipif(not (have() and os.path.exists(os.path.join(BIN, "plugin_driver"))), reason="baseline/_ref/petsc/bin/plugin_driver not built")
 def test_plugin_driver_device_coo_transpose_bindtocpu():
     out = run("plugin_driver", B200 + ["-mat_b200_spmv_ordered"])  # reference-order row sums: the products are compared bit for bit
     assert "all ok" in out and "FAILED" not in out, out
