@@ -198,6 +198,7 @@ typedef struct { /* Mat_MPIAIJ (mpiaij.h:41-76) */
 typedef struct _COOEntry {
   PetscInt row, col;
   double   v;
+  size_t   seq; /* arrival order: makes the (row,col) sort stable so that INSERT_VALUES keeps the LAST value */
 } COOEntry;
 struct _p_Mat {
   PetscObjectHeader hdr;
@@ -209,6 +210,8 @@ struct _p_Mat {
   /* MatSetValues staging (the stash of matstash.c, local rows only) */
   COOEntry *coo;
   size_t    ncoo, coocap;
+  int       stash_mode;    /* 0 = nothing staged, else the InsertMode of the staged entries (mixing is an error, matrix.c:1480) */
+  int       ever_assembled;
   int       spmv_layout[4];
   int       spmv_ordered; /* -mat_b200_spmv_ordered: row sums in the reference's order for every lane count (bit-exact MatMult) */
   int64_t   coo_n; /* length of the arrays given to MatSetPreallocationCOO */
@@ -232,6 +235,7 @@ struct _p_PC {
   struct _PCOps     ops;
   Mat               mat, pmat;
   int               setupcalled, type_set;
+  int64_t           matstate; /* pmat->hdr.state at the last set-up: PCSetUp refreshes when the operator changed (precon.c:1080-1110) */
   void             *data;
 };
 

@@ -141,7 +141,7 @@ PetscErrorCode KSPSetUp(KSP ksp)
   PetscValidHeader(ksp, 1);
   if (!ksp->type_set) PetscCall(KSPSetType(ksp, KSPGMRES));
   PetscCall(KSPGetPC(ksp, &pc));
-  if (ksp->setupcalled) return PETSC_SUCCESS;
+  if (ksp->setupcalled) return PCSetUp(pc); /* KSPSetUp always hands over to PCSetUp, which refreshes when the operator changed (itfunc.c:449) */
   PetscCheck(pc->mat, ksp->hdr.comm, PETSC_ERR_ARG_WRONGSTATE, "Matrix must be set first: call KSPSetOperators()");
   PetscCheck(ksp->vec_rhs && ksp->vec_sol, ksp->hdr.comm, PETSC_ERR_ARG_WRONGSTATE, "KSPSetUp() needs the vectors of KSPSolve() in this mirror");
   if (ksp->ops.setup) PetscCall((*ksp->ops.setup)(ksp));

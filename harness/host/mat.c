@@ -140,7 +140,13 @@ PetscErrorCode MatSetOption(Mat mat, MatOption op, PetscBool flg)
 PetscErrorCode MatSetValues(Mat mat, PetscInt m, const PetscInt idxm[], PetscInt n, const PetscInt idxn[], const PetscScalar v[], InsertMode addv)
 {
   PetscCall(MatPrep(mat));
-  (void)addv;
+  PetscCheck(addv == INSERT_VALUES || addv == ADD_VALUES, mat->hdr.comm, PETSC_ERR_ARG_OUTOFRANGE, "InsertMode must be INSERT_VALUES or ADD_VALUES");
+  /* MatSetValues (matrix.c:1480): one mode between two assemblies */
+  PetscCheck(!mat->stash_mode || mat->stash_mode == (int)addv, mat->hdr.comm, PETSC_ERR_ARG_WRONGSTATE, "Cannot mix add values and insert values");
+  /* this harness keeps no host copy of an assembled device matrix to merge new entries into (the reference merges into the
+     existing rows, aij.c:420-560): refuse instead of silently replacing the matrix */
+  PetscCheck(!mat->ever_assembled, mat->hdr.comm, PETSC_ERR_SUP, "MatSetValues on an already assembled matrix is not supported by the test harness (use MatSetValuesCOO or recreate the matrix)");
+  mat->stash_mode = (int)addv;
   for (PetscInt i = 0; i < m; i++) {
     if (idxm[i] < 0) continue;
     PetscCheck(idxm[i] >= mat->rstart && idxm[i] < mat->rend, mat->hdr.comm, PETSC_ERR_SUP, "MatSetValues of off-process row %d (owned [%d,%d)) is not supported by the b200 matrix types", idxm[i], mat->rstart, mat->rend);
@@ -155,6 +161,7 @@ PetscErrorCode MatSetValues(Mat mat, PetscInt m, const PetscInt idxm[], PetscInt
       mat->coo[mat->ncoo].row = idxm[i];
       mat->coo[mat->ncoo].col = idxn[j];
       mat->coo[mat->ncoo].v   = v[(size_t)i * n + j];
+      mat->coo[mat->ncoo].seq = mat->ncoo;
       mat->ncoo++;
     }
   }
@@ -166,7 +173,7 @@ static int coo_cmp(const void *a, const void *b)
   const COOEntry *x = (const COOEntry *)a, *y = (const COOEntry *)b;
   if (x->row != y->row) return x->row < y->row ? -1 : 1;
   if (x->col != y->col) return x->col < y->col ? -1 : 1;
-  return 0;
+  return x->seq < y->seq ? -1 : (x->seq > y->seq ? 1 : 0); /* arrival order: stable */
 }
 PetscErrorCode MatAssemblyBegin(Mat mat, MatAssemblyType type)
 {
@@ -182,12 +189,14 @@ PetscErrorCode MatAssemblyEnd(Mat mat, MatAssemblyType type)
       /* MatAssemblyEnd_SeqAIJ (aij.c:1085): compact the staged entries into sorted CSR rows, duplicates summed */
       size_t    k = 0, nent = mat->ncoo;
       PetscInt *ai = (PetscInt *)calloc((size_t)mat->m + 1, sizeof(PetscInt));
-      /* stable order within equal (row,col): mergesort semantic is irrelevant for ADD; qsort is fine */
+      /* stable within equal (row,col) through the arrival index: ADD_VALUES sums repeats in arrival order, INSERT_VALUES keeps
+         the last one (MatSetValues_SeqAIJ overwrites, aij.c:470) */
+      const int insert = mat->stash_mode == (int)INSERT_VALUES;
       qsort(mat->coo, nent, sizeof(COOEntry), coo_cmp);
       PetscInt *aj = (PetscInt *)malloc(sizeof(PetscInt) * (nent + 1));
       double   *aa = (double *)malloc(sizeof(double) * (nent + 1));
       for (size_t e = 0; e < nent; e++) {
-        if (k && mat->coo[e].row == mat->coo[e - 1].row && mat->coo[e].col == mat->coo[e - 1].col) aa[k - 1] += mat->coo[e].v;
+        if (k && mat->coo[e].row == mat->coo[e - 1].row && mat->coo[e].col == mat->coo[e - 1].col) aa[k - 1] = insert ? mat->coo[e].v : aa[k - 1] + mat->coo[e].v;
         else {
           aj[k] = mat->coo[e].col;
           aa[k] = mat->coo[e].v;
@@ -201,6 +210,8 @@ PetscErrorCode MatAssemblyEnd(Mat mat, MatAssemblyType type)
       free(mat->coo);
       mat->coo  = NULL;
       mat->ncoo = mat->coocap = 0;
+      if (nent) mat->ever_assembled = 1;
+      mat->stash_mode = 0;
     }
   }
   if (mat->ops.assemblyend) PetscCall((*mat->ops.assemblyend)(mat, type));

@@ -92,10 +92,15 @@ PetscErrorCode PCSetUp(PC pc)
 {
   PetscValidHeader(pc, 1);
   PetscCheck(pc->mat, pc->hdr.comm, PETSC_ERR_ARG_WRONGSTATE, "Matrix must be set first");
-  if (pc->setupcalled) return PETSC_SUCCESS;
+  /* PCSetUp (precon.c:1080-1110) compares the operator's object state with the one recorded at the last set-up and rebuilds the
+     preconditioner when the matrix changed (MatSetValuesCOO, MatB200SetCSRDevice, re-assembly all bump hdr.state): stale
+     ILU(0) factors or a stale 1/diag would otherwise be combined with the new A */
+  if (pc->setupcalled && pc->matstate == (int64_t)pc->pmat->hdr.state) return PETSC_SUCCESS;
+  if (pc->setupcalled) PetscCall(PCReset_Private(pc)); /* full rebuild: releases the old factors / diagonal / sub-block Mat */
   PetscCall(PCSetDefaultType(pc));
   if (pc->ops.setup) PetscCall((*pc->ops.setup)(pc));
   pc->setupcalled = 1;
+  pc->matstate    = (int64_t)pc->pmat->hdr.state;
   return PETSC_SUCCESS;
 }
 PetscErrorCode PCApply(PC pc, Vec x, Vec y)

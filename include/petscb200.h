@@ -195,6 +195,8 @@ int b200Ilu0Numeric(b200Handle h, b200IluPlan plan, const double *d_aval, double
 int b200Ilu0Solve(b200Handle h, b200IluPlan plan, const double *d_b, double *d_x);
 int b200Ilu0GetFactor(b200Handle h, b200IluPlan plan, int *h_bi, int *h_bj, int *h_bdiag, double *h_ba); /* tests: copies out */
 int b200Ilu0GetInfo(b200IluPlan plan, int *nlevels_lower, int *nlevels_upper, int64_t *nnz);
+/* schedule of the segment-marching sweeps (ilu.cu): lanes per row, padded segment slots and segment dependency levels */
+int b200Ilu0GetSegmentInfo(b200IluPlan plan, int *lanes, int *nslot_lower, int *nlev_lower, int *nslot_upper, int *nlev_upper);
 
 /* ---- multi-GPU: NCCL replaces MPI in VecScatter/PetscSF (sfbasic.c:352-381, sfmpi.c:6-47) and MPIU_Allreduce
         (pvecimpl.h:101-171) ---- */

@@ -34,6 +34,8 @@ struct b200IluPlan_s {
   int    *d_orderL, *d_orderU;       /* rows in level order, -1 padded to warp multiples */
   int4   *d_metaL, *d_metaU;         /* per slot: (row, first entry, end entry, 0) of the sweep's row segment */
   int     nslotL, nslotU;
+  int2   *d_segL, *d_segU;           /* segment schedule of the marching sweeps: (first row, number of rows) per slot, level order */
+  int     nsegslotL, nsegslotU, nseglevL, nseglevU, GS;
   int    *d_flag;                    /* per-row ready epoch (numeric factorisation) */
   double *d_tmp;                     /* result of the lower sweep */
   int    *d_ticket;                  /* [4] tickets + status */
@@ -46,6 +48,8 @@ struct b200IluPlan_s {
 };
 
 #define ILU_TPB 256
+static int2 *build_segments(int n, const int *bi, const int *bdiag, const int *bj, bool upper, int rpw, int minlen, int maxlen, int *nslot_out, int *nlev_out);
+static int   g_ilu_march = 1; /* PETSCB200_ILU_MARCH=0 selects the level-scheduled pipe kernels */
 
 __device__ __forceinline__ int ld_acquire(const int *p)
 {
@@ -299,6 +303,7 @@ extern "C" int b200Ilu0Destroy(b200IluPlan p)
 {
   if (!p) return 0;
   cudaFree(p->d_ai); cudaFree(p->d_adiag); cudaFree(p->d_bi); cudaFree(p->d_bj); cudaFree(p->d_bdiag); cudaFree(p->d_ba);
+  cudaFree(p->d_segL); cudaFree(p->d_segU);
   cudaFree(p->d_orderL); cudaFree(p->d_orderU); cudaFree(p->d_metaL); cudaFree(p->d_metaU); cudaFree(p->d_flag); cudaFree(p->d_ticket); cudaFree(p->d_tmp);
   free(p->h_bi); free(p->h_bj); free(p->h_bdiag);
   free(p);
@@ -413,6 +418,23 @@ extern "C" int b200Ilu0Symbolic(b200Handle h, int n, const int *ai, const int *a
     free(mL); free(mU);
   }
 #undef UP
+  { /* segment schedule of the marching sweeps; GS lanes per row = next power of two >= the longest common triangular row,
+       so that a whole row is one pipelined chunk (27-point: 13 -> 16, 7-point: 3 -> 4) */
+    double avg = n ? (double)(nnz - n) / (2.0 * n) : 0.0;
+    int    GS  = 2;
+    while (GS < 32 && GS < avg + 0.5) GS <<= 1;
+    p->GS = GS;
+    const char *e1 = getenv("PETSCB200_ILU_SEG_MIN"), *e2 = getenv("PETSCB200_ILU_SEG_MAX");
+    const int   minlen = e1 && atoi(e1) > 0 ? atoi(e1) : 8, maxlen = e2 && atoi(e2) > 0 ? atoi(e2) : 1024;
+    int2 *sL = build_segments(n, bi, bdiag, bj, false, 32 / GS, minlen, maxlen, &p->nsegslotL, &p->nseglevL);
+    int2 *sU = build_segments(n, bi, bdiag, bj, true, 32 / GS, minlen, maxlen, &p->nsegslotU, &p->nseglevU);
+    B200_CUDA(cudaMalloc(&p->d_segL, sizeof(int2) * ((size_t)p->nsegslotL + 64)));
+    B200_CUDA(cudaMalloc(&p->d_segU, sizeof(int2) * ((size_t)p->nsegslotU + 64)));
+    B200_CUDA(cudaMemcpyAsync(p->d_segL, sL, sizeof(int2) * (size_t)p->nsegslotL, cudaMemcpyHostToDevice, h->stream));
+    B200_CUDA(cudaMemcpyAsync(p->d_segU, sU, sizeof(int2) * (size_t)p->nsegslotU, cudaMemcpyHostToDevice, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    free(sL); free(sU);
+  }
   B200_CUDA(cudaMalloc(&p->d_ba, sizeof(double) * ((size_t)nnz + 64)));
   B200_CUDA(cudaMalloc(&p->d_tmp, sizeof(double) * ((size_t)n + 64)));
   B200_CUDA(cudaMalloc(&p->d_flag, sizeof(int) * ((size_t)n + 64)));
@@ -572,6 +594,193 @@ __global__ void __launch_bounds__(ILU_TPB) ilu_sweep_pipe_kernel(int nslot, cons
   }
 }
 
+
+/* ------------------------------------------------------------------ segment-marching sweeps (round 2)
+   The level-scheduled kernels above pay one L2 round trip per dependency LEVEL (~2 us x 3572 levels on the 27-point 256^3
+   operator: latency, not bandwidth).  Here the unit of scheduling is a SEGMENT: a maximal run of consecutive rows in which
+   every row depends on its predecessor (an x-line of a lexicographically ordered grid; capped and floored in length).  A group
+   of G lanes MARCHES through its segment row after row:
+     * the dependency on the rows just computed (the chain that makes a line sequential) never leaves the SM: the last RING
+       results of the segment sit in a shared-memory ring, so the per-row critical path is ld.shared -> dmul -> dsub -> st.shared;
+     * dependencies on OTHER segments are read from global memory with the value-as-flag protocol (sentinel-filled output,
+       ld.relaxed.gpu poll), issued one row AHEAD of their use -- they were produced a whole segment-level earlier, so the
+       poll normally succeeds at once and its latency is off the critical path;
+     * the factor entries of a segment are one contiguous range (L rows ascending; U rows are stored descending, and the upper
+       sweep marches descending): they are streamed two rows ahead with an L2 prefetch further out.
+   Segments are scheduled in dependency-level order of the SEGMENT graph (766 levels instead of 1786 row levels for the 27-point
+   operator) round-robin over a co-resident grid; a group only ever waits for rows of segments that precede its own in that
+   order, so the sweep cannot deadlock.  Per row the sum is still accumulated strictly left to right with __dmul_rn/__dsub_rn:
+   bit-identical to MatSolve_SeqAIJ_NaturalOrdering (aijfact.c:2413-2457). */
+#define ILU_RING 32
+template <int G, bool UPPER>
+__global__ void __launch_bounds__(ILU_TPB) ilu_sweep_march_kernel(int nslot, const int2 *__restrict__ segs, const int *__restrict__ ext /* bi (lower) | bdiag (upper) */, const int *__restrict__ bj,
+                                                                  const double *__restrict__ ba, const double *__restrict__ rhs, double *out, int nnz_total)
+{
+  constexpr int     RPW = 32 / G;
+  __shared__ double ring_all[ILU_TPB / G][ILU_RING];
+  const int         gl = threadIdx.x % G, grp = (threadIdx.x & 31) / G;
+  const unsigned    gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+  double           *ring = ring_all[threadIdx.x / G];
+  const int         wid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), W = (int)((gridDim.x * blockDim.x) >> 5);
+  for (int64_t chunk = wid; chunk * RPW < nslot; chunk += W) {
+    const int64_t slot = chunk * RPW + grp;
+    const int2    sg   = slot < nslot ? __ldg(segs + slot) : make_int2(0, 0);
+    const int     f = sg.x, cnt = sg.y;
+    int           maxc = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
+    /* row r of the segment: i = f + r (lower) / f - r (upper); entries [ks, ke); lower ke = bi[i+1]; upper ke = bdiag[i] (diagonal) */
+    auto rowidx = [&](int r) { return UPPER ? f - r : f + r; };
+    /* pipeline registers: E = entries of row r+2, P = polled values of row r+1, C = row r */
+    int    ksC = 0, keC = 0, colC = 0, ksP = 0, keP = 0, colP = 0, ksE = 0, keE = 0, colE = 0;
+    double aC = 0, aP = 0, aE = 0, rhsC = 0, rhsP = 0, rhsE = 0, vC = 0, vP = 0;
+    bool   pollC = false, pollP = false;
+    auto load_extent = [&](int r, int &ks, int &ke, double &rh) {
+      if (r < cnt) {
+        const int i = rowidx(r);
+        if (!UPPER) { ks = __ldg(ext + i); ke = __ldg(ext + i + 1); }
+        else { ks = __ldg(ext + i + 1) + 1; ke = __ldg(ext + i); }
+        rh = rhs[i];
+      } else { ks = ke = 0; rh = 0.0; }
+    };
+    auto load_entries = [&](int ks, int ke, int &col, double &a) {
+      if (ks + gl < ke) { col = __ldg(bj + ks + gl); a = __ldg(ba + ks + gl); }
+      else { col = -1; a = 0.0; }
+    };
+    /* is column c of row i served by the ring (computed by this group within the last ILU_RING rows)? */
+    auto in_ring = [&](int c, int i) { return UPPER ? (c <= f && c - i <= ILU_RING) : (c >= f && i - c <= ILU_RING); };
+    auto issue_poll = [&](int r, int col, bool &poll, double &v) {
+      poll = false;
+      if (col >= 0 && !in_ring(col, rowidx(r))) {
+        poll = true;
+        v    = __longlong_as_double((long long)ld_relaxed_u64(out + col));
+      }
+    };
+    /* prologue */
+    load_extent(0, ksC, keC, rhsC);
+    load_entries(ksC, keC, colC, aC);
+    issue_poll(0, colC, pollC, vC);
+    load_extent(1, ksP, keP, rhsP);
+    load_entries(ksP, keP, colP, aP);
+    for (int r = 0; r < maxc; r++) {
+      /* stage E: extents + first G entries of row r+2; L2 prefetch ~8 rows further */
+      load_extent(r + 2, ksE, keE, rhsE);
+      load_entries(ksE, keE, colE, aE);
+      if (r + 2 < cnt) {
+        const int pf = min(ksE + 8 * (keE - ksE + (UPPER ? 1 : 0)) + gl, nnz_total - 1);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ba + pf));
+        if ((gl & 1) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(bj + pf));
+      }
+      /* stage P: polls of row r+1 (its columns arrived during the previous iteration) */
+      issue_poll(r + 1, colP, pollP, vP);
+      /* stage C: row r */
+      {
+        const bool valid = r < cnt;
+        const int  i     = rowidx(r);
+        double     sum   = rhsC;
+        int        nch   = valid ? (keC - ksC + G - 1) / G : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nch = max(nch, __shfl_xor_sync(0xffffffffu, nch, o));
+        for (int c = 0; c < nch; c++) {
+          const int  k0 = ksC + c * G, k = k0 + gl;
+          const bool act = valid && k < keC;
+          int        col = colC;
+          double     a = aC, v = vC;
+          bool       poll = pollC;
+          if (c > 0) { /* rows longer than G entries: later chunks are fetched on the fly */
+            col = act ? bj[k] : -1;
+            a   = act ? ba[k] : 0.0;
+            poll = false;
+            if (act && !in_ring(col, i)) { poll = true; v = __longlong_as_double((long long)ld_relaxed_u64(out + col)); }
+          }
+          double p;
+          if (act && !poll) p = ring[col & (ILU_RING - 1)];
+          /* warp-convergent re-poll of the values that were not there yet */
+          {
+            bool ready = !(act && poll) || ((unsigned long long)__double_as_longlong(v) != ILU_SENTINEL);
+            while (!__all_sync(0xffffffffu, ready)) {
+              if (!ready) {
+                v     = __longlong_as_double((long long)ld_relaxed_u64(out + col));
+                ready = ((unsigned long long)__double_as_longlong(v) != ILU_SENTINEL);
+              }
+            }
+          }
+          if (act && poll) p = v;
+          p = act ? __dmul_rn(a, p) : 0.0;
+          const int n_in = min(G, keC - k0);
+#pragma unroll
+          for (int l = 0; l < G; l++) {
+            const double pl = __shfl_sync(gmask, p, l, G);
+            if (valid && l < n_in) sum = __dsub_rn(sum, pl); /* strict left-to-right, FMA-free */
+          }
+        }
+        if (valid && gl == 0) {
+          if (UPPER) sum = __dmul_rn(sum, __ldg(ba + keC));
+          ring[i & (ILU_RING - 1)] = sum;
+          st_relaxed_f64(out + i, sum);
+        }
+      }
+      __syncwarp();
+      ksC = ksP; keC = keP; colC = colP; aC = aP; rhsC = rhsP; vC = vP; pollC = pollP;
+      ksP = ksE; keP = keE; colP = colE; aP = aE; rhsP = rhsE;
+    }
+  }
+}
+
+/* host: segments and their dependency levels.  A segment is a run of consecutive rows (in sweep direction) in which every row
+   has its predecessor among its columns, cut at maxlen and merged up to minlen.  level(seg) = 1 + max level of the segments
+   that hold its out-of-segment columns.  Output: int2 (first row, count) per slot in level order, each level padded to a
+   multiple of rpw slots with empty segments. */
+static int2 *build_segments(int n, const int *bi, const int *bdiag, const int *bj, bool upper, int rpw, int minlen, int maxlen, int *nslot_out, int *nlev_out)
+{
+  int *segof = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+  int *first = (int *)malloc(sizeof(int) * (size_t)(n + 1)), *count = (int *)malloc(sizeof(int) * (size_t)(n + 1)), *lev = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+  int  ns = 0;
+  /* pass 1: cut */
+  for (int q = 0; q < n; q++) {
+    const int i = upper ? n - 1 - q : q;
+    bool      chained = false;
+    if (q > 0) {
+      if (!upper) { const int ke = bi[i + 1]; chained = ke > bi[i] && bj[ke - 1] == i - 1; }              /* largest column of L(i,:) */
+      else { const int ks = bdiag[i + 1] + 1; chained = bdiag[i] > ks && bj[ks] == i + 1; }                /* smallest column of U(i,:) */
+    }
+    const bool newseg = q == 0 || (count[ns - 1] >= maxlen) || (!chained && count[ns - 1] >= minlen);
+    if (newseg) { first[ns] = i; count[ns] = 0; ns++; }
+    count[ns - 1]++;
+    segof[i] = ns - 1;
+  }
+  /* pass 2: levels (segments are numbered in sweep order, so every dependency has a smaller number) */
+  int nlev = 0;
+  for (int s2 = 0; s2 < ns; s2++) {
+    int l = 0;
+    for (int r = 0; r < count[s2]; r++) {
+      const int i = upper ? first[s2] - r : first[s2] + r;
+      const int ks = upper ? bdiag[i + 1] + 1 : bi[i], ke = upper ? bdiag[i] : bi[i + 1];
+      for (int k = ks; k < ke; k++) {
+        const int t = segof[bj[k]];
+        if (t != s2 && lev[t] + 1 > l) l = lev[t] + 1;
+      }
+    }
+    lev[s2] = l;
+    if (l + 1 > nlev) nlev = l + 1;
+  }
+  /* pass 3: counting sort by level, padded */
+  int64_t *cnt = (int64_t *)calloc((size_t)nlev + 2, sizeof(int64_t)), tot = 0;
+  for (int s2 = 0; s2 < ns; s2++) cnt[lev[s2] + 1]++;
+  int64_t *start = (int64_t *)malloc(sizeof(int64_t) * ((size_t)nlev + 1));
+  for (int l = 0; l < nlev; l++) {
+    start[l] = tot;
+    tot += (cnt[l + 1] + rpw - 1) / rpw * rpw;
+  }
+  int2 *out = (int2 *)malloc(sizeof(int2) * (size_t)(tot + 1));
+  for (int64_t k = 0; k < tot; k++) out[k] = make_int2(0, 0);
+  for (int s2 = 0; s2 < ns; s2++) out[start[lev[s2]]++] = make_int2(first[s2], count[s2]);
+  *nslot_out = (int)tot;
+  *nlev_out  = nlev;
+  free(segof); free(first); free(count); free(lev); free(cnt); free(start);
+  return out;
+}
+
 static int ilu_set_backoff(void)
 {
   static int done = 0;
@@ -584,6 +793,7 @@ static int ilu_set_backoff(void)
     if ((e = getenv("PETSCB200_ILU_LOOKAHEAD")) && atoi(e) > 0) g_ilu_lookahead = atoi(e);
     if ((e = getenv("PETSCB200_ILU_BATCH")) && atoi(e) > 0) g_ilu_batch = atoi(e);
     if ((e = getenv("PETSCB200_ILU_PIPE"))) g_ilu_pipe = atoi(e);
+    if ((e = getenv("PETSCB200_ILU_MARCH"))) g_ilu_march = atoi(e);
     done = 1;
   }
   return 0;
@@ -630,6 +840,34 @@ static int sweeps_launch(b200Handle h, b200IluPlan p, const double *b, double *x
   return 0;
 }
 
+template <int G>
+static int march_launch(b200Handle h, b200IluPlan p, const double *b, double *x)
+{
+  static int occ = 0;
+  if (!occ) {
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ilu_sweep_march_kernel<G, true>, ILU_TPB, 0));
+    if (occ < 1) occ = 1;
+  }
+  B200_CUDA(cudaMemsetAsync(p->d_tmp, 0xFF, sizeof(double) * (size_t)p->n, h->stream)); /* sentinel fill */
+  B200_CUDA(cudaMemsetAsync(x, 0xFF, sizeof(double) * (size_t)p->n, h->stream));
+  const int     rpc = (ILU_TPB / 32) * (32 / G); /* segments per CTA */
+  int           gL = (p->nsegslotL + rpc - 1) / rpc, gU = (p->nsegslotU + rpc - 1) / rpc;
+  if (gL > occ * h->num_sms) gL = occ * h->num_sms;
+  if (gU > occ * h->num_sms) gU = occ * h->num_sms;
+  if (gL < 1) gL = 1;
+  if (gU < 1) gU = 1;
+  const double *rhsL = b, *rhsU = p->d_tmp;
+  double       *outL = p->d_tmp, *outU = x;
+  int   nnz_total = (int)p->nnz;
+  void *argsL[] = {&p->nsegslotL, &p->d_segL, &p->d_bi, &p->d_bj, &p->d_ba, &rhsL, &outL, &nnz_total};
+  void *argsU[] = {&p->nsegslotU, &p->d_segU, &p->d_bdiag, &p->d_bj, &p->d_ba, &rhsU, &outU, &nnz_total};
+  /* co-resident persistent grid: cudaLaunchCooperativeKernel fails rather than deadlocks if the grid does not fit */
+  B200_CUDA(cudaLaunchCooperativeKernel((void *)ilu_sweep_march_kernel<G, false>, dim3(gL), dim3(ILU_TPB), argsL, 0, h->stream));
+  B200_CUDA(cudaLaunchCooperativeKernel((void *)ilu_sweep_march_kernel<G, true>, dim3(gU), dim3(ILU_TPB), argsU, 0, h->stream));
+  B200_LAUNCHED(2);
+  return 0;
+}
+
 extern "C" int b200Ilu0Solve(b200Handle h, b200IluPlan p, const double *d_b, double *d_x)
 {
   B200_CHECK(h && p, B200_ERR_ARG_NULL, "null argument");
@@ -637,6 +875,20 @@ extern "C" int b200Ilu0Solve(b200Handle h, b200IluPlan p, const double *d_b, dou
   if (p->n == 0) return 0;
   B200_CHECK(d_b && d_x && d_b != d_x, B200_ERR_ARG_WRONG, "b and x must be distinct non-null vectors");
   B200_CHECK(p->epoch < 2147483000, B200_ERR_SUP, "epoch counter exhausted");
+  if (ilu_set_backoff()) return B200_ERR_GPU;
+  {
+    int coop = 0;
+    B200_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    if (g_ilu_march && coop == 1) {
+      switch (p->GS) {
+      case 2: return march_launch<2>(h, p, d_b, d_x);
+      case 4: return march_launch<4>(h, p, d_b, d_x);
+      case 8: return march_launch<8>(h, p, d_b, d_x);
+      case 16: return march_launch<16>(h, p, d_b, d_x);
+      default: return march_launch<32>(h, p, d_b, d_x);
+      }
+    }
+  }
   switch (p->G) {
   case 2: return sweeps_launch<2>(h, p, d_b, d_x);
   case 4: return sweeps_launch<4>(h, p, d_b, d_x);
@@ -665,5 +917,17 @@ extern "C" int b200Ilu0GetInfo(b200IluPlan p, int *nlevL, int *nlevU, int64_t *n
   if (nlevL) *nlevL = p->nlevL;
   if (nlevU) *nlevU = p->nlevU;
   if (nnz) *nnz = p->nnz;
+  return 0;
+}
+
+/* the marching sweeps' schedule: lanes per row, segment slots (padded) and segment dependency levels of both sweeps */
+extern "C" int b200Ilu0GetSegmentInfo(b200IluPlan p, int *lanes, int *nslotL, int *nlevL, int *nslotU, int *nlevU)
+{
+  B200_CHECK(p, B200_ERR_ARG_NULL, "null plan");
+  if (lanes) *lanes = p->GS;
+  if (nslotL) *nslotL = p->nsegslotL;
+  if (nlevL) *nlevL = p->nseglevL;
+  if (nslotU) *nslotU = p->nsegslotU;
+  if (nlevU) *nlevU = p->nseglevU;
   return 0;
 }
