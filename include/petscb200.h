@@ -107,6 +107,10 @@ int b200CsrPlanSetSummation(b200CsrPlan plan, int tree);
    argument of b200CsrSpMV* is then ignored.  Costs 16 B/nnz of extra device memory. */
 int b200CsrPlanSetColumnBlocks(b200Handle h, b200CsrPlan plan, int nblocks);
 int b200CsrPlanPackValues(b200Handle h, b200CsrPlan plan, const double *d_val);
+/* chooses the number of column blocks from n, the mean row length and the measured mean column span of a row (0 = none:
+   stencil-like or L2-resident gathers); callers that use it must keep the packed values coherent (b200CsrPlanPackValues after
+   every value change) -- the PETSc plugin does so through the Mat's object state */
+int b200CsrPlanAutoColumnBlocks(b200Handle h, b200CsrPlan plan, int *nblocks_chosen);
 /* L2 hints: bit0 = stream val/col/rowptr as evict_first, bit1 = keep x as evict_last, bit2 = persisting access-policy
    window on x for the launch (default: 2 for one lane per row, else 3, plus bit2 when x fits the L2 set-aside) */
 int b200CsrPlanSetCacheHints(b200CsrPlan plan, int hints);
@@ -197,6 +201,24 @@ int b200Ilu0GetFactor(b200Handle h, b200IluPlan plan, int *h_bi, int *h_bj, int 
 int b200Ilu0GetInfo(b200IluPlan plan, int *nlevels_lower, int *nlevels_upper, int64_t *nnz);
 /* schedule of the segment-marching sweeps (ilu.cu): lanes per row, padded segment slots and segment dependency levels */
 int b200Ilu0GetSegmentInfo(b200IluPlan plan, int *lanes, int *nslot_lower, int *nlev_lower, int *nslot_upper, int *nlev_upper);
+
+/* ---- ICC(0): MatICCFactorSymbolic_SeqAIJ (levels 0, natural ordering; aijfact.c:2049-2094),
+        MatCholeskyFactorNumeric_SeqAIJ (aijfact.c:1701-1866), MatSolve_SeqSBAIJ_1_NaturalOrdering (sbaijfact2.c:2030-2065);
+        the reference's GPU path is cusparseXcsric02 + cusparseSpSV (aijcusparse.cu) ---- */
+typedef struct b200IccPlan_s *b200IccPlan;
+/* symbolic: the reference's factor layout (row i = strictly upper entries of A's row i, diagonal LAST), the order in which
+   the reference's linked lists merge finished rows into a row (it fixes the rounding of every entry), dependency levels, the
+   column view for the gather form of the forward sweep, segment schedules.  Host CSR pattern in. */
+int b200Icc0Symbolic(b200Handle h, int n, const int *h_ai, const int *h_aj, b200IccPlan *plan);
+int b200Icc0Destroy(b200IccPlan plan);
+/* numeric factorisation on the device from A's device values, contributors merged in the reference's order, FMA-free => factor
+   bit-identical to the CPU reference.  *zero_pivot_row = 0, or 1 + a row whose pivot failed dk > zeropivot*rowsum
+   (MatPivotCheck_pd, matimpl.h:813-833, would shift and refactor; here the factorisation is reported as failed) */
+int b200Icc0Numeric(b200Handle h, b200IccPlan plan, const double *d_aval, double zeropivot, int *zero_pivot_row);
+/* x = U^-1 D^-1 U^-T b, operation order of MatSolve_SeqSBAIJ_1_NaturalOrdering: bit-identical */
+int b200Icc0Solve(b200Handle h, b200IccPlan plan, const double *d_b, double *d_x);
+int b200Icc0GetFactor(b200Handle h, b200IccPlan plan, int *h_ui, int *h_uj, int *h_udiag, double *h_ua); /* tests: copies out */
+int b200Icc0GetInfo(b200IccPlan plan, int64_t *nz_factor, int *nlevels_numeric, int *nlev_forward, int *nlev_backward);
 
 /* ---- multi-GPU: NCCL replaces MPI in VecScatter/PetscSF (sfbasic.c:352-381, sfmpi.c:6-47) and MPIU_Allreduce
         (pvecimpl.h:101-171) ---- */

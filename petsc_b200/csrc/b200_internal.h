@@ -56,4 +56,9 @@ extern long long g_b200_launches;
 #define B200_LAUNCHED(n) (g_b200_launches += (n))
 #define B200_KERNEL_CHECK() B200_CUDA(cudaPeekAtLastError())
 
+
+/* segment-marching triangular sweeps (ilu.cu), shared by ILU(0) and ICC(0): see sweep_march_kernel for the modes */
+#include <vector_types.h>
+int2 *b200_build_segments(int n, int mode, const int *ext, const int *bj, int rpw, int minlen, int maxlen, int *nslot_out, int *nlev_out);
+int   b200_sweep_march(b200Handle h, int G, int mode, int nslot, const int2 *segs, const int *ext, const int *bj, const double *ba, const double *rhs, double *out, int64_t nnz, const double *dinv, double *out2);
 #endif

@@ -48,8 +48,11 @@ struct b200IluPlan_s {
 };
 
 #define ILU_TPB 256
-static int2 *build_segments(int n, const int *bi, const int *bdiag, const int *bj, bool upper, int rpw, int minlen, int maxlen, int *nslot_out, int *nlev_out);
-static int   g_ilu_march = 1; /* PETSCB200_ILU_MARCH=0 selects the level-scheduled pipe kernels */
+/* PETSCB200_ILU_MARCH=1 selects the segment-marching sweeps for ILU(0).  Measured on the B200 (profiles/round2_notes.md): bit-exact,
+   but 8.05 ms vs 7.09 ms per PCApply on the 27-point 256^3 operator and 5x slower on the 7-point one -- a marching line catches up
+   with its producer line and then pays an L2 round trip on every row, and the 32/G lines of a warp stall each other in lockstep.
+   The level-scheduled pipe kernels stay the default; the marching kernel serves the ICC(0) sweeps (modes 2 and 3). */
+static int   g_ilu_march = 0;
 
 __device__ __forceinline__ int ld_acquire(const int *p)
 {
@@ -426,8 +429,8 @@ extern "C" int b200Ilu0Symbolic(b200Handle h, int n, const int *ai, const int *a
     p->GS = GS;
     const char *e1 = getenv("PETSCB200_ILU_SEG_MIN"), *e2 = getenv("PETSCB200_ILU_SEG_MAX");
     const int   minlen = e1 && atoi(e1) > 0 ? atoi(e1) : 8, maxlen = e2 && atoi(e2) > 0 ? atoi(e2) : 1024;
-    int2 *sL = build_segments(n, bi, bdiag, bj, false, 32 / GS, minlen, maxlen, &p->nsegslotL, &p->nseglevL);
-    int2 *sU = build_segments(n, bi, bdiag, bj, true, 32 / GS, minlen, maxlen, &p->nsegslotU, &p->nseglevU);
+    int2 *sL = b200_build_segments(n, 0, bi, bj, 32 / GS, minlen, maxlen, &p->nsegslotL, &p->nseglevL);
+    int2 *sU = b200_build_segments(n, 1, bdiag, bj, 32 / GS, minlen, maxlen, &p->nsegslotU, &p->nseglevU);
     B200_CUDA(cudaMalloc(&p->d_segL, sizeof(int2) * ((size_t)p->nsegslotL + 64)));
     B200_CUDA(cudaMalloc(&p->d_segU, sizeof(int2) * ((size_t)p->nsegslotU + 64)));
     B200_CUDA(cudaMemcpyAsync(p->d_segL, sL, sizeof(int2) * (size_t)p->nsegslotL, cudaMemcpyHostToDevice, h->stream));
@@ -612,11 +615,17 @@ __global__ void __launch_bounds__(ILU_TPB) ilu_sweep_pipe_kernel(int nslot, cons
    order, so the sweep cannot deadlock.  Per row the sum is still accumulated strictly left to right with __dmul_rn/__dsub_rn:
    bit-identical to MatSolve_SeqAIJ_NaturalOrdering (aijfact.c:2413-2457). */
 #define ILU_RING 32
-template <int G, bool UPPER>
-__global__ void __launch_bounds__(ILU_TPB) ilu_sweep_march_kernel(int nslot, const int2 *__restrict__ segs, const int *__restrict__ ext /* bi (lower) | bdiag (upper) */, const int *__restrict__ bj,
-                                                                  const double *__restrict__ ba, const double *__restrict__ rhs, double *out, int nnz_total)
+/* MODE 0: ILU lower sweep   rows ascending,  entries [bi[i], bi[i+1]) ascending,            sum = b[i] - ...           (aijfact.c:2431-2440)
+   MODE 1: ILU upper sweep   rows descending, entries [bdiag[i+1]+1, bdiag[i]) ascending,    sum = (t[i] - ...) * ba[bdiag[i]]   (aijfact.c:2443-2451)
+   MODE 2: ICC forward       rows ascending over the COLUMN view (tptr/trow/tval),           y[c] = b[c] + sum tval*y[i];  out2[c] = y[c]*dinv[c]
+   MODE 3: ICC backward      rows descending, entries [ui[i], ui[i+1]-1) taken DESCENDING,   x[i] = xf[i] + sum ua*x[col]
+           (MatSolve_SeqSBAIJ_1_NaturalOrdering, sbaijfact2.c:2030-2065, as gathers; see icc.cu) */
+template <int G, int MODE>
+__global__ void __launch_bounds__(ILU_TPB) sweep_march_kernel(int nslot, const int2 *__restrict__ segs, const int *__restrict__ ext, const int *__restrict__ bj, const double *__restrict__ ba,
+                                                              const double *__restrict__ rhs, double *out, int nnz_total, const double *__restrict__ dinv, double *out2)
 {
-  constexpr int     RPW = 32 / G;
+  constexpr bool    DOWN = (MODE == 1 || MODE == 3), DESC = (MODE == 3), ADD = (MODE >= 2);
+  constexpr int     RPW  = 32 / G;
   __shared__ double ring_all[ILU_TPB / G][ILU_RING];
   const int         gl = threadIdx.x % G, grp = (threadIdx.x & 31) / G;
   const unsigned    gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
@@ -629,26 +638,27 @@ __global__ void __launch_bounds__(ILU_TPB) ilu_sweep_march_kernel(int nslot, con
     int           maxc = cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
-    /* row r of the segment: i = f + r (lower) / f - r (upper); entries [ks, ke); lower ke = bi[i+1]; upper ke = bdiag[i] (diagonal) */
-    auto rowidx = [&](int r) { return UPPER ? f - r : f + r; };
+    auto rowidx = [&](int r) { return DOWN ? f - r : f + r; };
     /* pipeline registers: E = entries of row r+2, P = polled values of row r+1, C = row r */
-    int    ksC = 0, keC = 0, colC = 0, ksP = 0, keP = 0, colP = 0, ksE = 0, keE = 0, colE = 0;
+    int    ksC = 0, keC = 0, colC = -1, ksP = 0, keP = 0, colP = -1, ksE = 0, keE = 0, colE = -1;
     double aC = 0, aP = 0, aE = 0, rhsC = 0, rhsP = 0, rhsE = 0, vC = 0, vP = 0;
     bool   pollC = false, pollP = false;
     auto load_extent = [&](int r, int &ks, int &ke, double &rh) {
       if (r < cnt) {
         const int i = rowidx(r);
-        if (!UPPER) { ks = __ldg(ext + i); ke = __ldg(ext + i + 1); }
-        else { ks = __ldg(ext + i + 1) + 1; ke = __ldg(ext + i); }
+        if (MODE == 1) { ks = __ldg(ext + i + 1) + 1; ke = __ldg(ext + i); }
+        else { ks = __ldg(ext + i); ke = __ldg(ext + i + 1) - (MODE == 3 ? 1 : 0); }
         rh = rhs[i];
       } else { ks = ke = 0; rh = 0.0; }
     };
+    auto entry_pos = [&](int ks, int ke, int c) { return DESC ? ke - 1 - (c * G + gl) : ks + c * G + gl; };
     auto load_entries = [&](int ks, int ke, int &col, double &a) {
-      if (ks + gl < ke) { col = __ldg(bj + ks + gl); a = __ldg(ba + ks + gl); }
+      const int k = entry_pos(ks, ke, 0);
+      if (k >= ks && k < ke) { col = __ldg(bj + k); a = __ldg(ba + k); }
       else { col = -1; a = 0.0; }
     };
     /* is column c of row i served by the ring (computed by this group within the last ILU_RING rows)? */
-    auto in_ring = [&](int c, int i) { return UPPER ? (c <= f && c - i <= ILU_RING) : (c >= f && i - c <= ILU_RING); };
+    auto in_ring = [&](int c, int i) { return DOWN ? (c <= f && c - i <= ILU_RING) : (c >= f && i - c <= ILU_RING); };
     auto issue_poll = [&](int r, int col, bool &poll, double &v) {
       poll = false;
       if (col >= 0 && !in_ring(col, rowidx(r))) {
@@ -663,11 +673,12 @@ __global__ void __launch_bounds__(ILU_TPB) ilu_sweep_march_kernel(int nslot, con
     load_extent(1, ksP, keP, rhsP);
     load_entries(ksP, keP, colP, aP);
     for (int r = 0; r < maxc; r++) {
-      /* stage E: extents + first G entries of row r+2; L2 prefetch ~8 rows further */
+      /* stage E: extents + first G entries of row r+2; L2 prefetch ~8 rows further along the march */
       load_extent(r + 2, ksE, keE, rhsE);
       load_entries(ksE, keE, colE, aE);
       if (r + 2 < cnt) {
-        const int pf = min(ksE + 8 * (keE - ksE + (UPPER ? 1 : 0)) + gl, nnz_total - 1);
+        const int len = keE - ksE + (MODE == 1 || MODE == 3 ? 1 : 0);
+        const int pf  = DESC ? max(ksE - 8 * len - gl, 0) : min(ksE + 8 * len + gl, nnz_total - 1);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(ba + pf));
         if ((gl & 1) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(bj + pf));
       }
@@ -682,21 +693,20 @@ __global__ void __launch_bounds__(ILU_TPB) ilu_sweep_march_kernel(int nslot, con
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nch = max(nch, __shfl_xor_sync(0xffffffffu, nch, o));
         for (int c = 0; c < nch; c++) {
-          const int  k0 = ksC + c * G, k = k0 + gl;
-          const bool act = valid && k < keC;
+          const int  k   = entry_pos(ksC, keC, c);
+          const bool act = valid && k >= ksC && k < keC;
           int        col = colC;
           double     a = aC, v = vC;
           bool       poll = pollC;
           if (c > 0) { /* rows longer than G entries: later chunks are fetched on the fly */
-            col = act ? bj[k] : -1;
-            a   = act ? ba[k] : 0.0;
+            col  = act ? bj[k] : -1;
+            a    = act ? ba[k] : 0.0;
             poll = false;
             if (act && !in_ring(col, i)) { poll = true; v = __longlong_as_double((long long)ld_relaxed_u64(out + col)); }
           }
-          double p;
+          double p = 0.0;
           if (act && !poll) p = ring[col & (ILU_RING - 1)];
-          /* warp-convergent re-poll of the values that were not there yet */
-          {
+          { /* warp-convergent re-poll of the values that were not there yet */
             bool ready = !(act && poll) || ((unsigned long long)__double_as_longlong(v) != ILU_SENTINEL);
             while (!__all_sync(0xffffffffu, ready)) {
               if (!ready) {
@@ -707,17 +717,18 @@ __global__ void __launch_bounds__(ILU_TPB) ilu_sweep_march_kernel(int nslot, con
           }
           if (act && poll) p = v;
           p = act ? __dmul_rn(a, p) : 0.0;
-          const int n_in = min(G, keC - k0);
+          const int n_in = min(G, keC - ksC - c * G);
 #pragma unroll
           for (int l = 0; l < G; l++) {
             const double pl = __shfl_sync(gmask, p, l, G);
-            if (valid && l < n_in) sum = __dsub_rn(sum, pl); /* strict left-to-right, FMA-free */
+            if (valid && l < n_in) sum = ADD ? __dadd_rn(sum, pl) : __dsub_rn(sum, pl); /* strict order, FMA-free */
           }
         }
         if (valid && gl == 0) {
-          if (UPPER) sum = __dmul_rn(sum, __ldg(ba + keC));
+          if (MODE == 1) sum = __dmul_rn(sum, __ldg(ba + keC));
           ring[i & (ILU_RING - 1)] = sum;
           st_relaxed_f64(out + i, sum);
+          if (MODE == 2) out2[i] = __dmul_rn(sum, __ldg(dinv + i));
         }
       }
       __syncwarp();
@@ -727,22 +738,68 @@ __global__ void __launch_bounds__(ILU_TPB) ilu_sweep_march_kernel(int nslot, con
   }
 }
 
+/* launch of one marching sweep (shared with icc.cu): co-resident persistent grid; cudaLaunchCooperativeKernel fails rather than
+   deadlocks if the grid does not fit */
+template <int G, int MODE>
+static int sweep_march_launch(b200Handle h, int nslot, const int2 *segs, const int *ext, const int *bj, const double *ba, const double *rhs, double *out, int64_t nnz, const double *dinv, double *out2)
+{
+  static int occ = 0;
+  if (!occ) {
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_march_kernel<G, MODE>, ILU_TPB, 0));
+    if (occ < 1) occ = 1;
+  }
+  const int rpc = (ILU_TPB / 32) * (32 / G); /* segments per CTA */
+  int       g   = (nslot + rpc - 1) / rpc;
+  if (g > occ * h->num_sms) g = occ * h->num_sms;
+  if (g < 1) g = 1;
+  int   nnz_total = (int)nnz;
+  void *args[]    = {&nslot, &segs, &ext, &bj, &ba, &rhs, &out, &nnz_total, &dinv, &out2};
+  B200_CUDA(cudaLaunchCooperativeKernel((void *)sweep_march_kernel<G, MODE>, dim3(g), dim3(ILU_TPB), args, 0, h->stream));
+  B200_LAUNCHED(1);
+  return 0;
+}
+int b200_sweep_march(b200Handle h, int G, int mode, int nslot, const int2 *segs, const int *ext, const int *bj, const double *ba, const double *rhs, double *out, int64_t nnz, const double *dinv, double *out2)
+{
+#define SM_CASE(g) \
+  case g: \
+    switch (mode) { \
+    case 0: return sweep_march_launch<g, 0>(h, nslot, segs, ext, bj, ba, rhs, out, nnz, dinv, out2); \
+    case 1: return sweep_march_launch<g, 1>(h, nslot, segs, ext, bj, ba, rhs, out, nnz, dinv, out2); \
+    case 2: return sweep_march_launch<g, 2>(h, nslot, segs, ext, bj, ba, rhs, out, nnz, dinv, out2); \
+    default: return sweep_march_launch<g, 3>(h, nslot, segs, ext, bj, ba, rhs, out, nnz, dinv, out2); \
+    }
+  switch (G) {
+    SM_CASE(2)
+    SM_CASE(4)
+    SM_CASE(8)
+    SM_CASE(16)
+  default:
+    SM_CASE(32)
+  }
+#undef SM_CASE
+}
+
 /* host: segments and their dependency levels.  A segment is a run of consecutive rows (in sweep direction) in which every row
    has its predecessor among its columns, cut at maxlen and merged up to minlen.  level(seg) = 1 + max level of the segments
    that hold its out-of-segment columns.  Output: int2 (first row, count) per slot in level order, each level padded to a
    multiple of rpw slots with empty segments. */
-static int2 *build_segments(int n, const int *bi, const int *bdiag, const int *bj, bool upper, int rpw, int minlen, int maxlen, int *nslot_out, int *nlev_out)
+int2 *b200_build_segments(int n, int mode, const int *ext, const int *bj, int rpw, int minlen, int maxlen, int *nslot_out, int *nlev_out)
 {
+  /* row extents per sweep mode (see sweep_march_kernel) */
+  const bool down = (mode == 1 || mode == 3);
+#define EXT_KS(i) (mode == 1 ? ext[(i) + 1] + 1 : ext[i])
+#define EXT_KE(i) (mode == 1 ? ext[i] : ext[(i) + 1] - (mode == 3 ? 1 : 0))
   int *segof = (int *)malloc(sizeof(int) * (size_t)(n + 1));
   int *first = (int *)malloc(sizeof(int) * (size_t)(n + 1)), *count = (int *)malloc(sizeof(int) * (size_t)(n + 1)), *lev = (int *)malloc(sizeof(int) * (size_t)(n + 1));
   int  ns = 0;
-  /* pass 1: cut */
+  /* pass 1: cut -- a row continues the segment when its predecessor in sweep direction is among its columns (columns are sorted:
+     for a lower-type row that is the LAST entry, for an upper-type row the FIRST) */
   for (int q = 0; q < n; q++) {
-    const int i = upper ? n - 1 - q : q;
+    const int i = down ? n - 1 - q : q;
     bool      chained = false;
     if (q > 0) {
-      if (!upper) { const int ke = bi[i + 1]; chained = ke > bi[i] && bj[ke - 1] == i - 1; }              /* largest column of L(i,:) */
-      else { const int ks = bdiag[i + 1] + 1; chained = bdiag[i] > ks && bj[ks] == i + 1; }                /* smallest column of U(i,:) */
+      const int ks = EXT_KS(i), ke = EXT_KE(i);
+      if (ke > ks) chained = down ? (bj[ks] == i + 1) : (bj[ke - 1] == i - 1);
     }
     const bool newseg = q == 0 || (count[ns - 1] >= maxlen) || (!chained && count[ns - 1] >= minlen);
     if (newseg) { first[ns] = i; count[ns] = 0; ns++; }
@@ -754,8 +811,8 @@ static int2 *build_segments(int n, const int *bi, const int *bdiag, const int *b
   for (int s2 = 0; s2 < ns; s2++) {
     int l = 0;
     for (int r = 0; r < count[s2]; r++) {
-      const int i = upper ? first[s2] - r : first[s2] + r;
-      const int ks = upper ? bdiag[i + 1] + 1 : bi[i], ke = upper ? bdiag[i] : bi[i + 1];
+      const int i = down ? first[s2] - r : first[s2] + r;
+      const int ks = EXT_KS(i), ke = EXT_KE(i);
       for (int k = ks; k < ke; k++) {
         const int t = segof[bj[k]];
         if (t != s2 && lev[t] + 1 > l) l = lev[t] + 1;
@@ -764,6 +821,8 @@ static int2 *build_segments(int n, const int *bi, const int *bdiag, const int *b
     lev[s2] = l;
     if (l + 1 > nlev) nlev = l + 1;
   }
+#undef EXT_KS
+#undef EXT_KE
   /* pass 3: counting sort by level, padded */
   int64_t *cnt = (int64_t *)calloc((size_t)nlev + 2, sizeof(int64_t)), tot = 0;
   for (int s2 = 0; s2 < ns; s2++) cnt[lev[s2] + 1]++;
@@ -840,32 +899,13 @@ static int sweeps_launch(b200Handle h, b200IluPlan p, const double *b, double *x
   return 0;
 }
 
-template <int G>
 static int march_launch(b200Handle h, b200IluPlan p, const double *b, double *x)
 {
-  static int occ = 0;
-  if (!occ) {
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ilu_sweep_march_kernel<G, true>, ILU_TPB, 0));
-    if (occ < 1) occ = 1;
-  }
   B200_CUDA(cudaMemsetAsync(p->d_tmp, 0xFF, sizeof(double) * (size_t)p->n, h->stream)); /* sentinel fill */
   B200_CUDA(cudaMemsetAsync(x, 0xFF, sizeof(double) * (size_t)p->n, h->stream));
-  const int     rpc = (ILU_TPB / 32) * (32 / G); /* segments per CTA */
-  int           gL = (p->nsegslotL + rpc - 1) / rpc, gU = (p->nsegslotU + rpc - 1) / rpc;
-  if (gL > occ * h->num_sms) gL = occ * h->num_sms;
-  if (gU > occ * h->num_sms) gU = occ * h->num_sms;
-  if (gL < 1) gL = 1;
-  if (gU < 1) gU = 1;
-  const double *rhsL = b, *rhsU = p->d_tmp;
-  double       *outL = p->d_tmp, *outU = x;
-  int   nnz_total = (int)p->nnz;
-  void *argsL[] = {&p->nsegslotL, &p->d_segL, &p->d_bi, &p->d_bj, &p->d_ba, &rhsL, &outL, &nnz_total};
-  void *argsU[] = {&p->nsegslotU, &p->d_segU, &p->d_bdiag, &p->d_bj, &p->d_ba, &rhsU, &outU, &nnz_total};
-  /* co-resident persistent grid: cudaLaunchCooperativeKernel fails rather than deadlocks if the grid does not fit */
-  B200_CUDA(cudaLaunchCooperativeKernel((void *)ilu_sweep_march_kernel<G, false>, dim3(gL), dim3(ILU_TPB), argsL, 0, h->stream));
-  B200_CUDA(cudaLaunchCooperativeKernel((void *)ilu_sweep_march_kernel<G, true>, dim3(gU), dim3(ILU_TPB), argsU, 0, h->stream));
-  B200_LAUNCHED(2);
-  return 0;
+  int rc = b200_sweep_march(h, p->GS, 0, p->nsegslotL, p->d_segL, p->d_bi, p->d_bj, p->d_ba, b, p->d_tmp, p->nnz, NULL, NULL);
+  if (rc) return rc;
+  return b200_sweep_march(h, p->GS, 1, p->nsegslotU, p->d_segU, p->d_bdiag, p->d_bj, p->d_ba, p->d_tmp, x, p->nnz, NULL, NULL);
 }
 
 extern "C" int b200Ilu0Solve(b200Handle h, b200IluPlan p, const double *d_b, double *d_x)
@@ -879,15 +919,7 @@ extern "C" int b200Ilu0Solve(b200Handle h, b200IluPlan p, const double *d_b, dou
   {
     int coop = 0;
     B200_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
-    if (g_ilu_march && coop == 1) {
-      switch (p->GS) {
-      case 2: return march_launch<2>(h, p, d_b, d_x);
-      case 4: return march_launch<4>(h, p, d_b, d_x);
-      case 8: return march_launch<8>(h, p, d_b, d_x);
-      case 16: return march_launch<16>(h, p, d_b, d_x);
-      default: return march_launch<32>(h, p, d_b, d_x);
-      }
-    }
+    if (g_ilu_march && coop == 1) return march_launch(h, p, d_b, d_x);
   }
   switch (p->G) {
   case 2: return sweeps_launch<2>(h, p, d_b, d_x);

@@ -641,6 +641,51 @@ done:
 #undef BLK_CUDA
 }
 
+/* Automatic choice of the column blocks: blocking pays when the gathered vector does not stay in the L2 next
+   to the streamed matrix (n*8 well above ~40 MB of the 126 MB L2), the rows are long enough to amortise the extra row-pointer /
+   y traffic of every pass (>= 16 entries), and the columns of a row are SCATTERED (mean column span of a row, measured by a
+   reduction kernel, beyond the L2 window) -- stencil-like matrices gather from a narrow window whatever n is.  Measured on
+   random CSR n = 10 M: 2 blocks already bring d = 32 from 5.1 to 3.3 ms and d = 128 from 20.4 to 11.7 ms
+   (profiles/round1_configs_5_blocks_pipecg.json); more blocks only add passes.  *nblocks_out = 0 when blocking is not used. */
+__global__ void csr_span_kernel(int m, const int *__restrict__ rowptr, const int *__restrict__ colidx, double *sum)
+{
+  const int stride = gridDim.x * blockDim.x;
+  double    s      = 0.0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
+    const int k0 = rowptr[r], k1 = rowptr[r + 1];
+    if (k1 > k0) s += (double)(colidx[k1 - 1] - colidx[k0]); /* columns are sorted within a row */
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(sum, s);
+}
+
+extern "C" int b200CsrPlanAutoColumnBlocks(b200Handle h, b200CsrPlan p, int *nblocks_out)
+{
+  B200_CHECK(h && p, B200_ERR_ARG_NULL, "null argument");
+  if (nblocks_out) *nblocks_out = 0;
+  const double  avg     = p->m ? (double)p->nnz / p->m : 0.0;
+  const int64_t xbytes  = (int64_t)p->n * 8, window = 40LL << 20;
+  if (p->m == 0 || p->nnz == 0 || avg < 16.0 || xbytes <= (48LL << 20)) return b200CsrPlanSetColumnBlocks(h, p, 0);
+  double *d_sum = NULL, span = 0.0;
+  B200_CUDA(cudaMalloc(&d_sum, sizeof(double)));
+  B200_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), h->stream));
+  int g = (p->m + 255) / 256;
+  if (g > h->num_sms * 8) g = h->num_sms * 8;
+  csr_span_kernel<<<g, 256, 0, h->stream>>>(p->m, p->d_rowptr, p->d_colidx, d_sum);
+  B200_LAUNCHED(1);
+  B200_CUDA(cudaMemcpyAsync(&span, d_sum, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(d_sum);
+  span = span / p->m * 8.0; /* mean bytes of x spanned by one row */
+  if (span <= (double)window) return b200CsrPlanSetColumnBlocks(h, p, 0);
+  int nb = (int)((xbytes + window - 1) / window);
+  if (nb < 2) nb = 2;
+  if (nb > SPMV_MAX_BLOCKS) nb = SPMV_MAX_BLOCKS;
+  int rc = b200CsrPlanSetColumnBlocks(h, p, nb);
+  if (!rc && nblocks_out) *nblocks_out = nb;
+  return rc;
+}
+
 /* gathers the values into block order; call after every change of the matrix values (the blocked SpMV uses this copy) */
 extern "C" int b200CsrPlanPackValues(b200Handle h, b200CsrPlan p, const double *d_val)
 {

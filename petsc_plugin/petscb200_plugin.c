@@ -8,7 +8,7 @@
  *   VecRegister            "seqb200", "b200"                         (src/vec/vec/interface/vecreg.c:252)
  *   MatRegisterRootName    "aijb200" -> "seqaijb200" / "mpiaijb200"  (src/mat/interface/matreg.c:328)
  *   MatRegister            "seqaijb200"                              (matreg.c:293)
- *   MatSolverTypeRegister  "b200" for seqaijb200, MAT_FACTOR_ILU     (src/mat/interface/matrix.c:4720)
+ *   MatSolverTypeRegister  "b200" for seqaijb200, MAT_FACTOR_ILU and MAT_FACTOR_ICC   (src/mat/interface/matrix.c:4720)
  *   PCRegister             "jacobib200" and (unless -b200_keep_pcjacobi) "jacobi": the reference's PCJACOBI sub-classed with a
  *                          fused ops->applyBA (src/ksp/pc/interface/pcregis.c, precon.c:810-865)
  *   VecRegister            "mpib200";  MatRegister "mpiaijb200": the row-partitioned types over NCCL ranks (one process per GPU)
@@ -919,9 +919,14 @@ static PetscErrorCode PB_MatFreeDevice(Mat_B200 *m)
    MatMult_SeqAIJ's left-to-right row sums bit for bit (default 0 = chosen from the row-length statistics) */
 static PetscErrorCode PB_PlanSetFromOptions(Mat A, b200CsrPlan plan)
 {
-  PetscInt  lanes = 0;
+  PetscInt  lanes = 0, nb = -1;
   PetscBool set   = PETSC_FALSE;
   PetscFunctionBegin;
+  /* -mat_b200_spmv_column_blocks <n>: column-blocked SpMV passes for gathers that exceed the L2 (0 = off; default -1 = chosen
+     from n, the row length and the measured column span: only scattered matrices with n*8 beyond the L2 are blocked) */
+  PetscCall(PetscOptionsGetInt(((PetscObject)A)->options, ((PetscObject)A)->prefix, "-mat_b200_spmv_column_blocks", &nb, NULL));
+  if (nb < 0) PetscCallB200(b200CsrPlanAutoColumnBlocks(PB_h, plan, NULL));
+  else PetscCallB200(b200CsrPlanSetColumnBlocks(PB_h, plan, (int)nb));
   PetscCall(PetscOptionsGetInt(((PetscObject)A)->options, ((PetscObject)A)->prefix, "-mat_b200_spmv_lanes", &lanes, &set));
   if (set) PetscCallB200(b200CsrPlanSetLayout(plan, (int)lanes, 0, 0, 0));
   {
@@ -959,6 +964,7 @@ static PetscErrorCode PB_MatSyncEx(Mat A, PetscBool need_assembled)
     PetscCallB200(b200MemcpyHtoD(PB_h, m->d_a, a->a, sizeof(double) * nz));
     PetscCallB200(b200CsrPlanCreate(PB_h, (int)nr, (int)A->cmap->n, (int64_t)nz, m->d_i, m->d_j, &m->plan));
     PetscCall(PB_PlanSetFromOptions(A, m->plan));
+    PetscCallB200(b200CsrPlanPackValues(PB_h, m->plan, m->d_a)); /* no-op unless the plan is column-blocked */
     PetscCall(PetscLogCpuToGpu((PetscLogDouble)(sizeof(int) * ((size_t)nr + 1 + nz) + sizeof(double) * nz)));
     if (a->compressedrow.use && a->compressedrow.nrows > 0) { /* MatCheckCompressedRow found mostly empty rows (aij.c:1141) */
       const size_t ncr = (size_t)a->compressedrow.nrows;
@@ -973,6 +979,7 @@ static PetscErrorCode PB_MatSyncEx(Mat A, PetscBool need_assembled)
     m->valid        = PETSC_TRUE;
   } else if (m->valstate != st) {
     PetscCallB200(b200MemcpyHtoD(PB_h, m->d_a, a->a, sizeof(double) * nz));
+    PetscCallB200(b200CsrPlanPackValues(PB_h, m->plan, m->d_a));
     PetscCall(PetscLogCpuToGpu((PetscLogDouble)(sizeof(double) * nz)));
     m->valstate = st;
   }
@@ -993,6 +1000,7 @@ static PetscErrorCode PB_MatAdoptDevice(Mat A, int *d_i, int *d_j, double *d_a)
   m->d_a = d_a;
   PetscCallB200(b200CsrPlanCreate(PB_h, (int)A->rmap->n, (int)A->cmap->n, (int64_t)a->nz, m->d_i, m->d_j, &m->plan));
   PetscCall(PB_PlanSetFromOptions(A, m->plan));
+  PetscCallB200(b200CsrPlanPackValues(PB_h, m->plan, m->d_a));
   if (a->compressedrow.use && a->compressedrow.nrows > 0) {
     const size_t ncr = (size_t)a->compressedrow.nrows;
     PetscCallB200(b200Malloc(PB_h, (void **)&m->d_cr_i, sizeof(int) * (ncr + 1)));
@@ -1204,6 +1212,7 @@ static PetscErrorCode MatSetValuesCOO_SeqAIJB200(Mat A, const PetscScalar v[], I
   }
   PetscCall(PB_MatSyncEx(A, PETSC_FALSE)); /* MatSetValuesCOO() assembles AFTER this method (gcreate.c MatSetValuesCOO) */
   PetscCallB200(b200CooSetValues(PB_h, m->coo, v, imode == INSERT_VALUES, m->d_a));
+  PetscCallB200(b200CsrPlanPackValues(PB_h, m->plan, m->d_a));
   PetscCallB200(b200MemcpyDtoH(PB_h, a->a, m->d_a, sizeof(double) * (size_t)a->nz)); /* host master copy follows */
   PetscCall(PetscObjectStateIncrease((PetscObject)A));
   PetscCall(PetscObjectStateGet((PetscObject)A, &st));
@@ -1313,6 +1322,7 @@ PETSC_EXTERN PetscErrorCode MatCreateSeqAIJB200WithDeviceArrays(PetscInt m, Pets
 /* ================================================================== MatSolverType "b200": ILU(0) on the device */
 typedef struct {
   b200IluPlan plan;
+  b200IccPlan icc;        /* MAT_FACTOR_ICC */
   double     *d_aval_tmp; /* when A is a plain seqaij (no device mirror) */
   PetscInt    n;
   double      nz;
@@ -1324,6 +1334,7 @@ static PetscErrorCode MatDestroy_FactorB200(Mat F)
   PetscFunctionBegin;
   if (f) {
     if (f->plan) PetscCallB200(b200Ilu0Destroy(f->plan));
+    if (f->icc) PetscCallB200(b200Icc0Destroy(f->icc));
     PetscCallB200(b200Free(PB_h, f->d_aval_tmp));
     PetscCall(PetscFree(F->data));
   }
@@ -1404,6 +1415,84 @@ static PetscErrorCode MatILUFactorSymbolic_FactorB200(Mat F, Mat A, IS isrow, IS
   F->info.fill_ratio_needed    = 1.0;
   PetscFunctionReturn(PETSC_SUCCESS);
 }
+/* ---- ICC(0): MatICCFactorSymbolic_SeqAIJ / MatCholeskyFactorNumeric_SeqAIJ / MatSolve_SeqSBAIJ_1_NaturalOrdering on the device
+   (PCICC is PETSc's default PC for a sequential matrix flagged symmetric, e.g. ex2) */
+static PetscErrorCode MatSolve_IccB200(Mat F, Vec b, Vec x)
+{
+  MatFactor_B200 *f = (MatFactor_B200 *)F->data;
+  const double   *db;
+  double         *dx;
+  PetscFunctionBegin;
+  if (!PB_IsB200(b) || !PB_IsB200(x)) { /* host vectors: stage through temporaries of the device type */
+    Vec tb, tx;
+    PetscCall(VecCreateSeq(PETSC_COMM_SELF, F->rmap->n, &tb));
+    PetscCall(VecSetType(tb, VECSEQB200));
+    PetscCall(VecDuplicate(tb, &tx));
+    PetscCall(VecCopy(b, tb));
+    PetscCall(MatSolve_IccB200(F, tb, tx));
+    PetscCall(VecCopy(tx, x));
+    PetscCall(VecDestroy(&tb));
+    PetscCall(VecDestroy(&tx));
+    PetscFunctionReturn(PETSC_SUCCESS);
+  }
+  PetscCall(PB_VecRead(b, &db));
+  PetscCall(PB_VecWrite(x, &dx));
+  PetscCall(PB_LogTimeBegin());
+  PetscCallB200(b200Icc0Solve(PB_h, f->icc, db, dx)); /* sbaijfact2.c:2030-2065 */
+  PetscCall(PB_LogTimeEnd());
+  PetscCall(PB_LogFlops(4.0 * f->nz - 3.0 * F->rmap->n));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode MatCholeskyFactorNumeric_FactorB200(Mat F, Mat A, const MatFactorInfo *info)
+{
+  MatFactor_B200 *f = (MatFactor_B200 *)F->data;
+  const double   *d_a;
+  int             bad = 0;
+  PetscFunctionBegin;
+  if (A->ops->mult == MatMult_SeqAIJB200) {
+    PetscCall(PB_MatSync(A));
+    d_a = ((Mat_B200 *)A->spptr)->d_a;
+  } else {
+    Mat_SeqAIJ *a = (Mat_SeqAIJ *)A->data;
+    if (!f->d_aval_tmp) PetscCallB200(b200Malloc(PB_h, (void **)&f->d_aval_tmp, sizeof(double) * ((size_t)a->nz + 1)));
+    PetscCallB200(b200MemcpyHtoD(PB_h, f->d_aval_tmp, a->a, sizeof(double) * (size_t)a->nz));
+    d_a = f->d_aval_tmp;
+  }
+  PetscCallB200(b200Icc0Numeric(PB_h, f->icc, d_a, info->zeropivot, &bad));
+  if (bad) {
+    /* the reference's MatPivotCheck_pd would shift the diagonal and refactor (matimpl.h:813-833); this solver reports the
+       indefinite pivot instead -- choose -pc_factor_mat_solver_type petsc for such matrices */
+    PetscCheck(!F->erroriffailure, PetscObjectComm((PetscObject)A), PETSC_ERR_MAT_CH_ZRPVT, "Zero or negative pivot in ICC(0) at row %d (MatSolverType b200 does not shift)", bad - 1);
+    F->factorerrortype = MAT_FACTOR_NUMERIC_ZEROPIVOT;
+    PetscCall(PetscInfo(F, "Zero or negative pivot in ICC(0) at row %d: factorisation flagged as failed\n", bad - 1));
+  }
+  F->ops->solve          = MatSolve_IccB200;
+  F->ops->solvetranspose = MatSolve_IccB200; /* symmetric factor */
+  F->assembled           = PETSC_TRUE;
+  F->preallocated        = PETSC_TRUE;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode MatICCFactorSymbolic_FactorB200(Mat F, Mat A, IS perm, const MatFactorInfo *info)
+{
+  MatFactor_B200 *f = (MatFactor_B200 *)F->data;
+  Mat_SeqAIJ     *a = (Mat_SeqAIJ *)A->data;
+  PetscBool       id = PETSC_TRUE;
+  int64_t         nzu = 0;
+  PetscFunctionBegin;
+  PetscCheck(info->levels == 0, PETSC_COMM_SELF, PETSC_ERR_SUP, "MatSolverType b200 implements ICC(0) only (got %g levels)", (double)info->levels);
+  if (perm) PetscCall(ISIdentity(perm, &id));
+  PetscCheck(id, PETSC_COMM_SELF, PETSC_ERR_SUP, "MatSolverType b200 requires the natural ordering (-pc_factor_mat_ordering_type natural)");
+  PetscCheck(A->rmap->n == A->cmap->n, PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG, "Must be square matrix, rows %" PetscInt_FMT " columns %" PetscInt_FMT, A->rmap->n, A->cmap->n); /* aijfact.c:2064 */
+  if (f->icc) PetscCallB200(b200Icc0Destroy(f->icc));
+  f->icc = NULL;
+  PetscCallB200(b200Icc0Symbolic(PB_h, (int)A->rmap->n, a->i, a->j, &f->icc));
+  PetscCallB200(b200Icc0GetInfo(f->icc, &nzu, NULL, NULL, NULL));
+  f->nz                          = (double)nzu;
+  F->ops->choleskyfactornumeric  = MatCholeskyFactorNumeric_FactorB200;
+  F->info.fill_ratio_given       = info->fill;
+  F->info.fill_ratio_needed      = 1.0;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
 static PetscErrorCode MatGetInfo_FactorB200(Mat F, MatInfoType flag, MatInfo *info)
 {
   MatFactor_B200 *f = (MatFactor_B200 *)F->data;
@@ -1429,7 +1518,7 @@ static PetscErrorCode MatGetFactor_seqaijb200_b200(Mat A, MatFactorType ftype, M
   MatFactor_B200 *f;
   PetscInt        n = A->rmap->n;
   PetscFunctionBegin;
-  PetscCheck(ftype == MAT_FACTOR_ILU, PetscObjectComm((PetscObject)A), PETSC_ERR_SUP, "MatSolverType b200 provides MAT_FACTOR_ILU only");
+  PetscCheck(ftype == MAT_FACTOR_ILU || ftype == MAT_FACTOR_ICC, PetscObjectComm((PetscObject)A), PETSC_ERR_SUP, "MatSolverType b200 provides MAT_FACTOR_ILU and MAT_FACTOR_ICC");
   PetscCall(PB_Init());
   PetscCall(MatCreate(PetscObjectComm((PetscObject)A), F));
   PetscCall(MatSetSizes(*F, n, n, n, n));
@@ -1442,6 +1531,7 @@ static PetscErrorCode MatGetFactor_seqaijb200_b200(Mat A, MatFactorType ftype, M
   (*F)->factortype              = ftype;
   (*F)->canuseordering          = PETSC_FALSE; /* natural ordering: PCSetUp_ILU then skips MatGetOrdering (ilu.c:127) */
   (*F)->ops->ilufactorsymbolic  = MatILUFactorSymbolic_FactorB200;
+  (*F)->ops->iccfactorsymbolic  = MatICCFactorSymbolic_FactorB200;
   (*F)->ops->destroy            = MatDestroy_FactorB200;
   (*F)->ops->getinfo            = MatGetInfo_FactorB200;
   (*F)->preallocated            = PETSC_TRUE;
@@ -1888,6 +1978,8 @@ PETSC_EXTERN PetscErrorCode PetscDLLibraryRegister_petscb200plugin(void)
   PetscCall(MatRegister(MATMPIAIJB200, MatCreate_MPIAIJB200));
   PetscCall(MatSolverTypeRegister(MATSOLVERB200, MATSEQAIJB200, MAT_FACTOR_ILU, MatGetFactor_seqaijb200_b200));
   PetscCall(MatSolverTypeRegister(MATSOLVERB200, MATSEQAIJ, MAT_FACTOR_ILU, MatGetFactor_seqaijb200_b200));
+  PetscCall(MatSolverTypeRegister(MATSOLVERB200, MATSEQAIJB200, MAT_FACTOR_ICC, MatGetFactor_seqaijb200_b200));
+  PetscCall(MatSolverTypeRegister(MATSOLVERB200, MATSEQAIJ, MAT_FACTOR_ICC, MatGetFactor_seqaijb200_b200));
   PetscCall(PCRegister(PCJACOBIB200, PCCreate_JacobiB200));
   /* -pc_type jacobi is the fused sub-class unless -b200_keep_pcjacobi (PCRegister replaces an existing name; PCRegister
      itself runs PCRegisterAll first, so the stock entry is already there to be replaced) */
