@@ -105,3 +105,36 @@ def test_driver_in_process():
             "maps = open('/proc/self/maps').read(); assert all(k in maps for k in ('libpetscb200.so', 'libpetscb200plugin.so', 'libpetsc.so', 'libb200driver.so')); print('INPROC OK')")
     p = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "INPROC OK" in p.stdout, p.stdout[-2000:] + p.stderr[-3000:]
+
+
+@needs_petsc
+@pytest.mark.parametrize("fixture", ["ksp_lap27_10_cg_icc", "ksp_lap5_30_cg_icc", "ksp_lap7_12_gmres_icc", "ksp_lap27_10_cg_ilu", "ksp_ex2_100_gmres_jacobi"])
+def test_real_petsc_ksp_history_vs_reference_fixture(oracle, fixture):
+    """The reference's own KSPSolve + the b200 types against residual histories the reference produced on its CPU types
+    (tests/golden/ksp_*.npz): 1e-12 * r0 over the first restart cycle.  ICC(0) / ILU(0) are factored and applied on the device
+    (PCBJACOBI with its single block = the whole matrix on one rank: the same arithmetic as the plain PC)."""
+    import plugin_parity as PP
+    from conftest import assert_history_1e12, golden_path
+    g = np.load(golden_path(fixture + ".npz"))
+    ai, aj, aa = getattr(oracle, str(g["gen"]))(*[int(v) for v in g["args"]])
+    n = len(ai) - 1
+    opts = [str(o) for o in g["opts"]]
+    if "icc" in opts or "ilu" in opts:
+        k = opts.index("-pc_type")
+        sub = opts[k + 1]
+        opts[k + 1] = "bjacobi"
+        opts += ["-sub_pc_type", sub, "-sub_pc_factor_mat_solver_type", "b200"]
+    case = dict(name=fixture, ai=ai, aj=aj, aa=aa, x=np.ones(n), V=np.ones((1, n)), dev=0, solve=dict(opts=" ".join(opts)))
+    with tempfile.TemporaryDirectory(prefix="b200ksp_") as d:
+        orig = PP.cases
+        PP.cases = lambda O, size: [case]
+        try:
+            cs = PP.write(d, oracle, 0, 1)
+        finally:
+            PP.cases = orig
+        drv().run(["-parity", d], inproc=False)
+        hist = np.fromfile(os.path.join(cs[0]["dir"], "out_hist.f64"))
+        info = np.fromfile(os.path.join(cs[0]["dir"], "out_ksp.f64"))
+    ref = g["ref_hist"]
+    assert abs(int(info[0]) - int(g["ref_its"])) <= 1 and int(info[1]) == int(g["ref_reason"])
+    assert_history_1e12(hist, ref, min(31, len(ref), len(hist)), fixture)

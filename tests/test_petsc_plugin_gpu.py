@@ -61,6 +61,8 @@ def test_ex2_golden_through_plugin():
     ["-m", "60", "-n", "50", "-ksp_type", "cg", "-pc_type", "ilu"],
     ["-m", "60", "-n", "50", "-ksp_type", "gmres", "-pc_type", "none", "-ksp_gmres_restart", "10"],
     ["-m", "40", "-n", "40", "-ksp_type", "bcgs", "-pc_type", "jacobi"],               # a KSP the plugin never heard of
+    ["-m", "30", "-n", "25"],                                                          # ex2's defaults: GMRES + PCICC (A is flagged symmetric) -> ICC(0) on the device
+    ["-m", "30", "-n", "25", "-ksp_type", "cg", "-pc_type", "icc"],
 ])
 def test_ex2_plugin_matches_reference_cpu_types(opts):
     a = run("ex2", opts + ["-ksp_monitor"] + B200)
