@@ -11,6 +11,7 @@
  *   MatSolverTypeRegister  "b200" for seqaijb200, MAT_FACTOR_ILU and MAT_FACTOR_ICC   (src/mat/interface/matrix.c:4720)
  *   PCRegister             "jacobib200" and (unless -b200_keep_pcjacobi) "jacobi": the reference's PCJACOBI sub-classed with a
  *                          fused ops->applyBA (src/ksp/pc/interface/pcregis.c, precon.c:810-865)
+ *   KSPRegister            "pipecgb200": single-reduction CG, one reduction kernel + one recurrence kernel per iteration
  *   VecRegister            "mpib200";  MatRegister "mpiaijb200": the row-partitioned types over NCCL ranks (one process per GPU)
  *
  * Structure mirrors the reference's own device subclassing (aijcusparse.cu:2807-2868, veccupmimpl.h:994-1047): create the
@@ -27,6 +28,7 @@
 #include <petsc/private/pcimpl.h>
 #include <../src/vec/vec/impls/dvecimpl.h>
 #include <../src/mat/impls/aij/seq/aij.h>
+#include <petsc/private/kspimpl.h>
 #include <petscksp.h>
 #include "petscb200.h"
 
@@ -42,6 +44,7 @@
 #define MATAIJB200    "aijb200"
 #define MATSOLVERB200 "b200"
 #define PCJACOBIB200  "jacobib200"
+#define KSPPIPECGB200 "pipecgb200"
 
 #define VECMPIB200    "mpib200"
 #define MATMPIAIJB200 "mpiaijb200"
@@ -1965,6 +1968,146 @@ PETSC_EXTERN PetscErrorCode PCCreate_JacobiB200(PC pc)
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
+/* ================================================================== KSP "pipecgb200": single-reduction CG with fused recurrences
+   (a fused-reduction KSP registered through KSPRegister).  The method is Ghysels & Vanroose's pipelined CG, the
+   one behind the reference's KSPPIPECG (src/ksp/ksp/impls/cg/pipecg/pipecg.c); what this type adds on the device is
+     * ONE reduction kernel per iteration -- (u,u), (r,u), (w,u) as a 3-vector VecMDot: one kernel, one host synchronisation
+       and, on several GPUs, one ncclAllReduce of three numbers, where KSPCG needs three of each (cg.c:220-330);
+     * ONE kernel for the eight vector recurrences of an iteration (b200VecPipeCGUpdate: z,q,p,s <- n,m,u,w + beta(z,q,p,s);
+       x,u,w,r <- ... -/+ alpha(p,q,z,s)): 10 vector reads + 8 writes instead of the 24 + 8 of eight separate AYPX/AXPY kernels.
+   Per-entry arithmetic is that of the separate VecAYPX/VecAXPY calls (tested bit for bit against them), so the iterates are those
+   of KSPPIPECG: the residual histories of the reference's -ksp_type pipecg fixtures are reproduced to 1e-12 * r0.
+   Preconditioned residual norm, left preconditioning, zero or non-zero initial guess. */
+typedef struct {
+  Vec r, u, w, m, n, z, q, p, s; /* work vectors (KSPSetWorkVecs) */
+  PetscBool fuse;
+} PipeCGB200_Vecs;
+
+static PetscErrorCode KSPSetUp_PipeCGB200(KSP ksp)
+{
+  PetscFunctionBegin;
+  PetscCall(KSPSetWorkVecs(ksp, 9));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+/* the eight recurrences: one kernel when every vector is a device vector, else the eight BLAS-1 calls */
+static PetscErrorCode PipeCGB200_Advance(KSP ksp, PipeCGB200_Vecs *v, PetscScalar alpha, PetscScalar beta, PetscBool first)
+{
+  Vec       x = ksp->vec_sol, all[10] = {v->n, v->m, v->u, v->w, v->z, v->q, v->p, v->s, x, v->r};
+  PetscBool dev = v->fuse;
+  PetscFunctionBegin;
+  for (int k = 0; k < 10 && dev; k++) dev = PB_IsB200(all[k]) ? PETSC_TRUE : PETSC_FALSE;
+  if (dev) {
+    const double *dn, *dm;
+    double       *d[8];
+    PetscCall(PB_VecRead(v->n, &dn));
+    PetscCall(PB_VecRead(v->m, &dm));
+    for (int k = 0; k < 8; k++) {
+      if (first && k >= 2 && k < 6) PetscCall(PB_VecWrite(all[2 + k], &d[k])); /* z, q, p, s are overwritten in the first step */
+      else PetscCall(PB_VecRW(all[2 + k], &d[k]));
+      PetscCall(PetscObjectStateIncrease((PetscObject)all[2 + k]));
+    }
+    PetscCall(PB_LogTimeBegin());
+    PetscCallB200(b200VecPipeCGUpdate(PB_h, N_(x), alpha, beta, first ? 1 : 0, dn, dm, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]));
+    PetscCall(PB_LogTimeEnd());
+    PetscCall(PB_LogFlops((first ? 8.0 : 16.0) * x->map->n));
+  } else {
+    if (first) {
+      PetscCall(VecCopy(v->n, v->z));
+      PetscCall(VecCopy(v->m, v->q));
+      PetscCall(VecCopy(v->u, v->p));
+      PetscCall(VecCopy(v->w, v->s));
+    } else {
+      PetscCall(VecAYPX(v->z, beta, v->n));
+      PetscCall(VecAYPX(v->q, beta, v->m));
+      PetscCall(VecAYPX(v->p, beta, v->u));
+      PetscCall(VecAYPX(v->s, beta, v->w));
+    }
+    PetscCall(VecAXPY(x, alpha, v->p));
+    PetscCall(VecAXPY(v->u, -alpha, v->q));
+    PetscCall(VecAXPY(v->w, -alpha, v->z));
+    PetscCall(VecAXPY(v->r, -alpha, v->s));
+  }
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+/* residual norm bookkeeping shared by the start-up and the loop: history, monitors, convergence test */
+static PetscErrorCode PipeCGB200_Check(KSP ksp, PetscInt it, PetscReal rnorm)
+{
+  PetscFunctionBegin;
+  KSPCheckNorm(ksp, rnorm);
+  ksp->rnorm = rnorm;
+  PetscCall(KSPLogResidualHistory(ksp, rnorm));
+  PetscCall(KSPMonitor(ksp, it, rnorm));
+  PetscCall((*ksp->converged)(ksp, it, rnorm, &ksp->reason, ksp->cnvP));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode KSPSolve_PipeCGB200(KSP ksp)
+{
+  PipeCGB200_Vecs v;
+  Mat             A, P;
+  Vec             b = ksp->vec_rhs, x = ksp->vec_sol, trio[3];
+  PetscScalar     dots[3], alpha = 0.0, beta = 0.0, gamma_prev = 0.0;
+  PetscReal       rnorm;
+
+  PetscFunctionBegin;
+  v.r = ksp->work[0]; v.z = ksp->work[1]; v.p = ksp->work[2]; v.n = ksp->work[3]; v.w = ksp->work[4];
+  v.q = ksp->work[5]; v.u = ksp->work[6]; v.m = ksp->work[7]; v.s = ksp->work[8];
+  v.fuse = PETSC_TRUE;
+  PetscCall(PetscOptionsGetBool(((PetscObject)ksp)->options, ((PetscObject)ksp)->prefix, "-ksp_pipecgb200_fuse_update", &v.fuse, NULL));
+  PetscCall(PCGetOperators(ksp->pc, &A, &P));
+  ksp->its = 0;
+  /* r = b - A x,  u = B r,  w = A u */
+  if (ksp->guess_zero) PetscCall(VecCopy(b, v.r));
+  else {
+    PetscCall(KSP_MatMult(ksp, A, x, v.r));
+    PetscCall(VecAYPX(v.r, -1.0, b));
+  }
+  PetscCall(KSP_PCApply(ksp, v.r, v.u));
+  PetscCall(KSP_MatMult(ksp, A, v.u, v.w));
+  PetscCall(VecNorm(v.u, NORM_2, &rnorm));
+  PetscCall(PipeCGB200_Check(ksp, 0, rnorm));
+  trio[0] = v.u; trio[1] = v.r; trio[2] = v.w;
+  for (PetscInt it = 0; !ksp->reason; it++) {
+    if (it >= ksp->max_it) {
+      ksp->reason = KSP_DIVERGED_ITS;
+      break;
+    }
+    /* m = B w and n = A m do not depend on the reduction: queued first, so the device keeps working while the host waits */
+    PetscCall(KSP_PCApply(ksp, v.w, v.m));
+    PetscCall(KSP_MatMult(ksp, A, v.m, v.n));
+    PetscCall(VecMDot(v.u, 3, trio, dots)); /* (u,u), (r,u), (w,u) */
+    if (it > 0) {
+      PetscCall(PipeCGB200_Check(ksp, it, PetscSqrtReal(PetscAbsScalar(dots[0]))));
+      if (ksp->reason) break;
+    }
+    {
+      const PetscScalar gamma = dots[1], delta = dots[2];
+      if (it == 0) alpha = gamma / delta;
+      else {
+        beta  = gamma / gamma_prev;
+        alpha = gamma / (delta - beta / alpha * gamma);
+      }
+      gamma_prev = gamma;
+    }
+    PetscCall(PipeCGB200_Advance(ksp, &v, alpha, beta, it == 0 ? PETSC_TRUE : PETSC_FALSE));
+    ksp->its = it + 1;
+  }
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+PETSC_EXTERN PetscErrorCode KSPCreate_PipeCGB200(KSP ksp)
+{
+  PetscFunctionBegin;
+  PetscCall(KSPSetSupportedNorm(ksp, KSP_NORM_PRECONDITIONED, PC_LEFT, 3));
+  PetscCall(KSPSetSupportedNorm(ksp, KSP_NORM_NONE, PC_LEFT, 1));
+  ksp->ops->setup          = KSPSetUp_PipeCGB200;
+  ksp->ops->solve          = KSPSolve_PipeCGB200;
+  ksp->ops->destroy        = KSPDestroyDefault;
+  ksp->ops->view           = NULL;
+  ksp->ops->setfromoptions = NULL;
+  ksp->ops->buildsolution  = KSPBuildSolutionDefault;
+  ksp->ops->buildresidual  = KSPBuildResidualDefault;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
 /* ================================================================== registration (src/sys/dll/reg.c:79,150; dl.c:178-199) */
 PETSC_EXTERN PetscErrorCode PetscDLLibraryRegister_petscb200plugin(void)
 {
@@ -1981,6 +2124,7 @@ PETSC_EXTERN PetscErrorCode PetscDLLibraryRegister_petscb200plugin(void)
   PetscCall(MatSolverTypeRegister(MATSOLVERB200, MATSEQAIJB200, MAT_FACTOR_ICC, MatGetFactor_seqaijb200_b200));
   PetscCall(MatSolverTypeRegister(MATSOLVERB200, MATSEQAIJ, MAT_FACTOR_ICC, MatGetFactor_seqaijb200_b200));
   PetscCall(PCRegister(PCJACOBIB200, PCCreate_JacobiB200));
+  PetscCall(KSPRegister(KSPPIPECGB200, KSPCreate_PipeCGB200));
   /* -pc_type jacobi is the fused sub-class unless -b200_keep_pcjacobi (PCRegister replaces an existing name; PCRegister
      itself runs PCRegisterAll first, so the stock entry is already there to be replaced) */
   PetscCall(PetscOptionsGetBool(NULL, NULL, "-b200_keep_pcjacobi", &keep, NULL));

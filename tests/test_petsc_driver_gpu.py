@@ -108,7 +108,8 @@ def test_driver_in_process():
 
 
 @needs_petsc
-@pytest.mark.parametrize("fixture", ["ksp_lap27_10_cg_icc", "ksp_lap5_30_cg_icc", "ksp_lap7_12_gmres_icc", "ksp_lap27_10_cg_ilu", "ksp_ex2_100_gmres_jacobi"])
+@pytest.mark.parametrize("fixture", ["ksp_lap27_10_cg_icc", "ksp_lap5_30_cg_icc", "ksp_lap7_12_gmres_icc", "ksp_lap27_10_cg_ilu", "ksp_ex2_100_gmres_jacobi",
+                                     "ksp_lap5_30_pipecg_jacobi", "ksp_lap27_10_pipecg_icc"])
 def test_real_petsc_ksp_history_vs_reference_fixture(oracle, fixture):
     """The reference's own KSPSolve + the b200 types against residual histories the reference produced on its CPU types
     (tests/golden/ksp_*.npz): 1e-12 * r0 over the first restart cycle.  ICC(0) / ILU(0) are factored and applied on the device
@@ -119,6 +120,8 @@ def test_real_petsc_ksp_history_vs_reference_fixture(oracle, fixture):
     ai, aj, aa = getattr(oracle, str(g["gen"]))(*[int(v) for v in g["args"]])
     n = len(ai) - 1
     opts = [str(o) for o in g["opts"]]
+    if "pipecg" in opts:   # the reference's -ksp_type pipecg fixture against the plugin's fused single-reduction type
+        opts[opts.index("pipecg")] = "pipecgb200"
     if "icc" in opts or "ilu" in opts:
         k = opts.index("-pc_type")
         sub = opts[k + 1]
