@@ -54,6 +54,8 @@ struct b200CsrPlan_s {
                                   the last bits; one lane per row is always exact); 0: the reference's left-to-right FMA-free
                                   order for every lane count */
   int        hints_auto;
+  double     span_bytes;       /* mean bytes of x spanned by one row ((last col - first col) * 8): how scattered the gather is */
+  int        vec_lanes;        /* > 0: rows are handled by the streaming CSR-vector kernel with this many lanes per row */
   struct CsrBlocks *blk;       /* column-blocked copy (b200CsrPlanSetColumnBlocks) or NULL */
 };
 
@@ -375,6 +377,68 @@ __global__ void jacobi_invert_kernel(int64_t n, const double *__restrict__ d, do
   if (z) atomicAdd(nzero, z);
 }
 
+/* ------------------------------------------------------------------ streaming CSR-vector kernel (scattered / very long rows)
+   The tile kernel above stages whole row tiles in shared memory with TMA and then gathers x: ideal when the gather window is
+   cache-resident (stencils: 1.09 / 0.98 of the measured HBM peak), but on matrices whose columns are SCATTERED over a vector far
+   larger than the L2 every gather is a DRAM access (~1 us), and a single-stage tile keeps too few of them in flight (random CSR
+   d = 32: 65 G gathers/s, cuSPARSE CSR_ALG1 reaches 140 G/s); rows too long for a shared-memory stage (d = 512) fell back to a
+   slow in-kernel path.  This kernel is the classic CSR-vector scheme tuned for latency hiding: G lanes per row read val/col
+   coalesced straight from global memory (streaming, evict-first), four independent gathers per lane in flight, FMA
+   accumulation, shuffle reduction.  The row sum is therefore NOT the reference's left-to-right order (same contract as the
+   tile kernel with several lanes per row: equal to MatMult_SeqAIJ to rounding, <= 1e-12); -mat_b200_spmv_ordered /
+   b200CsrPlanSetSummation(plan, 0) and one-lane plans keep using the tile kernel.  Epilogues as in the tile kernel. */
+__device__ __forceinline__ double ld_stream_f64(const double *p)
+{
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream_s32(const int *p)
+{
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+template <int G>
+__global__ void __launch_bounds__(256) csr_spmv_vector_kernel(int m, const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ val, const double *__restrict__ x,
+                                                              const double *__restrict__ yin, const double *__restrict__ dinv, double *__restrict__ yout, double *__restrict__ yplain)
+{
+  const int      lane = threadIdx.x % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  const int64_t  stride = ((int64_t)gridDim.x * blockDim.x) / G;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; r < m; r += stride) {
+    const int k0 = rowptr[r], k1 = rowptr[r + 1];
+    double    s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int       k = k0 + lane;
+    for (; k + 3 * G < k1; k += 4 * G) { /* four independent gathers in flight per lane */
+      const int    c0 = ld_stream_s32(colidx + k), c1 = ld_stream_s32(colidx + k + G), c2 = ld_stream_s32(colidx + k + 2 * G), c3 = ld_stream_s32(colidx + k + 3 * G);
+      const double a0 = ld_stream_f64(val + k), a1 = ld_stream_f64(val + k + G), a2 = ld_stream_f64(val + k + 2 * G), a3 = ld_stream_f64(val + k + 3 * G);
+      const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+      s0 = fma(a0, x0, s0); s1 = fma(a1, x1, s1); s2 = fma(a2, x2, s2); s3 = fma(a3, x3, s3);
+    }
+    for (; k < k1; k += G) s0 = fma(ld_stream_f64(val + k), __ldg(x + ld_stream_s32(colidx + k)), s0);
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(gmask, s, o, G);
+    if (lane == 0) {
+      if (yin) s += yin[r];
+      if (yplain) yplain[r] = s;
+      yout[r] = dinv ? s * dinv[r] : s;
+    }
+  }
+}
+template <int G>
+static int spmv_vector_launch(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
+{
+  int64_t g = ((int64_t)p->m * G + 255) / 256;
+  if (g > (int64_t)h->num_sms * 32) g = (int64_t)h->num_sms * 32;
+  csr_spmv_vector_kernel<G><<<(int)g, 256, 0, h->stream>>>(p->m, p->d_rowptr, p->d_colidx, val, x, yin, dinv, yout, yplain);
+  B200_LAUNCHED(1);
+  B200_KERNEL_CHECK();
+  return 0;
+}
+__global__ void csr_span_kernel(int m, const int *__restrict__ rowptr, const int *__restrict__ colidx, double *sum);
+
 /* ------------------------------------------------------------------ plan */
 static int pick_lanes(double avg)
 {
@@ -422,6 +486,15 @@ static int plan_configure(b200CsrPlan p)
   }
   StageLayout L  = stage_layout(R, cap);
   p->lanes       = G;
+  { /* streaming CSR-vector kernel for scattered gathers (mean row span beyond ~16 MB of x) and for rows too long for a stage */
+    const char *e = getenv("PETSCB200_SPMV_VECTOR"); /* experiments: lanes per row, 0 = never */
+    int         v = 0;
+    if (p->span_bytes > (double)(16 << 20) && avg >= 2.0) v = avg < 6.0 ? 2 : (avg < 12.0 ? 4 : (avg < 24.0 ? 8 : (avg < 64.0 ? 16 : 32)));
+    if (avg > 192.0) v = 32;
+    if (e) v = atoi(e);
+    if (p->user_lanes == 1) v = 0; /* the caller asked for the parity layout */
+    p->vec_lanes = (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 0;
+  }
   /* L2 hints (measured, profiles/round1_notes.md): stencil-like matrices (G = 1): x evict_last only (2); matrices with
      scattered columns: also stream val/col as evict_first (3) so the gathered x keeps more of the L2 */
   if (p->hints < 0 || p->hints_auto) {
@@ -471,6 +544,17 @@ extern "C" int b200CsrPlanCreate(b200Handle h, int m, int n, int64_t nnz, const 
     B200_CUDA(cudaFree(d_stats));
     for (int k = 0; k < 16; k++) p->max_tile_nnz[k] = hstats[k];
     p->max_row_nnz = hstats[16];
+    if (nnz > 0 && (int64_t)n * 8 > (16 << 20)) { /* a gather can only be scattered if x is large */
+      double *d_sum = NULL, span = 0.0;
+      B200_CUDA(cudaMalloc(&d_sum, sizeof(double)));
+      B200_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), h->stream));
+      csr_span_kernel<<<g, 256, 0, h->stream>>>(m, d_rowptr, d_colidx, d_sum);
+      B200_LAUNCHED(1);
+      B200_CUDA(cudaMemcpyAsync(&span, d_sum, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      B200_CUDA(cudaStreamSynchronize(h->stream));
+      cudaFree(d_sum);
+      p->span_bytes = span / m * 8.0;
+    }
   }
   plan_configure(p);
   *plan = p;
@@ -666,17 +750,7 @@ extern "C" int b200CsrPlanAutoColumnBlocks(b200Handle h, b200CsrPlan p, int *nbl
   const double  avg     = p->m ? (double)p->nnz / p->m : 0.0;
   const int64_t xbytes  = (int64_t)p->n * 8, window = 40LL << 20;
   if (p->m == 0 || p->nnz == 0 || avg < 16.0 || xbytes <= (48LL << 20)) return b200CsrPlanSetColumnBlocks(h, p, 0);
-  double *d_sum = NULL, span = 0.0;
-  B200_CUDA(cudaMalloc(&d_sum, sizeof(double)));
-  B200_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), h->stream));
-  int g = (p->m + 255) / 256;
-  if (g > h->num_sms * 8) g = h->num_sms * 8;
-  csr_span_kernel<<<g, 256, 0, h->stream>>>(p->m, p->d_rowptr, p->d_colidx, d_sum);
-  B200_LAUNCHED(1);
-  B200_CUDA(cudaMemcpyAsync(&span, d_sum, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  B200_CUDA(cudaStreamSynchronize(h->stream));
-  cudaFree(d_sum);
-  span = span / p->m * 8.0; /* mean bytes of x spanned by one row */
+  const double span = p->span_bytes; /* mean bytes of x spanned by one row, measured at plan creation */
   if (span <= (double)window) return b200CsrPlanSetColumnBlocks(h, p, 0);
   int nb = (int)((xbytes + window - 1) / window);
   if (nb < 2) nb = 2;
@@ -800,6 +874,15 @@ static int spmv_launch_lanes(b200Handle h, b200CsrPlan p, const double *val, con
   B200_CHECK(h && p, B200_ERR_ARG_NULL, "null handle/plan");
   if (p->m == 0) return 0;
   B200_CHECK(yout && x && (val || p->nnz == 0), B200_ERR_ARG_NULL, "null vector/value pointer");
+  if (p->vec_lanes && p->tree_sum) {
+    switch (p->vec_lanes) {
+    case 2: return spmv_vector_launch<2>(h, p, val, x, yin, dinv, yout, yplain);
+    case 4: return spmv_vector_launch<4>(h, p, val, x, yin, dinv, yout, yplain);
+    case 8: return spmv_vector_launch<8>(h, p, val, x, yin, dinv, yout, yplain);
+    case 16: return spmv_vector_launch<16>(h, p, val, x, yin, dinv, yout, yplain);
+    default: return spmv_vector_launch<32>(h, p, val, x, yin, dinv, yout, yplain);
+    }
+  }
   B200_CHECK((((uintptr_t)val) & 15) == 0 && (((uintptr_t)p->d_colidx) & 15) == 0 && (((uintptr_t)p->d_rowptr) & 15) == 0, B200_ERR_ARG_WRONG, "CSR arrays must be 16-byte aligned (allocate with b200Malloc)");
   switch (p->lanes) {
   case 1: return spmv_launch_g<1>(h, p, val, x, yin, dinv, yout, yplain);
