@@ -34,6 +34,13 @@ struct b200IluPlan_s {
   int    *d_orderL, *d_orderU;       /* rows in level order, -1 padded to warp multiples */
   int4   *d_metaL, *d_metaU;         /* per slot: (row, first entry, end entry, 0) of the sweep's row segment */
   int     nslotL, nslotU;
+  /* slot-space ("level-set reordered") copy for the packed sweeps: everything a sweep touches is laid out in the order it is
+     processed, so every access of a warp is one coalesced run instead of 32/G scattered sectors */
+  int     packed;                    /* 1: every triangular row fits G entries -> packed sweeps are used */
+  int    *d_slotL, *d_slotU;         /* row -> slot */
+  int    *d_pkcolL, *d_pkcolU;       /* [nslot*G] dependency SLOT of entry e of the slot's row, -1 = padding */
+  double *d_pkvalL, *d_pkvalU, *d_pkdinvU, *d_tL, *d_xU;
+  int    *d_mapLU;                   /* U slot -> L slot of the same row (right-hand side of the upper sweep = result of the lower one) */
   int2   *d_segL, *d_segU;           /* segment schedule of the marching sweeps: (first row, number of rows) per slot, level order */
   int     nsegslotL, nsegslotU, nseglevL, nseglevU, GS;
   int    *d_flag;                    /* per-row ready epoch (numeric factorisation) */
@@ -48,6 +55,8 @@ struct b200IluPlan_s {
 };
 
 #define ILU_TPB 256
+__global__ void ilu_pack_cols_kernel(int nslot, int G, bool upper, const int *__restrict__ order, const int *__restrict__ slotof, const int *__restrict__ bi, const int *__restrict__ bdiag, const int *__restrict__ bj, int *__restrict__ pkcol);
+__global__ void ilu_pack_vals_kernel(int nslot, int G, bool upper, const int *__restrict__ order, const int *__restrict__ bi, const int *__restrict__ bdiag, const double *__restrict__ ba, double *__restrict__ pkval, double *__restrict__ pkdinv);
 /* PETSCB200_ILU_MARCH=1 selects the segment-marching sweeps for ILU(0).  Measured on the B200 (profiles/round2_notes.md): bit-exact,
    but 8.05 ms vs 7.09 ms per PCApply on the 27-point 256^3 operator and 5x slower on the 7-point one -- a marching line catches up
    with its producer line and then pays an L2 round trip on every row, and the 32/G lines of a warp stall each other in lockstep.
@@ -307,6 +316,8 @@ extern "C" int b200Ilu0Destroy(b200IluPlan p)
   if (!p) return 0;
   cudaFree(p->d_ai); cudaFree(p->d_adiag); cudaFree(p->d_bi); cudaFree(p->d_bj); cudaFree(p->d_bdiag); cudaFree(p->d_ba);
   cudaFree(p->d_segL); cudaFree(p->d_segU);
+  cudaFree(p->d_slotL); cudaFree(p->d_slotU); cudaFree(p->d_pkcolL); cudaFree(p->d_pkcolU); cudaFree(p->d_pkvalL); cudaFree(p->d_pkvalU); cudaFree(p->d_pkdinvU);
+  cudaFree(p->d_tL); cudaFree(p->d_xU); cudaFree(p->d_mapLU);
   cudaFree(p->d_orderL); cudaFree(p->d_orderU); cudaFree(p->d_metaL); cudaFree(p->d_metaU); cudaFree(p->d_flag); cudaFree(p->d_ticket); cudaFree(p->d_tmp);
   free(p->h_bi); free(p->h_bj); free(p->h_bdiag);
   free(p);
@@ -438,6 +449,56 @@ extern "C" int b200Ilu0Symbolic(b200Handle h, int n, const int *ai, const int *a
     B200_CUDA(cudaStreamSynchronize(h->stream));
     free(sL); free(sU);
   }
+  { /* slot-space copy for the packed sweeps: possible when every triangular row fits the G lanes of a slot */
+    int maxL = 0, maxU = 0;
+    for (int i = 0; i < n; i++) {
+      if (bi[i + 1] - bi[i] > maxL) maxL = bi[i + 1] - bi[i];
+      const int lu = bdiag[i] - (bdiag[i + 1] + 1);
+      if (lu > maxU) maxU = lu;
+    }
+    const size_t need = ((size_t)p->nslotL + (size_t)p->nslotU) * (size_t)p->G * 12 + ((size_t)p->nslotL + (size_t)p->nslotU) * 16 + (size_t)n * 8;
+    size_t       fr = 0, totm = 0;
+    cudaMemGetInfo(&fr, &totm);
+    /* measured (profiles/round2_notes.md): the packed sweeps win where the levels are WIDE (throughput-bound: 7-point 512^3, 87 k
+       rows per level: PCApply 16.5 -> 8.6 ms) and lose where they are narrow (latency-bound: 27-point 256^3, 9.4 k rows per level:
+       7.1 -> 8.4 ms, padding 13 -> 16 entries and the same ~2 us per level) */
+    const double rows_per_level = (double)n / (double)(nlevL > 0 ? nlevL : 1);
+    const char  *ep = getenv("PETSCB200_ILU_PACKED_MIN_WIDTH");
+    const double minw = ep ? atof(ep) : 24000.0;
+    p->packed = (n > 0 && maxL <= p->G && maxU <= p->G && rows_per_level >= minw && need + ((size_t)2 << 30) < fr) ? 1 : 0;
+    if (p->packed) {
+      int *slotL = (int *)malloc(sizeof(int) * (size_t)(n + 1)), *slotU = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+      for (int s2 = 0; s2 < p->nslotL; s2++)
+        if (orderL[s2] >= 0) slotL[orderL[s2]] = s2;
+      for (int s2 = 0; s2 < p->nslotU; s2++)
+        if (orderU[s2] >= 0) slotU[orderU[s2]] = s2;
+      B200_CUDA(cudaMalloc(&p->d_slotL, sizeof(int) * ((size_t)n + 64)));
+      B200_CUDA(cudaMalloc(&p->d_slotU, sizeof(int) * ((size_t)n + 64)));
+      B200_CUDA(cudaMemcpyAsync(p->d_slotL, slotL, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+      B200_CUDA(cudaMemcpyAsync(p->d_slotU, slotU, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+      B200_CUDA(cudaMalloc(&p->d_pkcolL, sizeof(int) * ((size_t)p->nslotL * p->G + 64)));
+      B200_CUDA(cudaMalloc(&p->d_pkcolU, sizeof(int) * ((size_t)p->nslotU * p->G + 64)));
+      B200_CUDA(cudaMalloc(&p->d_pkvalL, sizeof(double) * ((size_t)p->nslotL * p->G + 64)));
+      B200_CUDA(cudaMalloc(&p->d_pkvalU, sizeof(double) * ((size_t)p->nslotU * p->G + 64)));
+      B200_CUDA(cudaMalloc(&p->d_pkdinvU, sizeof(double) * ((size_t)p->nslotU + 64)));
+      B200_CUDA(cudaMalloc(&p->d_tL, sizeof(double) * ((size_t)p->nslotL + 64)));
+      B200_CUDA(cudaMalloc(&p->d_xU, sizeof(double) * ((size_t)p->nslotU + 64)));
+      {
+        int *mapLU = (int *)malloc(sizeof(int) * ((size_t)p->nslotU + 1));
+        for (int s2 = 0; s2 < p->nslotU; s2++) mapLU[s2] = orderU[s2] >= 0 ? slotL[orderU[s2]] : -1;
+        B200_CUDA(cudaMalloc(&p->d_mapLU, sizeof(int) * ((size_t)p->nslotU + 64)));
+        B200_CUDA(cudaMemcpyAsync(p->d_mapLU, mapLU, sizeof(int) * (size_t)p->nslotU, cudaMemcpyHostToDevice, h->stream));
+        B200_CUDA(cudaStreamSynchronize(h->stream));
+        free(mapLU);
+      }
+      const int g = h->num_sms * 8;
+      ilu_pack_cols_kernel<<<g, 256, 0, h->stream>>>(p->nslotL, p->G, false, p->d_orderL, p->d_slotL, p->d_bi, p->d_bdiag, p->d_bj, p->d_pkcolL);
+      ilu_pack_cols_kernel<<<g, 256, 0, h->stream>>>(p->nslotU, p->G, true, p->d_orderU, p->d_slotU, p->d_bi, p->d_bdiag, p->d_bj, p->d_pkcolU);
+      B200_LAUNCHED(2);
+      B200_CUDA(cudaStreamSynchronize(h->stream));
+      free(slotL); free(slotU);
+    }
+  }
   B200_CUDA(cudaMalloc(&p->d_ba, sizeof(double) * ((size_t)nnz + 64)));
   B200_CUDA(cudaMalloc(&p->d_tmp, sizeof(double) * ((size_t)n + 64)));
   B200_CUDA(cudaMalloc(&p->d_flag, sizeof(int) * ((size_t)n + 64)));
@@ -499,6 +560,13 @@ extern "C" int b200Ilu0Numeric(b200Handle h, b200IluPlan p, const double *d_aval
     B200_CHECK(nshift <= 60 && shift > 0.0, B200_ERR_MAT_LU_ZRPVT, "Zero pivot in ILU(0) factorisation; shift could not repair it");
   }
   if (nshift_out) *nshift_out = nshift;
+  if (p->packed) { /* slot-major copy of the factor values for the packed sweeps */
+    const int g = h->num_sms * 8;
+    ilu_pack_vals_kernel<<<g, 256, 0, h->stream>>>(p->nslotL, p->G, false, p->d_orderL, p->d_bi, p->d_bdiag, p->d_ba, p->d_pkvalL, NULL);
+    ilu_pack_vals_kernel<<<g, 256, 0, h->stream>>>(p->nslotU, p->G, true, p->d_orderU, p->d_bi, p->d_bdiag, p->d_ba, p->d_pkvalU, p->d_pkdinvU);
+    B200_LAUNCHED(2);
+    B200_KERNEL_CHECK();
+  }
   p->factored = 1;
   return 0;
 }
@@ -840,6 +908,112 @@ int2 *b200_build_segments(int n, int mode, const int *ext, const int *bj, int rp
   return out;
 }
 
+
+/* ------------------------------------------------------------------ packed ("level-set reordered") sweeps (round 2)
+   ncu of the level-scheduled pipe kernel on the 7-point operator: 1.7-2.0 TB/s of DRAM traffic, only 1.5-1.7x the algorithmic
+   bytes -- the L2 absorbs the scatter -- yet 5.5 us per level at 512^3: the limiter is L2 SECTOR THROUGHPUT.  Consecutive slots
+   of a level are rows nx-1 apart, so every 8-byte access of a lane (factor entries, right-hand side, the three polled
+   dependencies, the result) is its own 32-byte sector transaction: ~76 sectors per 8 rows.  Here the sweep runs entirely in
+   SLOT space: factor entries are packed slot-major ([slot][G], padding col = -1 / value 0), dependencies are stored as SLOT
+   numbers (the neighbours of consecutive slots are consecutive slots of the previous level: the polls coalesce too), and the
+   right-hand sides / results are reached through per-slot maps inside the sweeps (b[row], t_L[L-slot of the row], x[row]).  Per row the same strict left-to-right FMA-free sum (a padded entry contributes an exact -(+0.0)): bit-identical. */
+__global__ void ilu_pack_cols_kernel(int nslot, int G, bool upper, const int *__restrict__ order, const int *__restrict__ slotof, const int *__restrict__ bi, const int *__restrict__ bdiag, const int *__restrict__ bj, int *__restrict__ pkcol)
+{
+  const int64_t tot = (int64_t)nslot * G, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < tot; q += stride) {
+    const int s = (int)(q / G), e = (int)(q % G), i = order[s];
+    int       c = -1;
+    if (i >= 0) {
+      const int ks = upper ? bdiag[i + 1] + 1 : bi[i], ke = upper ? bdiag[i] : bi[i + 1];
+      if (ks + e < ke) c = slotof[bj[ks + e]];
+    }
+    pkcol[q] = c;
+  }
+}
+__global__ void ilu_pack_vals_kernel(int nslot, int G, bool upper, const int *__restrict__ order, const int *__restrict__ bi, const int *__restrict__ bdiag, const double *__restrict__ ba, double *__restrict__ pkval, double *__restrict__ pkdinv)
+{
+  const int64_t tot = (int64_t)nslot * G, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < tot; q += stride) {
+    const int s = (int)(q / G), e = (int)(q % G), i = order[s];
+    double    v = 0.0;
+    if (i >= 0) {
+      const int ks = upper ? bdiag[i + 1] + 1 : bi[i], ke = upper ? bdiag[i] : bi[i + 1];
+      if (ks + e < ke) v = ba[ks + e];
+      if (upper && e == 0) pkdinv[s] = ba[ke];
+    } else if (upper && e == 0) pkdinv[s] = 0.0;
+    pkval[q] = v;
+  }
+}
+template <int G, bool UPPER>
+__global__ void __launch_bounds__(ILU_TPB) ilu_sweep_packed_kernel(int nslot, const int *__restrict__ pkcol, const double *__restrict__ pkval, const double *__restrict__ pkdinv, const int *__restrict__ rhsmap,
+                                                                   const double *__restrict__ rhs, double *out, const int *__restrict__ out2map, double *out2)
+{
+  /* rhsmap[s]: where slot s finds its right-hand side (lower sweep: the row, rhs = b; upper sweep: the row's slot of the lower
+     sweep, rhs = t_L) -- folding the permutation passes b -> b_L and t_L -> t_U into the sweeps (as separate gather kernels they
+     cost 4 ms of the 14 ms PCApply at 512^3).  out2/out2map (upper sweep): the result is also stored in natural order. */
+  constexpr int  RPW  = 32 / G;
+  const int      lane = threadIdx.x & 31, gl = lane % G, grp = lane / G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+  const int64_t  wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, W = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t  nchunk = ((int64_t)nslot + RPW - 1) / RPW;
+  /* three chunks in flight per warp (static round robin c, c+W, c+2W over a co-resident grid; a chunk only waits for earlier
+     chunks): stage E = coalesced loads of the packed entries two chunks ahead, stage P = the dependency polls one chunk ahead
+     (issued as soon as its slot numbers are there: in a wide level the values were published long ago, so the poll's L2 round
+     trip overlaps the current chunk instead of sitting on the warp's critical path), stage C = re-poll what was not ready,
+     ordered subtraction, publish.  Measured before this stage existed: 8 rows per warp per ~2 us = 24 G rows/s at 512^3. */
+  int    colC = -1, colP = -1, colE = -1;
+  double aC = 0, aP = 0, aE = 0, rC = 0, rP = 0, rE = 0, dC = 0, dP = 0, dE = 0, vC = 0, vP = 0;
+  auto   load = [&](int64_t ch, int &col, double &a, double &r, double &d) {
+    if (ch < nchunk) {
+      const int64_t q = ch * 32 + lane, s = ch * RPW + grp;
+      col = __ldg(pkcol + q);
+      a   = __ldg(pkval + q);
+      const int m = s < nslot ? __ldg(rhsmap + s) : -1;
+      r   = m >= 0 ? rhs[m] : 0.0;
+      if (UPPER) d = s < nslot ? __ldg(pkdinv + s) : 0.0;
+    } else {
+      col = -1;
+      a = r = d = 0.0;
+    }
+  };
+  auto poll = [&](int col) -> double { return col >= 0 ? __longlong_as_double((long long)ld_relaxed_u64(out + col)) : 0.0; };
+  load(wid, colC, aC, rC, dC);
+  load(wid + W, colP, aP, rP, dP);
+  vC = poll(colC);
+  for (int64_t c = wid; c < nchunk; c += W) {
+    load(c + 2 * W, colE, aE, rE, dE);
+    vP = poll(colP);
+    {
+      const bool act   = colC >= 0;
+      double     v     = vC;
+      bool       ready = !act || ((unsigned long long)__double_as_longlong(v) != ILU_SENTINEL);
+      while (!__all_sync(0xffffffffu, ready)) { /* warp-convergent re-poll */
+        if (!ready) {
+          v     = __longlong_as_double((long long)ld_relaxed_u64(out + colC));
+          ready = ((unsigned long long)__double_as_longlong(v) != ILU_SENTINEL);
+        }
+      }
+      const double p   = act ? __dmul_rn(aC, v) : 0.0;
+      double       sum = rC;
+#pragma unroll
+      for (int l = 0; l < G; l++) sum = __dsub_rn(sum, __shfl_sync(gmask, p, l, G)); /* strict left-to-right, FMA-free; padding: - (+0.0) */
+      const int64_t s = c * RPW + grp;
+      if (gl == 0 && s < nslot) {
+        if (UPPER) sum = __dmul_rn(sum, dC);
+        st_relaxed_f64(out + s, sum);
+        if (out2) {
+          const int i2 = __ldg(out2map + s);
+          if (i2 >= 0) out2[i2] = sum;
+        }
+      }
+    }
+    __syncwarp();
+    colC = colP; aC = aP; rC = rP; dC = dP; vC = vP;
+    colP = colE; aP = aE; rP = rE; dP = dE;
+  }
+}
+static int g_ilu_packed = 1; /* PETSCB200_ILU_PACKED=0: level-scheduled pipe kernels on the factor's own layout */
+
 static int ilu_set_backoff(void)
 {
   static int done = 0;
@@ -853,6 +1027,7 @@ static int ilu_set_backoff(void)
     if ((e = getenv("PETSCB200_ILU_BATCH")) && atoi(e) > 0) g_ilu_batch = atoi(e);
     if ((e = getenv("PETSCB200_ILU_PIPE"))) g_ilu_pipe = atoi(e);
     if ((e = getenv("PETSCB200_ILU_MARCH"))) g_ilu_march = atoi(e);
+    if ((e = getenv("PETSCB200_ILU_PACKED"))) g_ilu_packed = atoi(e);
     done = 1;
   }
   return 0;
@@ -899,6 +1074,30 @@ static int sweeps_launch(b200Handle h, b200IluPlan p, const double *b, double *x
   return 0;
 }
 
+template <int G>
+static int packed_launch(b200Handle h, b200IluPlan p, const double *b, double *x)
+{
+  static int occ = 0;
+  if (!occ) {
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ilu_sweep_packed_kernel<G, true>, ILU_TPB, 0));
+    if (occ < 1) occ = 1;
+  }
+  B200_CUDA(cudaMemsetAsync(p->d_tL, 0xFF, sizeof(double) * (size_t)p->nslotL, h->stream)); /* sentinel fill */
+  B200_CUDA(cudaMemsetAsync(p->d_xU, 0xFF, sizeof(double) * (size_t)p->nslotU, h->stream));
+  int gL = ilu_grid(h, p->maxwL, G), gU = ilu_grid(h, p->maxwU, G);
+  if (gL > occ * h->num_sms) gL = occ * h->num_sms;
+  if (gU > occ * h->num_sms) gU = occ * h->num_sms;
+  const double *nuld = NULL, *rhsU = p->d_tL;
+  const int    *nuli = NULL;
+  double       *nulo = NULL;
+  void *argsL[] = {&p->nslotL, &p->d_pkcolL, &p->d_pkvalL, &nuld, &p->d_orderL, &b, &p->d_tL, &nuli, &nulo};
+  void *argsU[] = {&p->nslotU, &p->d_pkcolU, &p->d_pkvalU, &p->d_pkdinvU, &p->d_mapLU, &rhsU, &p->d_xU, &p->d_orderU, &x};
+  B200_CUDA(cudaLaunchCooperativeKernel((void *)ilu_sweep_packed_kernel<G, false>, dim3(gL), dim3(ILU_TPB), argsL, 0, h->stream));
+  B200_CUDA(cudaLaunchCooperativeKernel((void *)ilu_sweep_packed_kernel<G, true>, dim3(gU), dim3(ILU_TPB), argsU, 0, h->stream));
+  B200_LAUNCHED(2);
+  return 0;
+}
+
 static int march_launch(b200Handle h, b200IluPlan p, const double *b, double *x)
 {
   B200_CUDA(cudaMemsetAsync(p->d_tmp, 0xFF, sizeof(double) * (size_t)p->n, h->stream)); /* sentinel fill */
@@ -920,6 +1119,15 @@ extern "C" int b200Ilu0Solve(b200Handle h, b200IluPlan p, const double *d_b, dou
     int coop = 0;
     B200_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
     if (g_ilu_march && coop == 1) return march_launch(h, p, d_b, d_x);
+    if (g_ilu_packed && p->packed && coop == 1) {
+      switch (p->G) {
+      case 2: return packed_launch<2>(h, p, d_b, d_x);
+      case 4: return packed_launch<4>(h, p, d_b, d_x);
+      case 8: return packed_launch<8>(h, p, d_b, d_x);
+      case 16: return packed_launch<16>(h, p, d_b, d_x);
+      default: return packed_launch<32>(h, p, d_b, d_x);
+      }
+    }
   }
   switch (p->G) {
   case 2: return sweeps_launch<2>(h, p, d_b, d_x);
