@@ -56,6 +56,8 @@ struct b200CsrPlan_s {
   int        hints_auto;
   double     span_bytes;       /* mean bytes of x spanned by one row ((last col - first col) * 8): how scattered the gather is */
   int        vec_lanes;        /* > 0: rows are handled by the streaming CSR-vector kernel with this many lanes per row */
+  int       *d_longrows;       /* rows longer than SPMV_LONG_ROW (power-law tails): one CTA each in csr_spmv_longrow_kernel */
+  int        nlong;
   struct CsrBlocks *blk;       /* column-blocked copy (b200CsrPlanSetColumnBlocks) or NULL */
 };
 
@@ -399,15 +401,17 @@ __device__ __forceinline__ int ld_stream_s32(const int *p)
   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
+#define SPMV_LONG_ROW 8192 /* entries: beyond this a row gets a whole CTA (row-binning for power-law matrices: G is per bin, not per matrix) */
 template <int G>
 __global__ void __launch_bounds__(256) csr_spmv_vector_kernel(int m, const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ val, const double *__restrict__ x,
-                                                              const double *__restrict__ yin, const double *__restrict__ dinv, double *__restrict__ yout, double *__restrict__ yplain)
+                                                              const double *__restrict__ yin, const double *__restrict__ dinv, double *__restrict__ yout, double *__restrict__ yplain, int skip_long)
 {
   const int      lane = threadIdx.x % G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   const int64_t  stride = ((int64_t)gridDim.x * blockDim.x) / G;
   for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; r < m; r += stride) {
     const int k0 = rowptr[r], k1 = rowptr[r + 1];
+    if (skip_long && k1 - k0 > SPMV_LONG_ROW) continue; /* handled by csr_spmv_longrow_kernel */
     double    s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int       k = k0 + lane;
     for (; k + 3 * G < k1; k += 4 * G) { /* four independent gathers in flight per lane */
@@ -427,13 +431,53 @@ __global__ void __launch_bounds__(256) csr_spmv_vector_kernel(int m, const int *
     }
   }
 }
+/* the long-row bin: one CTA per row, 256 threads x 4 independent gathers, block reduction in fixed order */
+__global__ void __launch_bounds__(256) csr_spmv_longrow_kernel(int nlong, const int *__restrict__ rows, const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ val,
+                                                               const double *__restrict__ x, const double *__restrict__ yin, const double *__restrict__ dinv, double *__restrict__ yout, double *__restrict__ yplain)
+{
+  __shared__ double part[8];
+  for (int q = blockIdx.x; q < nlong; q += gridDim.x) {
+    const int r = rows[q], k0 = rowptr[r], k1 = rowptr[r + 1];
+    double    s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int       k = k0 + threadIdx.x;
+    for (; k + 3 * 256 < k1; k += 4 * 256) {
+      const int    c0 = ld_stream_s32(colidx + k), c1 = ld_stream_s32(colidx + k + 256), c2 = ld_stream_s32(colidx + k + 512), c3 = ld_stream_s32(colidx + k + 768);
+      const double a0 = ld_stream_f64(val + k), a1 = ld_stream_f64(val + k + 256), a2 = ld_stream_f64(val + k + 512), a3 = ld_stream_f64(val + k + 768);
+      s0 = fma(a0, __ldg(x + c0), s0); s1 = fma(a1, __ldg(x + c1), s1); s2 = fma(a2, __ldg(x + c2), s2); s3 = fma(a3, __ldg(x + c3), s3);
+    }
+    for (; k < k1; k += 256) s0 = fma(ld_stream_f64(val + k), __ldg(x + ld_stream_s32(colidx + k)), s0);
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
+      if (yin) t += yin[r];
+      if (yplain) yplain[r] = t;
+      yout[r] = dinv ? t * dinv[r] : t;
+    }
+    __syncthreads();
+  }
+}
+__global__ void csr_longrow_list_kernel(int m, const int *__restrict__ rowptr, int *list, int *count)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride)
+    if (rowptr[r + 1] - rowptr[r] > SPMV_LONG_ROW) list[atomicAdd(count, 1)] = r; /* order is irrelevant: every row is computed on its own */
+}
 template <int G>
 static int spmv_vector_launch(b200Handle h, b200CsrPlan p, const double *val, const double *x, const double *yin, const double *dinv, double *yout, double *yplain)
 {
   int64_t g = ((int64_t)p->m * G + 255) / 256;
   if (g > (int64_t)h->num_sms * 32) g = (int64_t)h->num_sms * 32;
-  csr_spmv_vector_kernel<G><<<(int)g, 256, 0, h->stream>>>(p->m, p->d_rowptr, p->d_colidx, val, x, yin, dinv, yout, yplain);
+  csr_spmv_vector_kernel<G><<<(int)g, 256, 0, h->stream>>>(p->m, p->d_rowptr, p->d_colidx, val, x, yin, dinv, yout, yplain, p->nlong > 0);
   B200_LAUNCHED(1);
+  if (p->nlong > 0) {
+    int gl = p->nlong < h->num_sms * 8 ? p->nlong : h->num_sms * 8;
+    csr_spmv_longrow_kernel<<<gl, 256, 0, h->stream>>>(p->nlong, p->d_longrows, p->d_rowptr, p->d_colidx, val, x, yin, dinv, yout, yplain);
+    B200_LAUNCHED(1);
+  }
   B200_KERNEL_CHECK();
   return 0;
 }
@@ -491,6 +535,7 @@ static int plan_configure(b200CsrPlan p)
     int         v = 0;
     if (p->span_bytes > (double)(16 << 20) && avg >= 2.0) v = avg < 6.0 ? 2 : (avg < 12.0 ? 4 : (avg < 24.0 ? 8 : (avg < 64.0 ? 16 : 32)));
     if (avg > 192.0) v = 32;
+    if (p->nlong > 0 && !v) v = avg < 6.0 ? 2 : (avg < 12.0 ? 4 : (avg < 24.0 ? 8 : (avg < 64.0 ? 16 : 32))); /* power-law tail: binned kernels instead of the tile kernel's in-kernel fallback */
     if (e) v = atoi(e);
     if (p->user_lanes == 1) v = 0; /* the caller asked for the parity layout */
     p->vec_lanes = (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 0;
@@ -555,6 +600,19 @@ extern "C" int b200CsrPlanCreate(b200Handle h, int m, int n, int64_t nnz, const 
       cudaFree(d_sum);
       p->span_bytes = span / m * 8.0;
     }
+    if (p->max_row_nnz > SPMV_LONG_ROW) { /* row-binning: the tail of very long rows gets its own kernel */
+      int *d_cnt = NULL, cnt = 0;
+      B200_CUDA(cudaMalloc(&d_cnt, sizeof(int)));
+      B200_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int), h->stream));
+      const int64_t cap = nnz / SPMV_LONG_ROW + 1; /* there cannot be more rows that long */
+      B200_CUDA(cudaMalloc(&p->d_longrows, sizeof(int) * (size_t)cap));
+      csr_longrow_list_kernel<<<g, 256, 0, h->stream>>>(m, d_rowptr, p->d_longrows, d_cnt);
+      B200_LAUNCHED(1);
+      B200_CUDA(cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      B200_CUDA(cudaStreamSynchronize(h->stream));
+      cudaFree(d_cnt);
+      p->nlong = cnt;
+    }
   }
   plan_configure(p);
   *plan = p;
@@ -575,7 +633,10 @@ static void csr_blocks_free(struct CsrBlocks *B)
 
 extern "C" int b200CsrPlanDestroy(b200CsrPlan plan)
 {
-  if (plan) csr_blocks_free(plan->blk);
+  if (plan) {
+    csr_blocks_free(plan->blk);
+    cudaFree(plan->d_longrows);
+  }
   free(plan);
   return 0;
 }

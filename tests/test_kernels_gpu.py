@@ -344,3 +344,89 @@ def test_device_laplace27_and_random_generators(H, oracle):
     H.csr_plan_set_layout(plan, lanes=1)
     H.spmv(plan, d_a, d_x, d_y)
     assert np.array_equal(d_y.download(), oracle.matmult(ai, aj.reshape(-1), aa, x))
+
+
+# ---------------------------------------------------------------------------------------------- streaming CSR-vector kernel
+def _spmv_all(H, ai, aj, aa, x, y, dinv):
+    """y0 = A x, z = y + A x, w = dinv .* (A x) through one plan (whatever kernel the plan chose)."""
+    from petsc_b200 import _capi
+    L = _capi.lib()
+    m, nnz = len(ai) - 1, len(aj)
+    n = len(x)
+    d_i, d_j, d_a = H.array(ai, np.int32), H.array(aj, np.int32), H.array(aa, np.float64)
+    plan = C.c_void_p()
+    _capi.check(L.b200CsrPlanCreate(H.h, m, n, C.c_int64(nnz), d_i.ptr, d_j.ptr, C.byref(plan)))
+    d_x, d_y, d_d = H.array(x), H.array(y), H.array(dinv)
+    o1, o2, o3 = H.empty(m), H.empty(m), H.empty(m)
+    _capi.check(L.b200CsrSpMV(H.h, plan, d_a.ptr, d_x.ptr, o1.ptr))
+    _capi.check(L.b200CsrSpMVAdd(H.h, plan, d_a.ptr, d_x.ptr, d_y.ptr, o2.ptr))
+    _capi.check(L.b200CsrSpMVJacobi(H.h, plan, d_a.ptr, d_x.ptr, d_d.ptr, o3.ptr, None))
+    lay = [C.c_int() for _ in range(6)]
+    _capi.check(L.b200CsrPlanGetLayout(plan, *[C.byref(v) for v in lay]))
+    res = o1.download(), o2.download(), o3.download()
+    L.b200CsrPlanDestroy(plan)
+    for o in (d_i, d_j, d_a, d_x, d_y, d_d, o1, o2, o3):
+        o.free()
+    return res
+
+
+@pytest.mark.parametrize("lanes", [2, 8, 32])
+def test_spmv_vector_kernel_forced(H, oracle, lanes, monkeypatch):
+    """The streaming CSR-vector kernel (auto-selected for scattered / very long rows) forced onto every test matrix: MatMult,
+    MatMultAdd and the Jacobi epilogue within 1e-12 of MatMult_SeqAIJ (tree-ordered row sums, like every multi-lane layout)."""
+    monkeypatch.setenv("PETSCB200_SPMV_VECTOR", str(lanes))
+    rng = np.random.default_rng(21)
+    for name, (ai, aj, aa) in matrices(oracle):
+        m = len(ai) - 1
+        n = int(max(aj.max() + 1 if len(aj) else 1, m))
+        x, y, dinv = rng.uniform(-1, 1, n), rng.uniform(-1, 1, m), rng.uniform(0.5, 2, m)
+        ref = oracle.matmult(ai, aj, aa, x) if n == m else None
+        if ref is None:
+            ref = np.array([np.dot(aa[ai[r]:ai[r + 1]], x[aj[ai[r]:ai[r + 1]]]) for r in range(m)])
+        scale = np.array([np.abs(aa[ai[r]:ai[r + 1]] * x[aj[ai[r]:ai[r + 1]]]).sum() for r in range(m)]) + 1e-300
+        y0, z, w = _spmv_all(H, ai, aj, aa, x, y, dinv)
+        assert np.all(np.abs(y0 - ref) <= 1e-12 * scale), name
+        assert np.all(np.abs(z - (y + ref)) <= 1e-12 * (scale + np.abs(y))), name
+        assert np.all(np.abs(w - dinv * ref) <= 1e-12 * scale * dinv), name
+
+
+def test_spmv_power_law_row_bins(H, oracle):
+    """A power-law matrix: 2.5 M rows of ~4 scattered entries plus a tail of very long rows (up to 600 k entries).  The plan must
+    pick the streaming kernel by itself (scattered columns), give the tail its own one-CTA-per-row bin, and agree with
+    MatMult_SeqAIJ to 1e-12."""
+    from petsc_b200 import _capi
+    L = _capi.lib()
+    n = 2_500_000
+    rng = np.random.default_rng(33)
+    ai0, aj0, aa0 = oracle.random_csr(n, 4, 5)
+    lens = np.full(n, 4, np.int64)
+    longrows = {7: 600_000, 1000: 120_000, 123_456: 40_000, 2_000_001: 9_000, n - 1: 20_000}
+    for r, l in longrows.items():
+        lens[r] = l
+    ai = np.zeros(n + 1, np.int64); ai[1:] = np.cumsum(lens)
+    aj = np.empty(ai[-1], np.int32); aa = np.empty(ai[-1])
+    short = np.ones(n, bool); short[list(longrows)] = False
+    # short rows keep their 4 entries
+    idx_new = (ai[:-1][short][:, None] + np.arange(4)[None, :]).ravel()
+    idx_old = (ai0[:-1].astype(np.int64)[short][:, None] + np.arange(4)[None, :]).ravel()
+    aj[idx_new] = aj0[idx_old]; aa[idx_new] = aa0[idx_old]
+    for r, l in longrows.items():
+        cols = np.sort(rng.choice(n, l, replace=False)).astype(np.int32)
+        aj[ai[r]:ai[r + 1]] = cols; aa[ai[r]:ai[r + 1]] = rng.uniform(-1, 1, l)
+    ai = ai.astype(np.int32)
+    x = rng.uniform(-1, 1, n)
+    ref = oracle.matmult(ai, aj, aa, x)
+    d_i, d_j, d_a, d_x, d_y = H.array(ai, np.int32), H.array(aj, np.int32), H.array(aa), H.array(x), H.empty(n)
+    plan = C.c_void_p()
+    _capi.check(L.b200CsrPlanCreate(H.h, n, n, C.c_int64(len(aj)), d_i.ptr, d_j.ptr, C.byref(plan)))
+    before = _capi.launch_count()
+    _capi.check(L.b200CsrSpMV(H.h, plan, d_a.ptr, d_x.ptr, d_y.ptr))
+    assert _capi.launch_count() - before == 2            # streaming kernel + the long-row bin
+    y = d_y.download()
+    scale = np.abs(ref) + 1e-9 * np.sqrt(lens)
+    assert np.all(np.abs(y - ref) <= 1e-12 * np.maximum(scale, np.sqrt(lens))), float(np.abs(y - ref).max())
+    for r in longrows:
+        assert abs(y[r] - ref[r]) <= 1e-12 * np.sqrt(lens[r]) * 10
+    L.b200CsrPlanDestroy(plan)
+    for o in (d_i, d_j, d_a, d_x, d_y):
+        o.free()
