@@ -76,6 +76,9 @@ int b200Malloc(b200Handle h, void **d_ptr, size_t bytes);   /* padded + aligned 
 int b200Free(b200Handle h, void *d_ptr);
 int b200MallocHost(void **h_ptr, size_t bytes);              /* pinned */
 int b200FreeHost(void *h_ptr);
+/* pinned host memory mapped into the device address space (*d_ptr aliases *h_ptr): a kernel writes its scalar result there and the
+   host reads it after b200Synchronize -- no cudaMemcpy on the latency-critical norm of every Krylov iteration; free with b200FreeHost(h_ptr) */
+int b200MallocMapped(void **h_ptr, void **d_ptr, size_t bytes);
 int b200MemcpyHtoD(b200Handle h, void *d_dst, const void *h_src, size_t bytes); /* stream-ordered, returns after completion */
 int b200MemcpyDtoH(b200Handle h, void *h_dst, const void *d_src, size_t bytes);
 int b200MemcpyDtoD(b200Handle h, void *d_dst, const void *d_src, size_t bytes); /* asynchronous */

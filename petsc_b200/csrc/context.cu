@@ -132,6 +132,15 @@ extern "C" int b200MallocHost(void **p, size_t bytes)
   B200_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
   return 0;
 }
+/* pinned host memory that kernels can write: *d_ptr is the device alias of *h_ptr.  A kernel that leaves its scalar result here
+   saves the host one cudaMemcpy per reduction: the host reads *h_ptr after synchronising the stream (cf. the mapped result
+   slots of the reduction kernels). */
+extern "C" int b200MallocMapped(void **h_ptr, void **d_ptr, size_t bytes)
+{
+  B200_CUDA(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocMapped));
+  B200_CUDA(cudaHostGetDevicePointer(d_ptr, *h_ptr, 0));
+  return 0;
+}
 extern "C" int b200FreeHost(void *p)
 {
   if (p) B200_CUDA(cudaFreeHost(p));

@@ -56,8 +56,12 @@ struct b200CsrPlan_s {
   int        hints_auto;
   double     span_bytes;       /* mean bytes of x spanned by one row ((last col - first col) * 8): how scattered the gather is */
   int        vec_lanes;        /* > 0: rows are handled by the streaming CSR-vector kernel with this many lanes per row */
-  int       *d_longrows;       /* rows longer than SPMV_LONG_ROW (power-law tails): one CTA each in csr_spmv_longrow_kernel */
+  int       *d_longrows;       /* rows longer than SPMV_LONG_ROW (power-law tails), handled by the long-row bin: */
   int        nlong;
+  int4      *d_longseg;        /* their entries cut into segments of SPMV_LONG_ROW: (row slot q, k0, k1, index of the row's first segment) */
+  int       *d_longfirst;      /* [nlong+1] first segment of every long row */
+  double    *d_longpart;       /* one partial sum per segment */
+  int        nlongseg;
   struct CsrBlocks *blk;       /* column-blocked copy (b200CsrPlanSetColumnBlocks) or NULL */
 };
 
@@ -431,34 +435,47 @@ __global__ void __launch_bounds__(256) csr_spmv_vector_kernel(int m, const int *
     }
   }
 }
-/* the long-row bin: one CTA per row, 256 threads x 4 independent gathers, block reduction in fixed order */
-__global__ void __launch_bounds__(256) csr_spmv_longrow_kernel(int nlong, const int *__restrict__ rows, const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ val,
-                                                               const double *__restrict__ x, const double *__restrict__ yin, const double *__restrict__ dinv, double *__restrict__ yout, double *__restrict__ yplain)
+/* the long-row bin: the entries of a long row are cut into segments of SPMV_LONG_ROW; one CTA per SEGMENT (256 threads x 4
+   independent gathers, block reduction in fixed order) leaves a partial sum, a second small kernel adds the partials of a row in
+   segment order and applies the epilogue -- deterministic, and a 600 k-entry row is spread over 74 CTAs instead of one */
+__global__ void __launch_bounds__(256) csr_spmv_longseg_kernel(int nseg, const int4 *__restrict__ seg, const int *__restrict__ colidx, const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ part)
 {
-  __shared__ double part[8];
-  for (int q = blockIdx.x; q < nlong; q += gridDim.x) {
-    const int r = rows[q], k0 = rowptr[r], k1 = rowptr[r + 1];
-    double    s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int       k = k0 + threadIdx.x;
-    for (; k + 3 * 256 < k1; k += 4 * 256) {
+  __shared__ double red[8];
+  for (int q = blockIdx.x; q < nseg; q += gridDim.x) {
+    const int4 sg = seg[q];
+    double     s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int        k = sg.y + threadIdx.x;
+    for (; k + 3 * 256 < sg.z; k += 4 * 256) {
       const int    c0 = ld_stream_s32(colidx + k), c1 = ld_stream_s32(colidx + k + 256), c2 = ld_stream_s32(colidx + k + 512), c3 = ld_stream_s32(colidx + k + 768);
       const double a0 = ld_stream_f64(val + k), a1 = ld_stream_f64(val + k + 256), a2 = ld_stream_f64(val + k + 512), a3 = ld_stream_f64(val + k + 768);
       s0 = fma(a0, __ldg(x + c0), s0); s1 = fma(a1, __ldg(x + c1), s1); s2 = fma(a2, __ldg(x + c2), s2); s3 = fma(a3, __ldg(x + c3), s3);
     }
-    for (; k < k1; k += 256) s0 = fma(ld_stream_f64(val + k), __ldg(x + ld_stream_s32(colidx + k)), s0);
+    for (; k < sg.z; k += 256) s0 = fma(ld_stream_f64(val + k), __ldg(x + ld_stream_s32(colidx + k)), s0);
     double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
-      if (yin) t += yin[r];
-      if (yplain) yplain[r] = t;
-      yout[r] = dinv ? t * dinv[r] : t;
-    }
+    if (threadIdx.x == 0) part[q] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
     __syncthreads();
   }
+}
+__global__ void csr_spmv_longfinal_kernel(int nlong, const int *__restrict__ rows, const int *__restrict__ first, const double *__restrict__ part, const double *__restrict__ yin, const double *__restrict__ dinv,
+                                          double *__restrict__ yout, double *__restrict__ yplain)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nlong) return;
+  const int r = rows[q];
+  double    t = 0.0;
+  for (int k = first[q]; k < first[q + 1]; k++) t += part[k]; /* segment order */
+  if (yin) t += yin[r];
+  if (yplain) yplain[r] = t;
+  yout[r] = dinv ? t * dinv[r] : t;
+}
+__global__ void csr_longrow_ext_kernel(int nlong, const int *__restrict__ rows, const int *__restrict__ rowptr, int2 *ext)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nlong) ext[q] = make_int2(rowptr[rows[q]], rowptr[rows[q] + 1]);
 }
 __global__ void csr_longrow_list_kernel(int m, const int *__restrict__ rowptr, int *list, int *count)
 {
@@ -474,9 +491,10 @@ static int spmv_vector_launch(b200Handle h, b200CsrPlan p, const double *val, co
   csr_spmv_vector_kernel<G><<<(int)g, 256, 0, h->stream>>>(p->m, p->d_rowptr, p->d_colidx, val, x, yin, dinv, yout, yplain, p->nlong > 0);
   B200_LAUNCHED(1);
   if (p->nlong > 0) {
-    int gl = p->nlong < h->num_sms * 8 ? p->nlong : h->num_sms * 8;
-    csr_spmv_longrow_kernel<<<gl, 256, 0, h->stream>>>(p->nlong, p->d_longrows, p->d_rowptr, p->d_colidx, val, x, yin, dinv, yout, yplain);
-    B200_LAUNCHED(1);
+    int gl = p->nlongseg < h->num_sms * 8 ? p->nlongseg : h->num_sms * 8;
+    csr_spmv_longseg_kernel<<<gl, 256, 0, h->stream>>>(p->nlongseg, p->d_longseg, p->d_colidx, val, x, p->d_longpart);
+    csr_spmv_longfinal_kernel<<<(p->nlong + 127) / 128, 128, 0, h->stream>>>(p->nlong, p->d_longrows, p->d_longfirst, p->d_longpart, yin, dinv, yout, yplain);
+    B200_LAUNCHED(2);
   }
   B200_KERNEL_CHECK();
   return 0;
@@ -612,6 +630,33 @@ extern "C" int b200CsrPlanCreate(b200Handle h, int m, int n, int64_t nnz, const 
       B200_CUDA(cudaStreamSynchronize(h->stream));
       cudaFree(d_cnt);
       p->nlong = cnt;
+      if (cnt > 0) { /* cut the long rows into segments (host: a handful of rows) */
+        int2 *d_ext = NULL, *ext = (int2 *)malloc(sizeof(int2) * (size_t)cnt);
+        B200_CUDA(cudaMalloc(&d_ext, sizeof(int2) * (size_t)cnt));
+        csr_longrow_ext_kernel<<<(cnt + 127) / 128, 128, 0, h->stream>>>(cnt, p->d_longrows, d_rowptr, d_ext);
+        B200_LAUNCHED(1);
+        B200_CUDA(cudaMemcpyAsync(ext, d_ext, sizeof(int2) * (size_t)cnt, cudaMemcpyDeviceToHost, h->stream));
+        B200_CUDA(cudaStreamSynchronize(h->stream));
+        cudaFree(d_ext);
+        int64_t nseg = 0;
+        for (int q = 0; q < cnt; q++) nseg += ((int64_t)(ext[q].y - ext[q].x) + SPMV_LONG_ROW - 1) / SPMV_LONG_ROW;
+        int4 *seg   = (int4 *)malloc(sizeof(int4) * (size_t)(nseg + 1));
+        int  *first = (int *)malloc(sizeof(int) * (size_t)(cnt + 1));
+        int   w     = 0;
+        for (int q = 0; q < cnt; q++) {
+          first[q] = w;
+          for (int k0 = ext[q].x; k0 < ext[q].y; k0 += SPMV_LONG_ROW) seg[w++] = make_int4(q, k0, k0 + SPMV_LONG_ROW < ext[q].y ? k0 + SPMV_LONG_ROW : ext[q].y, first[q]);
+        }
+        first[cnt]  = w;
+        p->nlongseg = w;
+        B200_CUDA(cudaMalloc(&p->d_longseg, sizeof(int4) * (size_t)(w + 1)));
+        B200_CUDA(cudaMalloc(&p->d_longfirst, sizeof(int) * (size_t)(cnt + 1)));
+        B200_CUDA(cudaMalloc(&p->d_longpart, sizeof(double) * (size_t)(w + 1)));
+        B200_CUDA(cudaMemcpyAsync(p->d_longseg, seg, sizeof(int4) * (size_t)w, cudaMemcpyHostToDevice, h->stream));
+        B200_CUDA(cudaMemcpyAsync(p->d_longfirst, first, sizeof(int) * (size_t)(cnt + 1), cudaMemcpyHostToDevice, h->stream));
+        B200_CUDA(cudaStreamSynchronize(h->stream));
+        free(ext); free(seg); free(first);
+      }
     }
   }
   plan_configure(p);
@@ -635,7 +680,7 @@ extern "C" int b200CsrPlanDestroy(b200CsrPlan plan)
 {
   if (plan) {
     csr_blocks_free(plan->blk);
-    cudaFree(plan->d_longrows);
+    cudaFree(plan->d_longrows); cudaFree(plan->d_longseg); cudaFree(plan->d_longfirst); cudaFree(plan->d_longpart);
   }
   free(plan);
   return 0;

@@ -134,6 +134,7 @@ typedef struct {
   double *d;      /* device mirror */
   int     mask;
   double *d_sumsq; /* fused MAXPY+norm */
+  double *h_sumsq; /* non-NULL: d_sumsq is the device alias of this mapped pinned host scalar (one rank: no all-reduce on it) */
   PetscObjectState sumsq_state;
   struct PB_Slab  *slab;       /* VecDuplicateVecs: d points into one shared device allocation (bvec2.c:670-691) */
   double          *lv_saved_d; /* VecGetLocalVector*: this vector's own device array while it aliases another's */
@@ -461,7 +462,13 @@ static PetscErrorCode VecMAXPY_SeqB200(Vec x, PetscInt nv, const PetscScalar *al
   PetscCall(PetscMalloc1(nv, &yp));
   for (PetscInt j = 0; j < nv; j++) PetscCall(PB_VecRead(y[j], &yp[j]));
   PetscCall(PB_VecRW(x, &dx));
-  if (!b->d_sumsq) PetscCallB200(b200Malloc(PB_h, (void **)&b->d_sumsq, sizeof(double)));
+  if (!b->d_sumsq) {
+    /* one rank: the kernel writes |x|^2 straight into mapped pinned host memory, VecNorm then only synchronises the stream (no
+       cudaMemcpy on the critical path of every iteration: config 1 is latency bound); several ranks: device memory, because the
+       value is all-reduced by NCCL first */
+    if (PB_size == 1) PetscCallB200(b200MallocMapped((void **)&b->h_sumsq, (void **)&b->d_sumsq, sizeof(double)));
+    else PetscCallB200(b200Malloc(PB_h, (void **)&b->d_sumsq, sizeof(double)));
+  }
   /* one pass, reference association (bit-identical to VecMAXPY_Seq) + ||x||^2 of the result for the VecNorm that
      KSPGMRESCycle issues next; the interface bumps the object state right after this returns (rvector.c:1385) */
   PetscCallB200(b200VecMAXPYAsync(PB_h, N_(x), (int)nv, alpha, yp, dx, b->d_sumsq));
@@ -479,7 +486,10 @@ static PetscErrorCode VecNorm_SeqB200(Vec x, NormType type, PetscReal *z)
   PetscCall(PetscObjectStateGet((PetscObject)x, &st));
   if ((type == NORM_2 || type == NORM_FROBENIUS) && b->d_sumsq && b->sumsq_state == st) {
     double ss;
-    PetscCallB200(b200MemcpyDtoH(PB_h, &ss, b->d_sumsq, sizeof(double)));
+    if (b->h_sumsq) {
+      PetscCallB200(b200Synchronize(PB_h));
+      ss = *(volatile double *)b->h_sumsq;
+    } else PetscCallB200(b200MemcpyDtoH(PB_h, &ss, b->d_sumsq, sizeof(double)));
     *z = PetscSqrtReal(ss);
     PetscFunctionReturn(PETSC_SUCCESS);
   }
@@ -502,7 +512,9 @@ static PetscErrorCode VecDestroy_SeqB200(Vec v)
         PetscCall(PetscFree(b->slab));
       }
     } else if (b->d) PetscCallB200(b200Free(PB_h, b->d));
-    if (b->d_sumsq) PetscCallB200(b200Free(PB_h, b->d_sumsq));
+    if (b->h_sumsq) PetscCallB200(b200FreeHost(b->h_sumsq));
+    else if (b->d_sumsq) PetscCallB200(b200Free(PB_h, b->d_sumsq));
+    b->h_sumsq = NULL;
     if (b->host_owned) {
       if (b->seq.array == b->host_owned) b->seq.array = NULL;
       PetscCall(PetscFree(b->host_owned));

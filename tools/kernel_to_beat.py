@@ -124,6 +124,26 @@ def main():
         n = nr if d < 512 else nr // 4
         spmv_case("random d=%d" % d, n, n * d, lambda i, j, v, n=n, d=d: _capi.check(L.b200GenRandomCsr(H.h, n, n, d, C.c_uint64(20260923 + d), i.ptr, j.ptr, v.ptr)))
 
+    # ---- a power-law matrix: 2.5 M scattered rows of 4 entries + a tail of very long rows (row bins vs one library call)
+    if not a.small:
+        from oracle import oracle_py as O   # generator of the test inputs only
+        npl = 2_500_000
+        rng = np.random.default_rng(33)
+        ai0, aj0, aa0 = O.random_csr(npl, 4, 5)
+        lens = np.full(npl, 4, np.int64)
+        longrows = {7: 600_000, 1000: 120_000, 123_456: 40_000, 2_000_001: 9_000, npl - 1: 20_000}
+        for r, l in longrows.items():
+            lens[r] = l
+        ai = np.zeros(npl + 1, np.int64); ai[1:] = np.cumsum(lens)
+        aj = np.empty(ai[-1], np.int32); av = np.empty(ai[-1])
+        short = np.ones(npl, bool); short[list(longrows)] = False
+        inew = (ai[:-1][short][:, None] + np.arange(4)[None, :]).ravel(); iold = (ai0[:-1].astype(np.int64)[short][:, None] + np.arange(4)[None, :]).ravel()
+        aj[inew] = aj0[iold]; av[inew] = aa0[iold]
+        for r, l in longrows.items():
+            aj[ai[r]:ai[r + 1]] = np.sort(rng.choice(npl, l, replace=False)).astype(np.int32); av[ai[r]:ai[r + 1]] = rng.uniform(-1, 1, l)
+        ai32 = ai.astype(np.int32)
+        spmv_case("power-law 2.5M rows (4/row + tail to 600k)", npl, int(ai[-1]), lambda i, j, v: (i.upload(ai32), j.upload(aj), v.upload(av)))
+
     # ---- BLAS-1 / orthogonalisation at the size of the headline workload
     n = (128 if a.small else 512) ** 3
     nv = 30
