@@ -12,7 +12,7 @@ set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"; ROOT="$(dirname "$HERE")"
 REF=/root/reference
 BLASDIR=/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs
-OUT="$(dirname "$HERE")/baseline/_ref/petsc"; mkdir -p "$OUT/bin"
+OUT="$(dirname "$HERE")/baseline/_ref/petsc"; mkdir -p "$OUT/bin" "$HERE/_ref"
 [ -e "$OUT/lib/libpetsc.so" ] && [ -e "$OUT/include/petscconf.h" ] && [ -d "$REF/include" ] || { echo "no reference library in $OUT (run oracle/build_ref.sh in the build container): skipping the reference demo build"; exit 0; }
 # headers: the reference's own include tree where it lies + the generated headers build_ref.sh installed next to the library
 INC="-I$REF/include -I$OUT/include"
