@@ -1047,6 +1047,10 @@ static int sweeps_launch(b200Handle h, b200IluPlan p, const double *b, double *x
     if (!occ) {
       B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ilu_sweep_pipe_kernel<G, true>, ILU_TPB, 0));
       if (occ < 1) occ = 1;
+      { /* experiments: PETSCB200_ILU_CTAS_PER_SM caps the resident grid of the level-scheduled sweeps */
+        const char *e = getenv("PETSCB200_ILU_CTAS_PER_SM");
+        if (e && atoi(e) > 0 && atoi(e) < occ) occ = atoi(e);
+      }
       B200_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
     }
     int gL = gridL, gU = gridU;
