@@ -118,3 +118,35 @@ def test_mpiaij_split_and_halo_plan_match_oracle(oracle, size):
             for p in range(size):
                 seg = g[ro[p]:ro[p] + rc[p]]
                 assert np.all((seg >= rs[p]) & (seg < rs[p + 1]))
+
+
+def test_mpiaij_setup_helpers_index_exact_on_cpu(oracle):
+    """The host half of MatSetUpMultiply_MPIAIJ that the PETSc plugin and the harness share (b200MpiaijSplitHost,
+    b200MpiaijBuildGarray: plain C inside libpetscb200.so, no device needed) against the oracle's restatement of mmaij.c:25-61:
+    diagonal / off-diagonal blocks, garray and the renumbered off-diagonal columns, for 1, 2, 3 and 5 ranks."""
+    L = _capi.lib()
+    for name, (ai, aj, aa) in (("lap5", oracle.lap5(13, 9)), ("lap7", oracle.lap7(7, 6, 9)), ("rand", oracle.random_csr(203, 7, 3))):
+        n = len(ai) - 1
+        for size in (1, 2, 3, 5):
+            rs = oracle.split_ownership(n, size)
+            for rank in range(size):
+                r0, r1 = int(rs[rank]), int(rs[rank + 1])
+                m = r1 - r0
+                lai = np.ascontiguousarray(ai[r0:r1 + 1] - ai[r0], np.int32)
+                laj = np.ascontiguousarray(aj[ai[r0]:ai[r1]], np.int32); laa = np.ascontiguousarray(aa[ai[r0]:ai[r1]])
+                nzA, nzB = C.c_int64(), C.c_int64()
+                vp = C.c_void_p
+                p = lambda a: a.ctypes.data_as(vp)   # noqa: E731
+                _capi.check(L.b200MpiaijSplitHost(m, r0, r1, p(lai), p(laj), p(laa), C.byref(nzA), C.byref(nzB), None, None, None, None, None, None))
+                Ai, Bi = np.zeros(m + 1, np.int32), np.zeros(m + 1, np.int32)
+                Aj, Bj = np.zeros(nzA.value + 1, np.int32), np.zeros(nzB.value + 1, np.int32)
+                Aa, Ba = np.zeros(nzA.value + 1), np.zeros(nzB.value + 1)
+                _capi.check(L.b200MpiaijSplitHost(m, r0, r1, p(lai), p(laj), p(laa), C.byref(nzA), C.byref(nzB), p(Ai), p(Aj), p(Aa), p(Bi), p(Bj), p(Ba)))
+                g, ec = vp(), C.c_int()
+                _capi.check(L.b200MpiaijBuildGarray(C.c_int64(nzB.value), p(Bj), C.byref(g), C.byref(ec)))
+                garray = np.ctypeslib.as_array(C.cast(g, C.POINTER(C.c_int)), shape=(max(ec.value, 1),))[:ec.value].copy()
+                _capi.check(L.b200HostFree(g))
+                oA, oB, og = oracle.mpiaij_split(lai, laj.astype(np.int64), laa, r0, r1)
+                assert np.array_equal(garray, og), (name, size, rank)
+                assert np.array_equal(Ai, oA[0]) and np.array_equal(Aj[:nzA.value], oA[1]) and np.array_equal(Aa[:nzA.value], oA[2]), (name, size, rank)
+                assert np.array_equal(Bi, oB[0]) and np.array_equal(Bj[:nzB.value], oB[1]) and np.array_equal(Ba[:nzB.value], oB[2]), (name, size, rank)
