@@ -124,3 +124,18 @@ def test_plugin_driver_device_coo_transpose_bindtocpu():
                  "matmulttranspose_bit_exact", "matmulttransposeadd_bit_exact", "matmulttransposeadd_inplace_bit_exact", "matmulttranspose_after_matscale",
                  "current_memtype_is_device", "matmult_bound_to_cpu"):
         assert "ok " + name in out, out
+
+
+@pytest.mark.skipif(not have(), reason="baseline/_ref/petsc not built (needs the build container)")
+def test_ex2_pipecgb200_registered_ksp_matches_reference_pipecg():
+    """KSPRegister("pipecgb200") (single-reduction CG with fused recurrences) inside the reference's own ex2: the residual history
+    equals the reference's KSPPIPECG on its CPU types to 1e-10 over the first 30 iterations, same iteration count."""
+    opts = ["-m", "40", "-n", "35", "-pc_type", "jacobi", "-ksp_monitor", "-ksp_rtol", "1e-8"]
+    a = run("ex2", opts + ["-ksp_type", "pipecgb200"] + B200)
+    b = run("ex2", opts + ["-ksp_type", "pipecg"])
+    ha, hb = history(a), history(b)
+    assert abs(len(ha) - len(hb)) <= 1
+    k = min(len(ha), len(hb), 31)
+    assert np.allclose(ha[:k], hb[:k], rtol=1e-10, atol=2e-12 * hb[0])
+    view = run("ex2", ["-m", "8", "-n", "8", "-ksp_type", "pipecgb200", "-pc_type", "jacobi", "-ksp_view"] + B200)
+    assert "pipecgb200" in view and "seqaijb200" in view
