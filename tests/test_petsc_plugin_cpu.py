@@ -1,0 +1,56 @@
+"""Host-side behaviour of the PETSc plugin WITHOUT a GPU (the build container): the reference's own ex2 loads
+libpetscb200plugin.so with -dll_append;
+  * the registrations do not disturb the reference's CPU types: -pc_type jacobi (now the plugin's sub-class of PCJACOBI) and the
+    registered KSP pipecgb200 give the stock results on -mat_type aij -vec_type standard, without touching CUDA;
+  * the b200 types fail loudly with PETSC_ERR_GPU -- there is no CPU fallback behind -mat_type aijb200 -vec_type b200.
+Skipped where the reference library is absent or a GPU is visible (the GPU suite covers that side)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EX2 = os.path.join(ROOT, "baseline", "_ref", "petsc", "bin", "ex2")
+PLUGIN = os.path.join(ROOT, "petsc_plugin", "libpetscb200plugin.so")
+BLASDIR = "/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs"
+
+
+def gpu_visible():
+    from petsc_b200 import _capi
+    n = C.c_int(0)
+    return _capi.lib().b200DeviceCount(C.byref(n)) == 0 and n.value > 0
+
+
+pytestmark = pytest.mark.skipif(not (os.path.exists(EX2) and os.path.exists(PLUGIN)) or gpu_visible(), reason="needs baseline/_ref/petsc (build container) and no GPU")
+
+
+def ex2(args):
+    env = dict(os.environ, LD_LIBRARY_PATH=BLASDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    return subprocess.run([EX2] + args, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+
+
+def last(out):
+    return [l for l in out.stdout.splitlines() if l.startswith("Norm of error")][-1]
+
+
+def test_plugin_leaves_cpu_types_untouched():
+    base = ["-m", "12", "-n", "11"]
+    for opts in (["-pc_type", "jacobi"], ["-pc_type", "jacobi", "-ksp_type", "cg"], ["-pc_type", "jacobi", "-pc_jacobi_type", "rowmax"], ["-pc_type", "ilu"], []):
+        a, b = ex2(base + opts + ["-dll_append", PLUGIN]), ex2(base + opts)
+        assert a.returncode == 0 and b.returncode == 0, a.stdout + a.stderr
+        assert last(a) == last(b), (opts, last(a), last(b))
+    # the registered KSP runs on host vectors through the eight BLAS-1 calls: same iterates as the reference's KSPPIPECG
+    a = ex2(base + ["-pc_type", "jacobi", "-ksp_type", "pipecgb200", "-dll_append", PLUGIN])
+    b = ex2(base + ["-pc_type", "jacobi", "-ksp_type", "pipecg"])
+    assert a.returncode == 0 and last(a) == last(b), a.stdout + a.stderr
+    view = ex2(base + ["-pc_type", "jacobi", "-ksp_view", "-dll_append", PLUGIN]).stdout
+    assert re.search(r"type: jacobi", view) and "seqaij" in view and "b200" not in view
+
+
+def test_b200_types_fail_loudly_without_gpu():
+    out = ex2(["-m", "5", "-n", "5", "-dll_append", PLUGIN, "-mat_type", "aijb200", "-vec_type", "b200"])
+    assert out.returncode != 0
+    err = out.stdout + out.stderr
+    assert "GPU error" in err and "petscb200 error 97" in err       # PETSC_ERR_GPU from PB_Init: no CPU fallback
