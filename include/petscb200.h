@@ -52,6 +52,7 @@ int         b200Destroy(b200Handle h);
 int         b200SetStream(b200Handle h, void *cudaStream);  /* cudaStream_t; NULL restores the handle's own stream */
 int         b200GetStream(b200Handle h, void **cudaStream);
 int         b200Synchronize(b200Handle h);
+int         b200DeviceSynchronize(void);                    /* every stream of the current device (cudaDeviceSynchronize): for callers that mix handles */
 int         b200GetDevice(b200Handle h, int *device);
 int         b200DeviceCount(int *n);
 const char *b200GetLastErrorString(void);
@@ -298,6 +299,25 @@ int b200CsrTransposeSpMV(b200Handle h, b200CsrTranspose T, const double *d_x, co
 int b200CsrTransposeGetPlan(b200CsrTranspose T, b200CsrPlan *plan);
 /* copies the transposed pattern (tptr[n+1], trow[nnz]) and the value permutation tperm[nnz] to HOST arrays (tests) */
 int b200CsrTransposeGet(b200Handle h, b200CsrTranspose T, int *h_tptr, int *h_trow, int *h_tperm);
+
+/* ---- local star-forest broadcast / reduction on device data -------------------------------------------
+ * replaces PetscSFLinkScatterLocal (sfpack.c:1082) with the host ScatterAnd<Op> loops of sfpack.c:190-222 (reference device
+ * path: the d_ScatterAnd<Op> kernels of src/vec/is/sf/impls/basic/cupm): for i = 0 .. n-1 IN THIS ORDER
+ *     dst[didx[i]*bs + c] = dst[didx[i]*bs + c] <op> src[sidx[i]*bs + c],   c < bs.
+ * sidx / didx are HOST int arrays (NULL = contiguous from s0 / d0); the plan copies what it needs to the device.  Entries that
+ * share a destination are applied in entry order (stable grouping, no atomics), so sums equal the reference's bit for bit.
+ * dtype: B200_SF_F64 (PetscScalar / PetscReal) or B200_SF_I32 (PetscInt); op: the MPI_Op a VecScatter can ask for
+ * (vscat.c:62-66) plus MPI_PROD.  d_src == d_dst (an in-place scatter has sequential semantics) is B200_ERR_SUP. */
+enum { B200_SF_F64 = 0, B200_SF_I32 = 1 };
+enum { B200_SF_REPLACE = 0, B200_SF_SUM = 1, B200_SF_PROD = 2, B200_SF_MAX = 3, B200_SF_MIN = 4 };
+typedef struct b200IndexedPlan_s *b200IndexedPlan;
+int b200IndexedPlanCreate(b200Handle h, int64_t n, const int *h_sidx, int s0, const int *h_didx, int d0, b200IndexedPlan *plan);
+int b200IndexedPlanDestroy(b200Handle h, b200IndexedPlan plan);
+/* the host half of the plan (no device): contiguity, extents and the stable grouping by destination; gdst[ngroups], goff[ngroups+1],
+   gsrc[n] are malloc'ed (b200HostFree) when *grouped, else NULL */
+int b200IndexedGroupHost(int64_t n, const int *h_sidx, int s0, const int *h_didx, int d0, int *src_contig, int *dst_contig, int64_t *src_extent, int64_t *dst_extent, int *grouped, int64_t *ngroups, int **gdst, int **goff, int **gsrc);
+int b200IndexedPlanGetInfo(b200IndexedPlan plan, int64_t *n, int64_t *ngroups, int *grouped, int *src_contig, int *dst_contig, int64_t *src_extent, int64_t *dst_extent);
+int b200IndexedOp(b200Handle h, b200IndexedPlan plan, int dtype, int bs, int op, const void *d_src, void *d_dst);
 
 /* ---- device-side generators of the benchmark operators (bench/test utility; SURVEY 8d inputs) ---- */
 /* rows [r0,r1) of the 7-point nx*ny*nz Laplacian, local row pointer, GLOBAL 32-bit columns */

@@ -6,6 +6,7 @@
 #   oracle/_ref/ref_driver                 oracle/ref_driver.c (our driver against the reference's public API)
 #   petsc_plugin/libpetscb200plugin.so     the plugin, built against exactly this PETSc
 #   baseline/_ref/petsc/bin/plugin_driver    petsc_plugin/plugin_driver.c (our PETSc program for device COO / transposed products)
+#   baseline/_ref/petsc/bin/sf_driver        petsc_plugin/sf_driver.c (our PETSc program for VecScatter / PetscSF on device data)
 #   petsc_plugin/b200_driver, libb200driver.so   petsc_plugin/b200_driver.c (our PETSc program for the BASELINE workloads)
 # Only runs in the build container (needs /root/reference and the configured PETSc build).  No reference SOURCE is copied.
 set -e
@@ -24,6 +25,8 @@ done
 make -s -C "$ROOT/petsc_plugin" PETSC_INC="$INC" PETSC_LIBDIR="$OUT/lib"
 # a PETSc program for the plugin paths the tutorials do not reach (device COO, MatMultTranspose, MatBindToCPU)
 /usr/bin/gcc -O2 -o "$OUT/bin/plugin_driver" "$ROOT/petsc_plugin/plugin_driver.c" $INC -I"$ROOT/include" $LNK -L"$ROOT/petsc_b200/lib" -lpetscb200 -Wl,-rpath,\$ORIGIN/../../../../petsc_b200/lib
+# VecScatter / PetscSF on device vectors against the host types (tests/test_petsc_plugin_{cpu,gpu}.py)
+/usr/bin/gcc -O2 -std=gnu11 -Wall -o "$OUT/bin/sf_driver" "$ROOT/petsc_plugin/sf_driver.c" $INC -I"$ROOT/include" $LNK -L"$ROOT/petsc_b200/lib" -lpetscb200 -Wl,-rpath,\$ORIGIN/../../../../petsc_b200/lib
 # the PETSc program that runs the BASELINE workloads on the b200 types (bench.py, tools/, GPU tests): executable + shared object
 DRV_LNK="-L$ROOT/petsc_plugin -lpetscb200plugin -L$ROOT/petsc_b200/lib -lpetscb200 -L$OUT/lib -lpetsc -Wl,-rpath,\$ORIGIN -Wl,-rpath,\$ORIGIN/../petsc_b200/lib -Wl,-rpath,\$ORIGIN/../baseline/_ref/petsc/lib -Wl,-rpath,$BLASDIR -Wl,-rpath-link,$BLASDIR -Wl,--allow-shlib-undefined -lm"
 /usr/bin/gcc -O2 -g -std=gnu11 -Wall -Wno-unused-parameter -Wno-format-truncation -o "$ROOT/petsc_plugin/b200_driver" "$ROOT/petsc_plugin/b200_driver.c" $INC -I"$ROOT/include" $DRV_LNK

@@ -158,6 +158,29 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
         print(name, "n", n, "nnz", len(rec["ref_aj"]))
 
+    # ---- PetscSF local broadcast / reduction: every MPI_Op a VecScatter can ask for + PROD, unit = bs scalars; roots
+    # with several leaves pin the order of application (PetscSFSetGraph sorts the leaves by location, sf.c:500)
+    srng = np.random.default_rng(20260925)
+    sfc = {"sf_rand_bs1": (300, 700, 900, 1), "sf_rand_bs3": (120, 260, 400, 3), "sf_contig_leaves": (64, 200, 200, 1), "sf_empty": (5, 0, 4, 1)}
+    for name, (nroots, nleaves, leafspan, bs) in sfc.items():
+        local = srng.permutation(leafspan)[:nleaves].astype(np.int32) if name != "sf_contig_leaves" else np.arange(nleaves, dtype=np.int32)
+        remote = srng.integers(0, nroots, nleaves).astype(np.int32)
+        root, leaf = srng.uniform(-1, 1, nroots * bs), srng.uniform(-1, 1, leafspan * bs)
+        rooti, leafi = srng.integers(-1000, 1000, nroots).astype(np.int32), srng.integers(-1000, 1000, leafspan).astype(np.int32)
+        env = dict(os.environ)
+        env["LD_LIBRARY_PATH"] = "%s:%s:%s" % (REFLIB, BLASDIR, env.get("LD_LIBRARY_PATH", ""))
+        with tempfile.TemporaryDirectory() as d:
+            for fn, arr in (("local.i32", local), ("remote.i32", remote), ("root.f64", root), ("leaf.f64", leaf), ("root.i32", rooti), ("leaf.i32", leafi)):
+                np.ascontiguousarray(arr).tofile(os.path.join(d, fn))
+            open(os.path.join(d, "meta_sf.txt"), "w").write("%d %d %d %d\n" % (nroots, nleaves, leafspan, bs))
+            subprocess.check_call([exe, "-sf", d], env=env)
+            rec = dict(nroots=nroots, leafspan=leafspan, bs=bs, local=local, remote=remote, root=root, leaf=leaf, rooti=rooti, leafi=leafi)
+            for f in sorted(os.listdir(d)):
+                if f.startswith("ref_"):
+                    rec[f.replace(".f64", "").replace(".i32", "_i32")] = np.fromfile(os.path.join(d, f), np.float64 if f.endswith(".f64") else np.int32)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print(name, "nleaves", nleaves)
+
     # ---- KSP cases: matrix by generator, b = A*1, reference options recorded ----
     ksp = {
         # ex2_1.out: -m 5 -n 5 -ksp_gmres_cgs_refinement_type refine_always, default PC (ILU), ex2.c rtol = 1e-2/((m+1)(n+1))

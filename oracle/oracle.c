@@ -1237,3 +1237,41 @@ void ora_matsolve_icc(int n, const int *ui, const int *uj, const int *udiag, con
     x[i] = xi;
   }
 }
+
+/* ---- PetscSF local scatter: PetscSFLinkScatterLocal (sfpack.c:1082) with the ScatterAnd<Op> loop of sfpack.c:211-218 ----
+   for i in order: dst[didx[i]*bs + c] = dst[...] op src[sidx[i]*bs + c]; NULL index = contiguous from 0.
+   op: 0 REPLACE (OP_ASSIGN), 1 SUM, 2 PROD (OP_BINARY), 3 MAX, 4 MIN (OP_FUNCTION with PetscMax / PetscMin, petscmath.h) */
+void ora_sf_scatter_f64(int64_t n, int bs, int op, const int *sidx, const int *didx, const double *src, double *dst)
+{
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t s = (int64_t)(sidx ? sidx[i] : i) * bs, t = (int64_t)(didx ? didx[i] : i) * bs;
+    for (int c = 0; c < bs; c++) {
+      const double u = src[s + c];
+      double      *v = &dst[t + c];
+      switch (op) {
+      case 0: *v = u; break;
+      case 1: *v = *v + u; break;
+      case 2: *v = *v * u; break;
+      case 3: *v = (*v < u) ? u : *v; break;
+      case 4: *v = (*v < u) ? *v : u; break;
+      }
+    }
+  }
+}
+void ora_sf_scatter_i32(int64_t n, int bs, int op, const int *sidx, const int *didx, const int *src, int *dst)
+{
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t s = (int64_t)(sidx ? sidx[i] : i) * bs, t = (int64_t)(didx ? didx[i] : i) * bs;
+    for (int c = 0; c < bs; c++) {
+      const int u = src[s + c];
+      int      *v = &dst[t + c];
+      switch (op) {
+      case 0: *v = u; break;
+      case 1: *v = (int)((unsigned)*v + (unsigned)u); break;
+      case 2: *v = (int)((unsigned)*v * (unsigned)u); break;
+      case 3: *v = (*v < u) ? u : *v; break;
+      case 4: *v = (*v < u) ? *v : u; break;
+      }
+    }
+  }
+}

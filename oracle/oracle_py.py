@@ -283,6 +283,23 @@ def coo_setvalues(jmap, perm, v, Aa=None):
     return out
 
 
+SF_OPS = {"replace": 0, "sum": 1, "prod": 2, "max": 3, "min": 4}
+
+
+def sf_scatter(sidx, didx, src, dst, op="replace", bs=1):
+    """PetscSFLinkScatterLocal / ScatterAnd<Op> (sfpack.c:190-222, 1082): returns dst after dst[didx[i]] op= src[sidx[i]] in order.
+    float64 or int32 data (by src.dtype); sidx / didx None = contiguous from 0."""
+    n = len(sidx) if sidx is not None else len(didx)
+    si = None if sidx is None else _i32(sidx); di = None if didx is None else _i32(didx)
+    if np.asarray(src).dtype == np.int32:
+        s = _i32(src); d = _i32(dst).copy()
+        lib().ora_sf_scatter_i32(C.c_int64(n), int(bs), SF_OPS[op], None if si is None else _p(si), None if di is None else _p(di), _p(s), _p(d))
+    else:
+        s = _f64(src); d = _f64(dst).copy()
+        lib().ora_sf_scatter_f64(C.c_int64(n), int(bs), SF_OPS[op], None if si is None else _p(si), None if di is None else _p(di), _p(s), _p(d))
+    return d
+
+
 def set_num_threads(n):
     lib().ora_set_num_threads(int(n))
 

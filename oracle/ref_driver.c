@@ -12,6 +12,7 @@
  *          ref_jacobi.f64 ref_dotnorm.f64 ref_hist.f64 ref_sol.f64 ref_ksp.txt
  */
 #include <petscksp.h>
+#include <petscsf.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -114,6 +115,83 @@ static PetscErrorCode coo_case(const char *dir)
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
+/* -sf <dir>: a process-local PetscSF (nroots, leaves at local[], leaf k attached to root remote[k]) through the public API:
+   PetscSFBcast / PetscSFReduce with each MPI_Op on PetscScalar units of bs entries, and SUM / MAX on PetscInt; every run starts
+   from the input root/leaf data.  Outputs ref_bcast_<op>.f64 (leaf data) / ref_reduce_<op>.f64 (root data), *_i32 for PetscInt. */
+static PetscErrorCode sf_case(const char *dir)
+{
+  int           nroots, nleaves, leafspan, bs;
+  PetscInt     *local, *rem, *ri, *li, *ri0, *li0;
+  PetscSFNode  *remote;
+  PetscScalar  *root0, *leaf0, *root, *leaf;
+  PetscSF       sf;
+  MPI_Datatype  unit;
+  char          p[4096];
+  FILE         *f;
+  const struct {
+    MPI_Op      op;
+    const char *name;
+  } ops[] = {{MPI_REPLACE, "replace"}, {MPI_SUM, "sum"}, {MPI_PROD, "prod"}, {MPI_MAX, "max"}, {MPI_MIN, "min"}};
+
+  PetscFunctionBeginUser;
+  snprintf(p, sizeof p, "%s/meta_sf.txt", dir);
+  f = fopen(p, "r");
+  if (!f || fscanf(f, "%d %d %d %d", &nroots, &nleaves, &leafspan, &bs) != 4) exit(2);
+  fclose(f);
+  local = (PetscInt *)rd(dir, "local.i32", sizeof(PetscInt) * (size_t)nleaves);
+  rem   = (PetscInt *)rd(dir, "remote.i32", sizeof(PetscInt) * (size_t)nleaves);
+  root0 = (PetscScalar *)rd(dir, "root.f64", sizeof(PetscScalar) * (size_t)nroots * bs);
+  leaf0 = (PetscScalar *)rd(dir, "leaf.f64", sizeof(PetscScalar) * (size_t)leafspan * bs);
+  ri0   = (PetscInt *)rd(dir, "root.i32", sizeof(PetscInt) * (size_t)nroots);
+  li0   = (PetscInt *)rd(dir, "leaf.i32", sizeof(PetscInt) * (size_t)leafspan);
+  PetscCall(PetscMalloc1(nleaves, &remote));
+  for (int k = 0; k < nleaves; k++) {
+    remote[k].rank  = 0;
+    remote[k].index = rem[k];
+  }
+  PetscCall(PetscMalloc4((size_t)nroots * bs, &root, (size_t)leafspan * bs, &leaf, nroots, &ri, leafspan, &li));
+  PetscCall(PetscSFCreate(PETSC_COMM_SELF, &sf));
+  PetscCall(PetscSFSetGraph(sf, nroots, nleaves, local, PETSC_COPY_VALUES, remote, PETSC_COPY_VALUES));
+  PetscCall(PetscSFSetUp(sf));
+  if (bs > 1) { /* the unit VecScatterCreate makes for block index sets (vscat.c:1087-1090) */
+    PetscCallMPI(MPI_Type_contiguous(bs, MPIU_SCALAR, &unit));
+    PetscCallMPI(MPI_Type_commit(&unit));
+  } else unit = MPIU_SCALAR;
+  for (int o = 0; o < 5; o++) {
+    char name[64];
+    memcpy(root, root0, sizeof(PetscScalar) * (size_t)nroots * bs);
+    memcpy(leaf, leaf0, sizeof(PetscScalar) * (size_t)leafspan * bs);
+    PetscCall(PetscSFBcastBegin(sf, unit, root, leaf, ops[o].op));
+    PetscCall(PetscSFBcastEnd(sf, unit, root, leaf, ops[o].op));
+    snprintf(name, sizeof name, "ref_bcast_%s.f64", ops[o].name);
+    wr(dir, name, leaf, sizeof(PetscScalar) * (size_t)leafspan * bs);
+    memcpy(leaf, leaf0, sizeof(PetscScalar) * (size_t)leafspan * bs);
+    PetscCall(PetscSFReduceBegin(sf, unit, leaf, root, ops[o].op));
+    PetscCall(PetscSFReduceEnd(sf, unit, leaf, root, ops[o].op));
+    snprintf(name, sizeof name, "ref_reduce_%s.f64", ops[o].name);
+    wr(dir, name, root, sizeof(PetscScalar) * (size_t)nroots * bs);
+    if (ops[o].op == MPI_SUM || ops[o].op == MPI_MAX) {
+      memcpy(ri, ri0, sizeof(PetscInt) * (size_t)nroots);
+      memcpy(li, li0, sizeof(PetscInt) * (size_t)leafspan);
+      PetscCall(PetscSFBcastBegin(sf, MPIU_INT, ri, li, ops[o].op));
+      PetscCall(PetscSFBcastEnd(sf, MPIU_INT, ri, li, ops[o].op));
+      snprintf(name, sizeof name, "ref_bcast_%s.i32", ops[o].name);
+      wr(dir, name, li, sizeof(PetscInt) * (size_t)leafspan);
+      memcpy(li, li0, sizeof(PetscInt) * (size_t)leafspan);
+      PetscCall(PetscSFReduceBegin(sf, MPIU_INT, li, ri, ops[o].op));
+      PetscCall(PetscSFReduceEnd(sf, MPIU_INT, li, ri, ops[o].op));
+      snprintf(name, sizeof name, "ref_reduce_%s.i32", ops[o].name);
+      wr(dir, name, ri, sizeof(PetscInt) * (size_t)nroots);
+    }
+  }
+  if (bs > 1) PetscCallMPI(MPI_Type_free(&unit));
+  PetscCall(PetscSFDestroy(&sf));
+  PetscCall(PetscFree4(root, leaf, ri, li));
+  PetscCall(PetscFree(remote));
+  free(local); free(rem); free(root0); free(leaf0); free(ri0); free(li0);
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
 static void *rd(const char *dir, const char *name, size_t bytes)
 {
   char  p[4096];
@@ -158,6 +236,11 @@ int main(int argc, char **argv)
   }
   if (!strcmp(dir, "-coo")) {
     PetscCall(coo_case(argv[2]));
+    PetscCall(PetscFinalize());
+    return 0;
+  }
+  if (!strcmp(dir, "-sf")) {
+    PetscCall(sf_case(argv[2]));
     PetscCall(PetscFinalize());
     return 0;
   }

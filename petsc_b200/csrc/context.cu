@@ -100,6 +100,11 @@ extern "C" int b200Synchronize(b200Handle h)
   B200_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
 }
+extern "C" int b200DeviceSynchronize(void)
+{
+  B200_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
 extern "C" int b200GetDevice(b200Handle h, int *d)
 {
   B200_CHECK(h && d, B200_ERR_ARG_NULL, "null argument");

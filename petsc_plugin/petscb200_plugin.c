@@ -13,6 +13,8 @@
  *                          fused ops->applyBA (src/ksp/pc/interface/pcregis.c, precon.c:810-865)
  *   KSPRegister            "pipecgb200": single-reduction CG, one reduction kernel + one recurrence kernel per iteration
  *   VecRegister            "mpib200";  MatRegister "mpiaijb200": the row-partitioned types over NCCL ranks (one process per GPU)
+ *   PetscSFRegister        "b200" and (unless -b200_keep_sfbasic) "basic": PETSCSFBASIC sub-classed so that VecScatter / PetscSF
+ *                          broadcasts and reductions on device data run as device kernels (src/vec/is/sf/interface/sfregi.c:78)
  *
  * Structure mirrors the reference's own device subclassing (aijcusparse.cu:2807-2868, veccupmimpl.h:994-1047): create the
  * parent (MATSEQAIJ / VECSEQ), keep its host data structures, overwrite the ops of the hot path with functions that run
@@ -2120,6 +2122,285 @@ PETSC_EXTERN PetscErrorCode KSPCreate_PipeCGB200(KSP ksp)
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
+/* ================================================================== PetscSF "b200": PETSCSFBASIC sub-classed for device data
+   (SURVEY 8f.4).  VecScatterBegin hands the SF whatever VecGetArray[Read]AndMemType returns (vscat.c:50-51,70-73): for b200 vectors
+   that is a device pointer tagged PETSC_MEMTYPE_CUDA.  A PETSc configured with a device back end runs its d_ScatterAnd<Op> kernels
+   on such pointers (sfpack.c:759-775); a host-only PETSc has none and would dereference them on the host.  This type keeps every
+   host-memory operation with the parent (PETSCSFBASIC, sfbasic.c:607) and runs the device ones itself:
+     * roots and leaves both on the device, graph local to the process, unit = n x PetscScalar or n x PetscInt, op one of
+       REPLACE/SUM/PROD/MAX/MIN: one b200IndexedOp kernel in Begin (leaf <- leaf op root for a broadcast, root <- root op leaf for a
+       reduction), entries sharing a destination applied in graph order like PetscSFLinkScatterLocal (sfpack.c:1082) -- results
+       equal the reference's host results bit for bit;
+     * anything else that involves device memory (mixed host/device, other units or ops, an in-place scatter, a graph that spans
+       MPI ranks): the device side is staged through a host buffer and the PARENT does the operation -- correct, not fast.
+   Registered as "b200" and, unless -b200_keep_sfbasic, under the name "basic" too so that every VecScatter of a program that
+   runs with -vec_type b200 is covered without an -sf_type option. */
+#include <petsc/private/sfimpl.h>
+#define PETSCSFB200 "b200"
+#define PB_SF_MAXINFLIGHT 8
+static PetscErrorCode (*PB_SFCreate_Basic)(PetscSF) = NULL; /* the reference's creator, looked up at registration */
+
+typedef struct {
+  PetscErrorCode (*bcastbegin)(PetscSF, MPI_Datatype, PetscMemType, const void *, PetscMemType, void *, MPI_Op);
+  PetscErrorCode (*bcastend)(PetscSF, MPI_Datatype, const void *, void *, MPI_Op);
+  PetscErrorCode (*reducebegin)(PetscSF, MPI_Datatype, PetscMemType, const void *, PetscMemType, void *, MPI_Op);
+  PetscErrorCode (*reduceend)(PetscSF, MPI_Datatype, const void *, void *, MPI_Op);
+  PetscErrorCode (*fetchbegin)(PetscSF, MPI_Datatype, PetscMemType, void *, PetscMemType, const void *, void *, MPI_Op);
+  PetscErrorCode (*reset)(PetscSF);
+  b200IndexedPlan bcast, reduce; /* root -> leaf, leaf -> root; built on first device use of the current graph */
+  PetscBool       planned, local;
+  PetscInt        nroots, leafextent;
+  int             ninflight;
+  struct {
+    const void *root, *leaf;
+  } inflight[PB_SF_MAXINFLIGHT]; /* Begin calls this type completed itself: the matching End is a no-op */
+  PetscLogDouble nnative, nstaged; /* operations run by the device kernel / staged through the host (PetscSFView) */
+} SF_B200;
+
+static PetscErrorCode PB_SFCtx(PetscSF sf, SF_B200 **b)
+{
+  PetscContainer c;
+  PetscFunctionBegin;
+  PetscCall(PetscObjectQuery((PetscObject)sf, "PetscSFB200_ctx", (PetscObject *)&c));
+  PetscCheck(c, PetscObjectComm((PetscObject)sf), PETSC_ERR_PLIB, "PetscSF of type b200 without its context");
+  PetscCall(PetscContainerGetPointer(c, (void **)b));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode PB_SFDropPlans(SF_B200 *b)
+{
+  PetscFunctionBegin;
+  if (b->bcast) PetscCallB200(b200IndexedPlanDestroy(PB_h, b->bcast));
+  if (b->reduce) PetscCallB200(b200IndexedPlanDestroy(PB_h, b->reduce));
+  b->bcast = b->reduce = NULL;
+  b->planned   = PETSC_FALSE;
+  b->ninflight = 0;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode PB_SFCtxDestroy(PetscCtxRt ctx)
+{
+  SF_B200 *b = *(SF_B200 **)ctx;
+  PetscFunctionBegin;
+  PetscCall(PB_SFDropPlans(b));
+  PetscCall(PetscFree(b));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode PetscSFReset_B200(PetscSF sf) /* PetscSFSetGraph / PetscSFDestroy: the graph is about to change */
+{
+  SF_B200 *b;
+  PetscFunctionBegin;
+  PetscCall(PB_SFCtx(sf, &b));
+  PetscCall(PB_SFDropPlans(b));
+  if (b->reset) PetscCall((*b->reset)(sf));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+/* extents of the two data buffers and, for a process-local graph, the two indexed plans */
+static PetscErrorCode PB_SFPlan(PetscSF sf, SF_B200 *b)
+{
+  PetscInt           nroots, nleaves, minleaf, maxleaf;
+  const PetscInt    *ilocal;
+  const PetscSFNode *iremote;
+  PetscMPIInt        size;
+  PetscFunctionBegin;
+  if (b->planned) PetscFunctionReturn(PETSC_SUCCESS);
+  PetscCall(PetscSFGetGraph(sf, &nroots, &nleaves, &ilocal, &iremote));
+  PetscCheck(nroots >= 0, PetscObjectComm((PetscObject)sf), PETSC_ERR_ARG_WRONGSTATE, "PetscSF graph has not been set");
+  PetscCall(PetscSFGetLeafRange(sf, &minleaf, &maxleaf));
+  PetscCallMPI(MPI_Comm_size(PetscObjectComm((PetscObject)sf), &size));
+  b->nroots     = nroots;
+  b->leafextent = nleaves ? maxleaf + 1 : 0;
+  b->local      = (size == 1) ? PETSC_TRUE : PETSC_FALSE;
+  if (b->local) {
+    int *ridx;
+    PetscCall(PetscMalloc1(nleaves + 1, &ridx));
+    for (PetscInt k = 0; k < nleaves; k++) {
+      PetscCheck(iremote[k].rank == 0 && iremote[k].index >= 0 && iremote[k].index < nroots, PETSC_COMM_SELF, PETSC_ERR_ARG_OUTOFRANGE, "leaf %" PetscInt_FMT " points at root (%" PetscInt_FMT ",%" PetscInt_FMT ") outside this process", k, (PetscInt)iremote[k].rank, iremote[k].index);
+      ridx[k] = (int)iremote[k].index;
+    }
+    PetscCall(PB_Init());
+    PetscCallB200(b200IndexedPlanCreate(PB_h, (int64_t)nleaves, ridx, 0, (const int *)ilocal, 0, &b->bcast));  /* leaf[ilocal[k]] <- root[ridx[k]] */
+    PetscCallB200(b200IndexedPlanCreate(PB_h, (int64_t)nleaves, (const int *)ilocal, 0, ridx, 0, &b->reduce)); /* root[ridx[k]] <- leaf[ilocal[k]] */
+    PetscCall(PetscFree(ridx));
+  }
+  b->planned = PETSC_TRUE;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+/* unit and op as the kernels know them; *native = PETSC_FALSE when they do not */
+static PetscErrorCode PB_SFDecode(MPI_Datatype unit, MPI_Op op, int *dtype, int *bs, int *sfop, size_t *unitbytes, PetscBool *native)
+{
+  PetscMPIInt sz;
+  PetscFunctionBegin;
+  *native = PETSC_TRUE;
+  *dtype  = -1;
+  *bs     = 1;
+  PetscCallMPI(MPI_Type_size(unit, &sz));
+  *unitbytes = (size_t)sz;
+#if defined(PETSC_HAVE_MPIUNI)
+  { /* MPIUNI packs a datatype as [combiner:4 | type-index:8 | count:12 | base-bytes:8] (include/petsc/mpiuni/mpi.h:205) */
+    const int idx = ((int)unit >> 20) & 0xff, cnt = ((int)unit >> 8) & 0xfff, esz = (int)unit & 0xff;
+    if (idx == (((int)MPI_DOUBLE >> 20) & 0xff) && esz == (int)sizeof(double)) *dtype = B200_SF_F64;
+    else if (idx == (((int)MPI_INT >> 20) & 0xff) && esz == (int)sizeof(int)) *dtype = B200_SF_I32;
+    *bs = cnt;
+  }
+#else
+  if (unit == MPIU_SCALAR || unit == MPIU_REAL) *dtype = B200_SF_F64;
+  else if (unit == MPIU_INT) *dtype = B200_SF_I32;
+#endif
+  if (op == MPI_REPLACE) *sfop = B200_SF_REPLACE;
+  else if (op == MPI_SUM || op == MPIU_SUM) *sfop = B200_SF_SUM;
+  else if (op == MPI_PROD) *sfop = B200_SF_PROD;
+  else if (op == MPI_MAX || op == MPIU_MAX) *sfop = B200_SF_MAX;
+  else if (op == MPI_MIN || op == MPIU_MIN) *sfop = B200_SF_MIN;
+  else *native = PETSC_FALSE;
+  if (*dtype < 0 || *bs < 1) *native = PETSC_FALSE;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+static PetscErrorCode PB_SFPush(SF_B200 *b, const void *root, const void *leaf)
+{
+  PetscFunctionBegin;
+  PetscCheck(b->ninflight < PB_SF_MAXINFLIGHT, PETSC_COMM_SELF, PETSC_ERR_SUP, "more than %d PetscSF operations in flight on device data", PB_SF_MAXINFLIGHT);
+  b->inflight[b->ninflight].root = root;
+  b->inflight[b->ninflight].leaf = leaf;
+  b->ninflight++;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscBool PB_SFPop(SF_B200 *b, const void *root, const void *leaf)
+{
+  for (int i = 0; i < b->ninflight; i++)
+    if (b->inflight[i].root == root && b->inflight[i].leaf == leaf) {
+      b->inflight[i] = b->inflight[--b->ninflight];
+      return PETSC_TRUE;
+    }
+  return PETSC_FALSE;
+}
+
+/* direction 0: broadcast (src = root, dst = leaf); 1: reduction (src = leaf, dst = root) */
+static PetscErrorCode PB_SFBegin(PetscSF sf, int direction, MPI_Datatype unit, PetscMemType rmtype, const void *rootdata, PetscMemType lmtype, const void *leafdata, MPI_Op op)
+{
+  SF_B200    *b;
+  const PetscBool rdev = PetscMemTypeDevice(rmtype) ? PETSC_TRUE : PETSC_FALSE, ldev = PetscMemTypeDevice(lmtype) ? PETSC_TRUE : PETSC_FALSE;
+  int         dtype, bs, sfop;
+  size_t      ub;
+  PetscBool   native;
+  PetscFunctionBegin;
+  PetscCall(PB_SFCtx(sf, &b));
+  if (!rdev && !ldev) { /* host data: the parent, untouched */
+    if (direction == 0) PetscCall((*b->bcastbegin)(sf, unit, rmtype, rootdata, lmtype, (void *)leafdata, op));
+    else PetscCall((*b->reducebegin)(sf, unit, lmtype, leafdata, rmtype, (void *)rootdata, op));
+    PetscFunctionReturn(PETSC_SUCCESS);
+  }
+  PetscCall(PB_Init());
+  PetscCall(PB_SFPlan(sf, b));
+  PetscCall(PB_SFDecode(unit, op, &dtype, &bs, &sfop, &ub, &native));
+  if (rdev && ldev && native && b->local && rootdata != leafdata) {
+    PetscCall(PB_LogTimeBegin());
+    if (direction == 0) PetscCallB200(b200IndexedOp(PB_h, b->bcast, dtype, bs, sfop, rootdata, (void *)leafdata));
+    else PetscCallB200(b200IndexedOp(PB_h, b->reduce, dtype, bs, sfop, leafdata, (void *)rootdata));
+    PetscCall(PB_LogTimeEnd());
+    b->nnative += 1;
+  } else { /* stage the device side(s) through the host and let the parent do the operation there */
+    const size_t rbytes = (size_t)b->nroots * ub, lbytes = (size_t)b->leafextent * ub;
+    const PetscBool same = (rootdata == leafdata) ? PETSC_TRUE : PETSC_FALSE;
+    char *hroot = (char *)rootdata, *hleaf = (char *)leafdata;
+    if (rdev) {
+      PetscCall(PetscMalloc1(PetscMax(rbytes, same ? lbytes : 0) + 1, &hroot));
+      if (PetscMax(rbytes, same ? lbytes : 0)) PetscCallB200(b200MemcpyDtoH(PB_h, hroot, rootdata, PetscMax(rbytes, same ? lbytes : 0)));
+    }
+    if (same) hleaf = hroot;
+    else if (ldev) {
+      PetscCall(PetscMalloc1(lbytes + 1, &hleaf));
+      if (lbytes) PetscCallB200(b200MemcpyDtoH(PB_h, hleaf, leafdata, lbytes));
+    }
+    if (direction == 0) {
+      PetscCall((*b->bcastbegin)(sf, unit, PETSC_MEMTYPE_HOST, hroot, PETSC_MEMTYPE_HOST, hleaf, op));
+      PetscCall((*b->bcastend)(sf, unit, hroot, hleaf, op));
+      if (ldev && lbytes) PetscCallB200(b200MemcpyHtoD(PB_h, (void *)leafdata, hleaf, lbytes));
+    } else {
+      PetscCall((*b->reducebegin)(sf, unit, PETSC_MEMTYPE_HOST, hleaf, PETSC_MEMTYPE_HOST, hroot, op));
+      PetscCall((*b->reduceend)(sf, unit, hleaf, hroot, op));
+      if (rdev && rbytes) PetscCallB200(b200MemcpyHtoD(PB_h, (void *)rootdata, hroot, rbytes));
+    }
+    if (rdev) PetscCall(PetscFree(hroot));
+    if (ldev && !same) PetscCall(PetscFree(hleaf));
+    b->nstaged += 1;
+  }
+  PetscCall(PB_SFPush(b, rootdata, leafdata));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode PetscSFBcastBegin_B200(PetscSF sf, MPI_Datatype unit, PetscMemType rmtype, const void *rootdata, PetscMemType lmtype, void *leafdata, MPI_Op op)
+{
+  return PB_SFBegin(sf, 0, unit, rmtype, rootdata, lmtype, leafdata, op);
+}
+static PetscErrorCode PetscSFReduceBegin_B200(PetscSF sf, MPI_Datatype unit, PetscMemType lmtype, const void *leafdata, PetscMemType rmtype, void *rootdata, MPI_Op op)
+{
+  return PB_SFBegin(sf, 1, unit, rmtype, rootdata, lmtype, leafdata, op);
+}
+static PetscErrorCode PetscSFBcastEnd_B200(PetscSF sf, MPI_Datatype unit, const void *rootdata, void *leafdata, MPI_Op op)
+{
+  SF_B200 *b;
+  PetscFunctionBegin;
+  PetscCall(PB_SFCtx(sf, &b));
+  if (!PB_SFPop(b, rootdata, leafdata)) PetscCall((*b->bcastend)(sf, unit, rootdata, leafdata, op));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode PetscSFReduceEnd_B200(PetscSF sf, MPI_Datatype unit, const void *leafdata, void *rootdata, MPI_Op op)
+{
+  SF_B200 *b;
+  PetscFunctionBegin;
+  PetscCall(PB_SFCtx(sf, &b));
+  if (!PB_SFPop(b, rootdata, leafdata)) PetscCall((*b->reduceend)(sf, unit, leafdata, rootdata, op));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode PetscSFFetchAndOpBegin_B200(PetscSF sf, MPI_Datatype unit, PetscMemType rmtype, void *rootdata, PetscMemType lmtype, const void *leafdata, void *leafupdate, MPI_Op op)
+{
+  SF_B200 *b;
+  PetscFunctionBegin;
+  PetscCall(PB_SFCtx(sf, &b));
+  PetscCheck(!PetscMemTypeDevice(rmtype) && !PetscMemTypeDevice(lmtype), PetscObjectComm((PetscObject)sf), PETSC_ERR_SUP, "PetscSFFetchAndOp on device data is not supported by PetscSF type b200");
+  PetscCall((*b->fetchbegin)(sf, unit, rmtype, rootdata, lmtype, leafdata, leafupdate, op));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+/* for tests and PETSc programs that link the plugin: how many Begin calls of this SF ran on the device / were staged */
+PETSC_EXTERN PetscErrorCode PetscSFB200GetCounts(PetscSF sf, PetscInt *native, PetscInt *staged)
+{
+  SF_B200 *b;
+  PetscFunctionBegin;
+  PetscCall(PB_SFCtx(sf, &b));
+  if (native) *native = (PetscInt)b->nnative;
+  if (staged) *staged = (PetscInt)b->nstaged;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+PETSC_EXTERN PetscErrorCode PetscSFCreate_B200(PetscSF sf)
+{
+  SF_B200       *b;
+  PetscContainer c;
+  PetscFunctionBegin;
+  PetscCheck(PB_SFCreate_Basic, PetscObjectComm((PetscObject)sf), PETSC_ERR_ORDER, "PetscSF type b200 used before the plugin was registered");
+  PetscCall((*PB_SFCreate_Basic)(sf)); /* the reference's PETSCSFBASIC: data, setup, host pack/unpack, view, destroy */
+  PetscCall(PetscNew(&b));
+  b->bcastbegin  = sf->ops->BcastBegin;
+  b->bcastend    = sf->ops->BcastEnd;
+  b->reducebegin = sf->ops->ReduceBegin;
+  b->reduceend   = sf->ops->ReduceEnd;
+  b->fetchbegin  = sf->ops->FetchAndOpBegin;
+  b->reset       = sf->ops->Reset;
+  PetscCall(PetscContainerCreate(PetscObjectComm((PetscObject)sf), &c));
+  PetscCall(PetscContainerSetPointer(c, b));
+  PetscCall(PetscContainerSetCtxDestroy(c, PB_SFCtxDestroy));
+  PetscCall(PetscObjectCompose((PetscObject)sf, "PetscSFB200_ctx", (PetscObject)c));
+  PetscCall(PetscContainerDestroy(&c));
+  sf->ops->BcastBegin      = PetscSFBcastBegin_B200;
+  sf->ops->BcastEnd        = PetscSFBcastEnd_B200;
+  sf->ops->ReduceBegin     = PetscSFReduceBegin_B200;
+  sf->ops->ReduceEnd       = PetscSFReduceEnd_B200;
+  sf->ops->FetchAndOpBegin = PetscSFFetchAndOpBegin_B200;
+  sf->ops->Reset           = PetscSFReset_B200;
+  PetscCall(PetscObjectComposeFunction((PetscObject)sf, "PetscSFB200GetCounts_C", PetscSFB200GetCounts));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
 /* ================================================================== registration (src/sys/dll/reg.c:79,150; dl.c:178-199) */
 PETSC_EXTERN PetscErrorCode PetscDLLibraryRegister_petscb200plugin(void)
 {
@@ -2141,5 +2422,14 @@ PETSC_EXTERN PetscErrorCode PetscDLLibraryRegister_petscb200plugin(void)
      itself runs PCRegisterAll first, so the stock entry is already there to be replaced) */
   PetscCall(PetscOptionsGetBool(NULL, NULL, "-b200_keep_pcjacobi", &keep, NULL));
   if (!keep) PetscCall(PCRegister(PCJACOBI, PCCreate_JacobiB200));
+  /* PetscSF: the parent's creator is not exported by name, it is found in the registry (sfregi.c:33); "basic" then becomes the
+     sub-class (host operations are the parent's, unchanged) unless -b200_keep_sfbasic */
+  PetscCall(PetscSFInitializePackage());
+  PetscCall(PetscFunctionListFind(PetscSFList, PETSCSFBASIC, &PB_SFCreate_Basic));
+  PetscCheck(PB_SFCreate_Basic, PETSC_COMM_SELF, PETSC_ERR_PLIB, "PETSCSFBASIC is not registered");
+  PetscCall(PetscSFRegister(PETSCSFB200, PetscSFCreate_B200));
+  keep = PETSC_FALSE;
+  PetscCall(PetscOptionsGetBool(NULL, NULL, "-b200_keep_sfbasic", &keep, NULL));
+  if (!keep) PetscCall(PetscSFRegister(PETSCSFBASIC, PetscSFCreate_B200));
   PetscFunctionReturn(PETSC_SUCCESS);
 }

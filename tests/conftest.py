@@ -31,3 +31,14 @@ def assert_history_1e12(hist, ref, k, label=""):
     dev = float(np.max(np.abs(h - r))) / float(r[0]) if k else 0.0
     print("history %s: max|h-ref|/r0 = %.2e over %d entries (bound 1e-12, margin %.0fx)" % (label, dev, k, 1e-12 / dev if dev else float("inf")))
     assert dev <= 1e-12, (label, dev)
+
+
+SF_OPS = ("replace", "sum", "prod", "max", "min")
+
+
+def sf_graph_order(g):
+    """The order the reference applies the leaves of a PetscSF fixture in: PetscSFSetGraph sorts them by location
+    (sf.c:500; locations are distinct) and PETSCSFBASIC keeps that order for the process-local part."""
+    import numpy as np
+    perm = np.argsort(g["local"], kind="stable")
+    return g["local"][perm].astype(np.int32), g["remote"][perm].astype(np.int32)

@@ -150,3 +150,57 @@ def test_mpiaij_setup_helpers_index_exact_on_cpu(oracle):
                 assert np.array_equal(garray, og), (name, size, rank)
                 assert np.array_equal(Ai, oA[0]) and np.array_equal(Aj[:nzA.value], oA[1]) and np.array_equal(Aa[:nzA.value], oA[2]), (name, size, rank)
                 assert np.array_equal(Bi, oB[0]) and np.array_equal(Bj[:nzB.value], oB[1]) and np.array_equal(Ba[:nzB.value], oB[2]), (name, size, rank)
+
+
+def test_indexed_plan_host_grouping_is_stable(oracle):
+    """The host half of b200IndexedPlanCreate (b200IndexedGroupHost, plain C, no device): destinations grouped in increasing order,
+    the entries of a group in ENTRY order -- replaying the groups reproduces the oracle's sequential PetscSFLinkScatterLocal."""
+    L = _capi.lib()
+    vp = C.c_void_p
+    p = lambda a: None if a is None else a.ctypes.data_as(vp)   # noqa: E731
+    rng = np.random.default_rng(5)
+
+    def group(sidx, didx, n):
+        sc, dc, grouped = C.c_int(), C.c_int(), C.c_int()
+        se, de, ng = C.c_int64(), C.c_int64(), C.c_int64()
+        gd, go, gs = vp(), vp(), vp()
+        _capi.check(L.b200IndexedGroupHost(C.c_int64(n), p(sidx), 0, p(didx), 0, C.byref(sc), C.byref(dc), C.byref(se), C.byref(de), C.byref(grouped), C.byref(ng),
+                                           C.byref(gd), C.byref(go), C.byref(gs)))
+        out = dict(sc=sc.value, dc=dc.value, se=se.value, de=de.value, grouped=grouped.value, ng=ng.value)
+        if grouped.value:
+            arr = lambda q, k: np.ctypeslib.as_array(C.cast(q, C.POINTER(C.c_int)), shape=(k,)).copy()   # noqa: E731
+            out.update(gdst=arr(gd, ng.value), goff=arr(go, ng.value + 1), gsrc=arr(gs, n))
+            for q in (gd, go, gs):
+                _capi.check(L.b200HostFree(q))
+        else:
+            assert not gd.value and not go.value and not gs.value
+        return out
+
+    n = 5000
+    sidx = rng.integers(0, 700, n).astype(np.int32); didx = rng.integers(0, 300, n).astype(np.int32)
+    g = group(sidx, didx, n)
+    assert g["grouped"] and g["ng"] == len(np.unique(didx)) and g["se"] == sidx.max() + 1 and g["de"] == didx.max() + 1 and not g["sc"] and not g["dc"]
+    order = np.argsort(didx, kind="stable")
+    assert np.array_equal(g["gdst"], np.unique(didx)) and np.array_equal(g["gsrc"], sidx[order]) and g["goff"][-1] == n
+    assert np.array_equal(np.diff(g["goff"]), np.bincount(didx)[np.unique(didx)])
+    # replay group by group == the sequential reference loop, bit for bit (sums are order dependent)
+    src, dst = rng.uniform(-1, 1, 700), rng.uniform(-1, 1, 300)
+    want = oracle.sf_scatter(sidx, didx, src, dst, "sum")
+    got = dst.copy()
+    for k in range(g["ng"]):
+        v = got[g["gdst"][k]]
+        for j in range(g["goff"][k], g["goff"][k + 1]):
+            v = v + src[g["gsrc"][j]]
+        got[g["gdst"][k]] = v
+    assert np.array_equal(got, want)
+    # distinct destinations: no grouping; contiguous sides detected; NULL index arrays = contiguous
+    perm = rng.permutation(400).astype(np.int32)
+    g = group(perm, np.arange(7, 407, dtype=np.int32), 400)
+    assert not g["grouped"] and g["dc"] and not g["sc"] and g["de"] == 407
+    g = group(None, perm, 400)
+    assert not g["grouped"] and g["sc"] and not g["dc"] and g["ng"] == 400
+    g = group(None, None, 0)
+    assert not g["grouped"] and g["se"] == 0 and g["de"] == 0
+    sc = C.c_int()
+    assert L.b200IndexedGroupHost(C.c_int64(2), p(np.array([0, -3], np.int32)), 0, None, 0, C.byref(sc), C.byref(sc), C.byref(C.c_int64()), C.byref(C.c_int64()), C.byref(sc),
+                                  C.byref(C.c_int64()), C.byref(vp()), C.byref(vp()), C.byref(vp())) == 63

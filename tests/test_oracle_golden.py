@@ -140,6 +140,25 @@ def test_coo_assembly_bit_exact_vs_reference(oracle, path):
     assert (np.diff(jmap) >= 1).all() and jmap[-1] == ok.sum()
 
 
+SF = sorted(glob.glob(golden_path("sf_*.npz")))
+
+
+@pytest.mark.parametrize("path", SF, ids=[os.path.basename(p)[:-4] for p in SF])
+def test_sf_local_scatter_bit_exact_vs_reference(oracle, path):
+    """PetscSFBcast / PetscSFReduce of the reference (fixtures from oracle/ref_driver.c -sf) against the oracle's restatement of
+    PetscSFLinkScatterLocal + ScatterAnd<Op> (sfpack.c:1082, 190-222): every op, unit of bs scalars, PetscInt for SUM / MAX."""
+    from conftest import SF_OPS, sf_graph_order
+    g = np.load(path)
+    leafloc, rootidx = sf_graph_order(g)
+    bs = int(g["bs"])
+    for op in SF_OPS:
+        assert np.array_equal(oracle.sf_scatter(rootidx, leafloc, g["root"], g["leaf"], op, bs), g["ref_bcast_" + op]), op
+        assert np.array_equal(oracle.sf_scatter(leafloc, rootidx, g["leaf"], g["root"], op, bs), g["ref_reduce_" + op]), op
+    for op in ("sum", "max"):
+        assert np.array_equal(oracle.sf_scatter(rootidx, leafloc, g["rooti"], g["leafi"], op), g["ref_bcast_%s_i32" % op]), op
+        assert np.array_equal(oracle.sf_scatter(leafloc, rootidx, g["leafi"], g["rooti"], op), g["ref_reduce_%s_i32" % op]), op
+
+
 def test_coo_out_of_range_is_an_error(oracle):
     with pytest.raises(ValueError):
         oracle.coo_prealloc(4, 4, [0, 4], [0, 0])

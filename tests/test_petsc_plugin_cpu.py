@@ -49,6 +49,22 @@ def test_plugin_leaves_cpu_types_untouched():
     assert re.search(r"type: jacobi", view) and "seqaij" in view and "b200" not in view
 
 
+def test_sf_subclass_leaves_host_scatters_to_the_reference():
+    """The plugin registers its PetscSF sub-class under the name "basic" as well; on host vectors every VecScatter / PetscSF operation
+    of petsc_plugin/sf_driver.c must still be the reference's (no device touched, nothing staged), and -b200_keep_sfbasic must leave
+    the stock type in place."""
+    exe = os.path.join(ROOT, "baseline", "_ref", "petsc", "bin", "sf_driver")
+    if not os.path.exists(exe):
+        pytest.skip("sf_driver not built")
+    env = dict(os.environ, LD_LIBRARY_PATH=BLASDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([exe, "-dll_append", PLUGIN], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert out.returncode == 0 and "all ok" in out.stdout and "FAILED" not in out.stdout, out.stdout + out.stderr
+    assert "general scatter: 0 operations on the device, 0 staged through the host" in out.stdout
+    assert "ok sf_operations_ran_where_expected" in out.stdout and "ok in_place_overlapping_insert" in out.stdout
+    keep = subprocess.run([exe, "-dll_append", PLUGIN, "-b200_keep_sfbasic"], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert "FAILED vecscatter_sf_is_the_b200_subclass" in keep.stdout      # the stock PETSCSFBASIC: no composed counter
+
+
 def test_b200_types_fail_loudly_without_gpu():
     out = ex2(["-m", "5", "-n", "5", "-dll_append", PLUGIN, "-mat_type", "aijb200", "-vec_type", "b200"])
     assert out.returncode != 0

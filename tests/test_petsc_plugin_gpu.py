@@ -139,3 +139,23 @@ def test_ex2_pipecgb200_registered_ksp_matches_reference_pipecg():
     assert np.allclose(ha[:k], hb[:k], rtol=1e-10, atol=2e-12 * hb[0])
     view = run("ex2", ["-m", "8", "-n", "8", "-ksp_type", "pipecgb200", "-pc_type", "jacobi", "-ksp_view"] + B200)
     assert "pipecgb200" in view and "seqaijb200" in view
+
+
+SF_CHECKS = ("vecscatter_sf_is_the_b200_subclass", "general_forward_insert", "general_forward_add", "general_forward_max", "general_reverse_add_repeated_roots",
+             "general_reverse_insert_repeated_roots", "general_reverse_min_repeated_roots", "general_scatter_ran_where_expected", "mixed_device_to_host_add",
+             "mixed_host_to_device_reverse_add", "mixed_scatters_were_staged", "stride_forward_insert", "stride_reverse_add", "identity_forward_insert",
+             "identity_forward_add", "in_place_overlapping_insert", "block_forward_add_repeated_destinations", "block_forward_insert_repeated_destinations",
+             "block_reverse_add", "scatter_to_all", "petscsf_default_type_is_the_b200_subclass", "sf_operations_ran_where_expected", "sf_new_graph_replans")
+
+
+@pytest.mark.skipif(not (have() and os.path.exists(os.path.join(BIN, "sf_driver"))), reason="baseline/_ref/petsc/bin/sf_driver not built")
+def test_sf_driver_vecscatter_and_petscsf_on_device_vectors():
+    """VecScatter / PetscSF on b200 vectors and raw device buffers inside real PETSc (petsc_plugin/sf_driver.c): every result equals
+    the same operation on the reference's host vectors bit for bit; device-to-device operations ran as device kernels (counted),
+    mixed and in-place ones were staged."""
+    out = run("sf_driver", B200)
+    assert "vec type seqb200" in out and "all ok" in out and "FAILED" not in out, out
+    for name in SF_CHECKS:
+        assert "ok " + name in out, (name, out)
+    for op in ("replace", "sum", "max", "min", "prod"):
+        assert "ok sf_bcast_%s_int_and_scalar" % op in out and "ok sf_reduce_%s_int_and_scalar" % op in out, out
