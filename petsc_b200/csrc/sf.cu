@@ -8,7 +8,8 @@
  * (one root with many leaves).  The reference applies them in index order; so does this file: the plan groups the entries by
  * destination with a STABLE counting sort on the host (setup time) and the kernel walks each group sequentially -- no atomics, and
  * floating-point sums come out in the reference's association, bit for bit.  Destinations that are hit once (every VecScatter
- * with distinct "to" indices) take the one-thread-per-entry kernel.
+ * with distinct "to" indices) take the one-thread-per-entry kernel, with the entries re-ordered by destination at plan time
+ * ("pull" order: coalesced writes, gathered reads; a permutation of a range then needs no destination indices at all).
  *
  * HBM-bound gather/scatter: per entry 8 B of indices (none when a side is contiguous), bs*8 B read, bs*8 B written (+ bs*8 B read
  * for a non-REPLACE op).  Not on the Krylov inner loop; it is what VecScatterBegin/End cost on device vectors.
@@ -24,7 +25,8 @@ struct b200IndexedPlan_s {
   int     src_contig, dst_contig; /* sidx[i] = s0 + i / didx[i] = d0 + i: no index loads */
   int     s0, d0;
   int64_t src_extent, dst_extent; /* 1 + largest index: bounds the buffers the kernels touch */
-  int    *d_sidx, *d_didx;        /* [n] entry order (ungrouped kernel) */
+  int     k_src_contig, k_dst_contig, k_s0, k_d0; /* what the ungrouped kernel sees: entries re-ordered by destination ("pull" order) */
+  int    *d_sidx, *d_didx;        /* [n] ungrouped kernel, pull order */
   int    *d_gdst, *d_goff, *d_gsrc; /* grouped: destination of group g, entries goff[g]..goff[g+1] of gsrc (in entry order) */
 };
 
@@ -42,12 +44,12 @@ template <> __device__ __forceinline__ int sf_apply<int, B200_SF_MAX>(int s, int
 template <> __device__ __forceinline__ int sf_apply<int, B200_SF_MIN>(int s, int t) { return (s < t) ? s : t; }
 
 /* one thread per (entry, component): destinations are distinct */
-template <typename T, int OP> __global__ void __launch_bounds__(256) sf_scatter_kernel(int64_t n, int bs, const int *__restrict__ sidx, int s0, const int *__restrict__ didx, int d0, const T *__restrict__ src, T *dst)
+template <typename T, int OP, bool BS1> __global__ void __launch_bounds__(256) sf_scatter_kernel(int64_t n, int bs, const int *__restrict__ sidx, int s0, const int *__restrict__ didx, int d0, const T *__restrict__ src, T *dst)
 {
   const int64_t total = n * bs, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-    const int64_t i = e / bs;
-    const int     c = (int)(e - i * bs);
+    const int64_t i = BS1 ? e : e / bs; /* no 64-bit division on the scalar (bs = 1) path */
+    const int     c = BS1 ? 0 : (int)(e - i * bs);
     const int64_t s = (int64_t)(sidx ? sidx[i] : s0 + (int)i) * bs + c;
     const int64_t t = (int64_t)(didx ? didx[i] : d0 + (int)i) * bs + c;
     const T       u = src[s];
@@ -57,12 +59,12 @@ template <typename T, int OP> __global__ void __launch_bounds__(256) sf_scatter_
 }
 
 /* one thread per (destination group, component): the entries of a group are applied in entry order */
-template <typename T, int OP> __global__ void __launch_bounds__(256) sf_scatter_grouped_kernel(int64_t ng, int bs, const int *__restrict__ gdst, const int *__restrict__ goff, const int *__restrict__ gsrc, const T *__restrict__ src, T *dst)
+template <typename T, int OP, bool BS1> __global__ void __launch_bounds__(256) sf_scatter_grouped_kernel(int64_t ng, int bs, const int *__restrict__ gdst, const int *__restrict__ goff, const int *__restrict__ gsrc, const T *__restrict__ src, T *dst)
 {
   const int64_t total = ng * bs, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-    const int64_t g = e / bs;
-    const int     c = (int)(e - g * bs);
+    const int64_t g = BS1 ? e : e / bs;
+    const int     c = BS1 ? 0 : (int)(e - g * bs);
     const int64_t t = (int64_t)gdst[g] * bs + c;
     T             v = dst[t];
     for (int k = goff[g]; k < goff[g + 1]; k++) v = sf_apply<T, OP>(v, src[(int64_t)gsrc[k] * bs + c]);
@@ -153,9 +155,42 @@ extern "C" int b200IndexedPlanCreate(b200Handle h, int64_t n, const int *sidx, i
   p->n  = n;
   p->s0 = (sidx && n) ? sidx[0] : s0;
   p->d0 = (didx && n) ? didx[0] : d0;
-  if (!p->grouped) {
+  p->k_src_contig = p->src_contig;
+  p->k_dst_contig = p->dst_contig;
+  p->k_s0         = p->s0;
+  p->k_d0         = p->d0;
+  if (!p->grouped && !p->dst_contig && n) {
+    /* distinct, non-contiguous destinations: the order of the entries does not matter, so give the kernel "pull" order -- entries
+       sorted by destination.  Consecutive threads then WRITE consecutive (or increasing) addresses and gather their sources;
+       scattered 8-byte read-modify-writes measured 5x slower than gathers of the same index set (profiles/round2_notes.md).
+       A permutation of a range (the usual VecScatter "to" set) needs no destination indices at all after the sort. */
+    const int64_t ext = p->dst_extent;
+    int *inv = (int *)malloc(sizeof(int) * (size_t)ext), *sd = (int *)malloc(sizeof(int) * (size_t)n), *ss = (int *)malloc(sizeof(int) * (size_t)n);
+    if (!inv || !sd || !ss) {
+      free(inv); free(sd); free(ss); free(p);
+      B200_CHECK(0, B200_ERR_MEM, "out of host memory");
+    }
+    for (int64_t d = 0; d < ext; d++) inv[d] = -1;
+    for (int64_t i = 0; i < n; i++) inv[didx[i]] = (int)i;
+    int64_t k = 0;
+    int     sc = 1, dc = 1;
+    for (int64_t d = 0; d < ext; d++)
+      if (inv[d] >= 0) {
+        sd[k] = (int)d;
+        ss[k] = sidx ? sidx[inv[d]] : s0 + inv[d];
+        if (sd[k] != sd[0] + (int)k) dc = 0;
+        if (ss[k] != ss[0] + (int)k) sc = 0;
+        k++;
+      }
+    p->k_src_contig = sc;
+    p->k_dst_contig = dc;
+    p->k_s0         = ss[0];
+    p->k_d0         = sd[0];
+    if (!sc) rc = sf_upload(h, &p->d_sidx, ss, (size_t)n);
+    if (!rc && !dc) rc = sf_upload(h, &p->d_didx, sd, (size_t)n);
+    free(inv); free(sd); free(ss);
+  } else if (!p->grouped) {
     if (!p->src_contig && n) rc = sf_upload(h, &p->d_sidx, sidx, (size_t)n);
-    if (!rc && !p->dst_contig && n) rc = sf_upload(h, &p->d_didx, didx, (size_t)n);
   } else {
     rc = sf_upload(h, &p->d_gdst, gdst, (size_t)p->ngroups);
     if (!rc) rc = sf_upload(h, &p->d_goff, goff, (size_t)p->ngroups + 1);
@@ -204,8 +239,11 @@ template <typename T, int OP> static int sf_launch(b200Handle h, b200IndexedPlan
   if (!units) return 0;
   int64_t g = (units + 255) / 256;
   if (g > (int64_t)h->num_sms * 16) g = (int64_t)h->num_sms * 16;
-  if (p->grouped) sf_scatter_grouped_kernel<T, OP><<<(int)g, 256, 0, h->stream>>>(p->ngroups, bs, p->d_gdst, p->d_goff, p->d_gsrc, src, dst);
-  else sf_scatter_kernel<T, OP><<<(int)g, 256, 0, h->stream>>>(p->n, bs, p->src_contig ? NULL : p->d_sidx, p->s0, p->dst_contig ? NULL : p->d_didx, p->d0, src, dst);
+  const int *si = p->k_src_contig ? NULL : p->d_sidx, *di = p->k_dst_contig ? NULL : p->d_didx;
+  if (p->grouped && bs == 1) sf_scatter_grouped_kernel<T, OP, true><<<(int)g, 256, 0, h->stream>>>(p->ngroups, bs, p->d_gdst, p->d_goff, p->d_gsrc, src, dst);
+  else if (p->grouped) sf_scatter_grouped_kernel<T, OP, false><<<(int)g, 256, 0, h->stream>>>(p->ngroups, bs, p->d_gdst, p->d_goff, p->d_gsrc, src, dst);
+  else if (bs == 1) sf_scatter_kernel<T, OP, true><<<(int)g, 256, 0, h->stream>>>(p->n, bs, si, p->k_s0, di, p->k_d0, src, dst);
+  else sf_scatter_kernel<T, OP, false><<<(int)g, 256, 0, h->stream>>>(p->n, bs, si, p->k_s0, di, p->k_d0, src, dst);
   B200_LAUNCHED(1);
   B200_KERNEL_CHECK();
   return 0;
