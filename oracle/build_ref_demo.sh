@@ -31,4 +31,6 @@ make -s -C "$ROOT/petsc_plugin" PETSC_INC="$INC" PETSC_LIBDIR="$OUT/lib"
 DRV_LNK="-L$ROOT/petsc_plugin -lpetscb200plugin -L$ROOT/petsc_b200/lib -lpetscb200 -L$OUT/lib -lpetsc -Wl,-rpath,\$ORIGIN -Wl,-rpath,\$ORIGIN/../petsc_b200/lib -Wl,-rpath,\$ORIGIN/../baseline/_ref/petsc/lib -Wl,-rpath,$BLASDIR -Wl,-rpath-link,$BLASDIR -Wl,--allow-shlib-undefined -lm"
 /usr/bin/gcc -O2 -g -std=gnu11 -Wall -Wno-unused-parameter -Wno-format-truncation -o "$ROOT/petsc_plugin/b200_driver" "$ROOT/petsc_plugin/b200_driver.c" $INC -I"$ROOT/include" $DRV_LNK
 /usr/bin/gcc -O2 -g -std=gnu11 -fPIC -shared -Wno-format-truncation -DB200_DRIVER_NO_MAIN -o "$ROOT/petsc_plugin/libb200driver.so" "$ROOT/petsc_plugin/b200_driver.c" $INC -I"$ROOT/include" $DRV_LNK
+# the reference's own device-variant test programs (tools/ref_conformance.py: compiled from the sources where they lie + manifest)
+python "$ROOT/tools/ref_conformance.py" build | tail -1
 echo "reference demo built in $OUT"

@@ -1,0 +1,35 @@
+"""The reference's OWN test programs on the plugin's types (tools/ref_conformance.py): the single-rank `-vec_type cuda` /
+`-mat_type aijcusparse` variants of PETSc's Vec / Mat / KSP tests and a set of KSP tutorials, compiled from the reference's sources
+where they lie, run with -dll_append <plugin> on the b200 types and on the host types on the same box; outputs must agree (type
+names and object views dropped, numbers to 1e-6 like petscdiff -j).  The cases asserted here are the ones recorded as passing in
+tests/ref_conformance_expected.json; the full table, with the known gaps, is profiles/round2_ref_conformance.md."""
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+pytestmark = pytest.mark.gpu
+EXPECTED = json.load(open(os.path.join(ROOT, "tests", "ref_conformance_expected.json")))["expected_pass"]
+
+
+def test_reference_device_variant_tests_pass_on_b200_types():
+    import ref_conformance as rc
+    if not os.path.exists(rc.MANIFEST):
+        pytest.skip("baseline/_ref/petsc/reftests.json not built (needs the build container)")
+    if not EXPECTED:
+        pytest.skip("no cases recorded yet")
+    manifest = {rc.case_id(c): c for c in json.load(open(rc.MANIFEST))}
+    missing = [e for e in EXPECTED if e not in manifest]
+    assert not missing, missing
+    bad = []
+    for e in EXPECTED:
+        c = manifest[e]
+        rc_h, out_h = rc.run_case(c, False)
+        rc_d, out_d = rc.run_case(c, True)
+        ok, why = rc.same_output(out_h, out_d) if (rc_h == 0 and rc_d == 0) else (False, "exit codes %d / %d: %s" % (rc_h, rc_d, out_d[-600:]))
+        if not ok:
+            bad.append((e, why))
+    assert not bad, bad
