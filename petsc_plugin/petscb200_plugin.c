@@ -214,12 +214,18 @@ static PetscErrorCode PB_VecRead(Vec v, const double **p)
   *p = ((Vec_SeqB200 *)v->data)->d;
   PetscFunctionReturn(PETSC_SUCCESS);
 }
+/* Every device WRITE access bumps the vector's object state, as VecRestoreArray[Write]() / VecCUDARestoreArrayWrite() do for the
+   reference's implementations (rvector.c:2085, veccupmimpl.h): PETSc keys its norm cache on that state (VecNormAvailable), and
+   e.g. VecSet(x, 0) returns early when the cached 2-norm is 0 (rvector.c:506-512).  MatMult / PCApply / PCApplyBAorAB do NOT bump
+   the state of their output themselves -- the implementation's array access does.  Found by the reference's ex9 (BiCGStab's
+   VecSet(V,0) skipped on the second solve) and mat/tests/ex254 (MatMultEqual reading a stale cached norm). */
 static PetscErrorCode PB_VecRW(Vec v, double **p)
 {
   PetscFunctionBegin;
   PetscCall(PB_VecToDevice(v));
   ((Vec_SeqB200 *)v->data)->mask = PB_GPU;
   *p = ((Vec_SeqB200 *)v->data)->d;
+  PetscCall(PetscObjectStateIncrease((PetscObject)v));
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 static PetscErrorCode PB_VecWrite(Vec v, double **p)
@@ -228,6 +234,7 @@ static PetscErrorCode PB_VecWrite(Vec v, double **p)
   PetscCall(PB_VecAlloc(v));
   ((Vec_SeqB200 *)v->data)->mask = PB_GPU;
   *p = ((Vec_SeqB200 *)v->data)->d;
+  PetscCall(PetscObjectStateIncrease((PetscObject)v));
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
@@ -1237,6 +1244,29 @@ static PetscErrorCode MatSetValuesCOO_SeqAIJB200(Mat A, const PetscScalar v[], I
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
+/* Products with a dense matrix (MatMatMult / MatTransposeMatMult / MatMatTransposeMult with MATSEQDENSE): MatProductSetFromOptions
+   looks the implementation up under a name built from BOTH type names (matproduct.c:445-471), so a sub-class of MATSEQAIJ has to
+   route its own name to the parent's entry, which MATSEQDENSE composes on the dense matrix ("..._seqaij_seqdense_C",
+   "..._seqdense_seqaij_C").  The parent's kernels read the host CSR, which is always current (host master copy). */
+static PetscErrorCode PB_ProductForward(Mat C, const char *parentname)
+{
+  Mat_Product *product = C->product;
+  PetscErrorCode (*f)(Mat) = NULL;
+  PetscFunctionBegin;
+  PetscCall(PetscObjectQueryFunction((PetscObject)product->B, parentname, &f));
+  if (!f) PetscCall(PetscObjectQueryFunction((PetscObject)product->A, parentname, &f));
+  if (f) PetscCall((*f)(C));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode MatProductSetFromOptions_SeqAIJB200_SeqDense(Mat C)
+{
+  return PB_ProductForward(C, "MatProductSetFromOptions_seqaij_seqdense_C");
+}
+static PetscErrorCode MatProductSetFromOptions_SeqDense_SeqAIJB200(Mat C)
+{
+  return PB_ProductForward(C, "MatProductSetFromOptions_seqdense_seqaij_C");
+}
+
 static PetscErrorCode MatDestroy_SeqAIJB200(Mat A)
 {
   Mat_B200 *m = (Mat_B200 *)A->spptr;
@@ -1246,6 +1276,8 @@ static PetscErrorCode MatDestroy_SeqAIJB200(Mat A)
   if (m->coo) b200CooPlanDestroy(m->coo);
   PetscCall(PetscFree(A->spptr));
   PetscCall(PetscObjectComposeFunction((PetscObject)A, "MatConvert_seqaij_seqaijb200_C", NULL));
+  PetscCall(PetscObjectComposeFunction((PetscObject)A, "MatProductSetFromOptions_seqaijb200_seqdense_C", NULL));
+  PetscCall(PetscObjectComposeFunction((PetscObject)A, "MatProductSetFromOptions_seqdense_seqaijb200_C", NULL));
   PetscCall((*destroy)(A));
   PetscFunctionReturn(PETSC_SUCCESS);
 }
@@ -1300,6 +1332,8 @@ PETSC_EXTERN PetscErrorCode MatConvert_SeqAIJ_SeqAIJB200(Mat A, MatType type, Ma
   ((Mat_SeqAIJ *)B->data)->inode.use = PETSC_FALSE; /* the device kernel is the mult path */
   PetscCall(PetscObjectChangeTypeName((PetscObject)B, MATSEQAIJB200));
   PetscCall(PetscObjectComposeFunction((PetscObject)B, "MatConvert_seqaij_seqaijb200_C", MatConvert_SeqAIJ_SeqAIJB200));
+  PetscCall(PetscObjectComposeFunction((PetscObject)B, "MatProductSetFromOptions_seqaijb200_seqdense_C", MatProductSetFromOptions_SeqAIJB200_SeqDense));
+  PetscCall(PetscObjectComposeFunction((PetscObject)B, "MatProductSetFromOptions_seqdense_seqaijb200_C", MatProductSetFromOptions_SeqDense_SeqAIJB200));
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 

@@ -60,7 +60,7 @@ def test_sf_subclass_leaves_host_scatters_to_the_reference():
     out = subprocess.run([exe, "-dll_append", PLUGIN], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert out.returncode == 0 and "all ok" in out.stdout and "FAILED" not in out.stdout, out.stdout + out.stderr
     assert "general scatter: 0 operations on the device, 0 staged through the host" in out.stdout
-    assert "ok sf_operations_ran_where_expected" in out.stdout and "ok in_place_overlapping_insert" in out.stdout
+    assert "ok sf_operations_ran_where_expected" in out.stdout and "ok in_place_insert" in out.stdout
     keep = subprocess.run([exe, "-dll_append", PLUGIN, "-b200_keep_sfbasic"], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert "FAILED vecscatter_sf_is_the_b200_subclass" in keep.stdout      # the stock PETSCSFBASIC: no composed counter
 

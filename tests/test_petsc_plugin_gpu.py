@@ -144,7 +144,7 @@ def test_ex2_pipecgb200_registered_ksp_matches_reference_pipecg():
 SF_CHECKS = ("vecscatter_sf_is_the_b200_subclass", "general_forward_insert", "general_forward_add", "general_forward_max", "general_reverse_add_repeated_roots",
              "general_reverse_insert_repeated_roots", "general_reverse_min_repeated_roots", "general_scatter_ran_where_expected", "mixed_device_to_host_add",
              "mixed_host_to_device_reverse_add", "mixed_scatters_were_staged", "stride_forward_insert", "stride_reverse_add", "identity_forward_insert",
-             "identity_forward_add", "in_place_overlapping_insert", "block_forward_add_repeated_destinations", "block_forward_insert_repeated_destinations",
+             "identity_forward_add", "in_place_insert", "block_forward_add_repeated_destinations", "block_forward_insert_repeated_destinations",
              "block_reverse_add", "scatter_to_all", "petscsf_default_type_is_the_b200_subclass", "sf_operations_ran_where_expected", "sf_new_graph_replans")
 
 

@@ -12,20 +12,22 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 pytestmark = pytest.mark.gpu
-EXPECTED = json.load(open(os.path.join(ROOT, "tests", "ref_conformance_expected.json")))["expected_pass"]
+_EXP = json.load(open(os.path.join(ROOT, "tests", "ref_conformance_expected.json")))
+EXPECTED = _EXP["expected_pass"]
+FIXED = _EXP["fixed_after_last_gpu_run"]
 
 
-def test_reference_device_variant_tests_pass_on_b200_types():
+def _run(cases):
     import ref_conformance as rc
     if not os.path.exists(rc.MANIFEST):
         pytest.skip("baseline/_ref/petsc/reftests.json not built (needs the build container)")
-    if not EXPECTED:
-        pytest.skip("no cases recorded yet")
+    if not cases:
+        pytest.skip("no cases recorded")
     manifest = {rc.case_id(c): c for c in json.load(open(rc.MANIFEST))}
-    missing = [e for e in EXPECTED if e not in manifest]
+    missing = [e for e in cases if e not in manifest]
     assert not missing, missing
     bad = []
-    for e in EXPECTED:
+    for e in cases:
         c = manifest[e]
         rc_h, out_h = rc.run_case(c, False)
         rc_d, out_d = rc.run_case(c, True)
@@ -33,3 +35,13 @@ def test_reference_device_variant_tests_pass_on_b200_types():
         if not ok:
             bad.append((e, why))
     assert not bad, bad
+
+
+def test_reference_device_variant_tests_pass_on_b200_types():
+    """The 63 cases that matched on a B200 (profiles/round2_ref_conformance.json)."""
+    _run(EXPECTED)
+
+
+@pytest.mark.xfail(strict=False, reason="fixed after the last GPU run of the round (vector object state on device writes); verified on the CPU mock device only")
+def test_cases_fixed_after_the_last_gpu_run():
+    _run(FIXED)
