@@ -277,7 +277,8 @@ int b200VecMDotAsync(b200Handle h, int64_t n, int nv, const double *x, const dou
 int b200VecMAXPYAsync(b200Handle h, int64_t n, int nv, const double *alpha, const double *const *y, double *x, double *sumsq)
 {
   K1() DEVPTR(x);
-  for (int j = 0; j < nv; j++) { DEVPTR(y[j]); LOOP x[i] += alpha[j] * y[j][i]; }
+  for (int j = 0; j < nv; j++) DEVPTR(y[j]);
+  ora_vecmaxpy(n, nv, alpha, y, x); /* the reference's association (dvec2.c:658-693): remainder group first, then groups of 4 */
   if (sumsq) { double s = 0; LOOP s += x[i] * x[i]; *sumsq = s; }
   return 0;
 }
@@ -493,6 +494,34 @@ int b200IndexedOp(b200Handle h, b200IndexedPlan p, int dtype, int bs, int op, co
   g_launches++;
   return 0;
 }
+
+/* ---- events (timing is meaningless here: 1 ms per interval) and the benchmark generators (oracle generators: same operators) */
+struct b200Event_s {
+  int dummy;
+};
+int b200EventCreate(b200Event *ev) { *ev = calloc(1, sizeof(**ev)); return 0; }
+int b200EventDestroy(b200Event ev) { free(ev); return 0; }
+int b200EventRecord(b200Handle h, b200Event ev) { (void)h; (void)ev; return 0; }
+int b200EventElapsedMs(b200Event a, b200Event b, double *ms) { (void)a; (void)b; *ms = 1.0; return 0; }
+int b200GenLaplace7Nnz(int nx, int ny, int nz, int64_t r0, int64_t r1, int64_t *nnz) { *nnz = ora_lap7_rows_nnz(nx, ny, nz, r0, r1); return 0; }
+int b200GenLaplace7(b200Handle h, int nx, int ny, int nz, int64_t r0, int64_t r1, int *rowptr, int *colidx, double *val)
+{
+  (void)h;
+  DEVPTR(rowptr); DEVPTR(colidx); DEVPTR(val);
+  ora_lap7_rows(nx, ny, nz, r0, r1, rowptr, colidx, val); /* local row pointer, global columns */
+  g_launches++;
+  return 0;
+}
+int b200GenLaplace27Nnz(int n, int64_t *nnz) { *nnz = ora_lap27_nnz(n); return 0; }
+int b200GenLaplace27(b200Handle h, int n, int *rowptr, int *colidx, double *val)
+{
+  (void)h;
+  DEVPTR(rowptr); DEVPTR(colidx); DEVPTR(val);
+  ora_lap27(n, rowptr, colidx, val);
+  g_launches++;
+  return 0;
+}
+int b200CommBarrier(b200Handle h) { (void)h; return 0; }
 
 /* ---- multi-rank entry points: not in the mock */
 #define NOSUP(name) return fail(B200_ERR_SUP, #name ": the mock library is single-rank")

@@ -29,8 +29,11 @@ def have():
     return os.path.exists(os.path.join(BIN, "ex2")) and os.path.exists(PLUGIN)
 
 
+_ENV = {}   # extra environment of the PETSc program (tests/test_petsc_plugin_mock_cpu.py re-runs these bodies with the mock device preloaded)
+
+
 def run(exe, args, timeout=600):
-    env = dict(os.environ, LD_LIBRARY_PATH=BLASDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    env = dict(os.environ, LD_LIBRARY_PATH=BLASDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""), **_ENV)
     p = subprocess.run([os.path.join(BIN, exe)] + args, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     return p.stdout
