@@ -1,5 +1,5 @@
 """The PETSc plugin's HOST LOGIC on the CPU: the reference's own device-variant test programs and KSP tutorials
-(tools/ref_conformance.py, 75 cases) run inside real PETSc with the plugin loaded and the b200 types selected, while the plugin's
+(tools/ref_conformance.py, 82 cases) run inside real PETSc with the plugin loaded and the b200 types selected, while the plugin's
 C-ABI calls are bound (LD_PRELOAD) to tests/mock/libb200mock.so, a host test double of libpetscb200.so with malloc'ed "device"
 memory and sequential kernels.  What is exercised is everything the plugin does around the kernels: offload masks, object states and
 PETSc's norm cache, lazy host arrays, mirror invalidation after MatSetValues / MatZeroEntries / COO, sub-classing of PCJACOBI and
@@ -52,7 +52,7 @@ def test_reference_programs_on_b200_types_through_the_mock_device():
     assert not bad, bad
     assert not gaps_now_passing, ("listed as known gaps but passing: update tests/ref_conformance_expected.json", gaps_now_passing)
     covered = {rc.case_id(c) for c in manifest}
-    assert set(EXP["expected_pass"]) | set(EXP["fixed_after_last_gpu_run"]) | set(EXP["known_gaps"]) == covered
+    assert set(EXP["expected_pass"]) | set(EXP["fixed_after_last_gpu_run"]) | set(EXP["added_after_last_gpu_run"]) | set(EXP["known_gaps"]) == covered
 
 
 def test_plugin_drivers_on_the_mock_device():

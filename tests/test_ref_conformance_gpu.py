@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 pytestmark = pytest.mark.gpu
 _EXP = json.load(open(os.path.join(ROOT, "tests", "ref_conformance_expected.json")))
 EXPECTED = _EXP["expected_pass"]
-FIXED = _EXP["fixed_after_last_gpu_run"]
+FIXED = _EXP["fixed_after_last_gpu_run"] + _EXP["added_after_last_gpu_run"]
 
 
 def _run(cases):
@@ -42,6 +42,6 @@ def test_reference_device_variant_tests_pass_on_b200_types():
     _run(EXPECTED)
 
 
-@pytest.mark.xfail(strict=False, reason="fixed after the last GPU run of the round (vector object state on device writes); verified on the CPU mock device only")
+@pytest.mark.xfail(strict=False, reason="fixed (vector object state on device writes) or added after the last GPU run of the round; verified on the CPU mock device only")
 def test_cases_fixed_after_the_last_gpu_run():
     _run(FIXED)

@@ -59,6 +59,12 @@ GENERIC = {
     "ksp/ksp/tutorials/ex34.c": [("1", "-pc_type mg -pc_mg_type full -ksp_type fgmres -ksp_monitor -pc_mg_levels 3 -mg_coarse_pc_factor_shift_type nonzero -ksp_view", "D")],
     "ksp/ksp/tutorials/ex45.c": [("jacobi", "-ksp_monitor -da_grid_x 21 -da_grid_y 21 -da_grid_z 21 -pc_type jacobi", "D"), ("ilu", "-ksp_monitor -da_grid_x 21 -da_grid_y 21 -da_grid_z 21 -pc_type ilu", "D"),
                                    ("2", "-ksp_monitor -da_grid_x 21 -da_grid_y 21 -da_grid_z 21 -pc_type mg -pc_mg_levels 3 -mg_levels_ksp_type richardson -mg_levels_ksp_max_it 1 -mg_levels_pc_type bjacobi", "D")],
+    # callers one layer up (Newton / time stepping on DMDA grids: re-assembled Jacobians, coloring, matrix-free, multigrid, fieldsplit)
+    "snes/tutorials/ex5.c": [("1", "-snes_monitor -ksp_monitor_short -da_grid_x 17 -da_grid_y 17", "D"), ("mg", "-snes_monitor -pc_type mg -da_refine 2 -snes_view", "D"),
+                               ("fd_color_ilu", "-snes_monitor -snes_fd_color -pc_type ilu -da_grid_x 12 -da_grid_y 12", "D"), ("mf", "-snes_monitor -snes_mf -pc_type none -da_grid_x 12 -da_grid_y 12", "D")],
+    "snes/tutorials/ex19.c": [("ilu", "-da_refine 2 -snes_monitor_short -pc_type ilu", "D"),
+                                ("fieldsplit", "-da_refine 2 -snes_monitor_short -pc_type fieldsplit -pc_fieldsplit_block_size 4 -pc_fieldsplit_type additive", "D")],
+    "ts/tutorials/ex3.c": [("1", "-ts_monitor -ts_max_steps 5 -nox", "T")],
     "ksp/ksp/tutorials/ex50.c": [("tut_1", "-da_grid_x 4 -da_grid_y 4 -mat_view", "D"), ("1", "-pc_type mg -pc_mg_type full -ksp_type cg -ksp_monitor -da_refine 3 -mg_coarse_pc_type svd -ksp_view", "D")],
 }
 TYPE_OPTS = {("T", False): "-mat_type aij -vec_type standard", ("T", True): "-mat_type aijb200 -vec_type b200",
