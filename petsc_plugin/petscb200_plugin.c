@@ -644,6 +644,40 @@ static PetscErrorCode PB_LocalVectorEnd(Vec v, Vec w, PetscBool write)
   if (write) ((Vec_SeqB200 *)v->data)->mask = PB_GPU;
   PetscFunctionReturn(PETSC_SUCCESS);
 }
+/* VecGetSubVector / VecRestoreSubVector (MatMult_Nest, PCFIELDSPLIT, VecNest ...).  The default implementation
+   (rvector.c:1699-1707) hands out, for a contiguous index set, a vector of X's type PLACED on X's host array; what the caller writes
+   into it -- on the device, if it is a b200 vector -- reaches that host array when the default VecRestoreSubVector resets the placed
+   array (our resetarray copies the device values down first).  X's offload mask has to follow: after such a restore the HOST array
+   is the valid copy.  The default code does this bookkeeping only for the device types it knows by name (rvector.c:1766-1795),
+   so the two ops wrap it.  Non-contiguous index sets take the default's scatter path, which goes through VecScatter on X itself. */
+static PetscErrorCode VecGetSubVector_SeqB200(Vec X, IS is, Vec *Y)
+{
+  PetscErrorCode (*self)(Vec, IS, Vec *) = X->ops->getsubvector;
+  PetscErrorCode ierr;
+  PetscFunctionBegin;
+  X->ops->getsubvector = NULL;
+  ierr                 = VecGetSubVector(X, is, Y);
+  X->ops->getsubvector = self;
+  PetscCall(ierr);
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode VecRestoreSubVector_SeqB200(Vec X, IS is, Vec *Y)
+{
+  PetscErrorCode (*self)(Vec, IS, Vec *) = X->ops->restoresubvector;
+  PetscErrorCode   ierr;
+  PetscObjectState before, after;
+  PetscObject      scatter = NULL;
+  PetscFunctionBegin;
+  PetscCall(PetscObjectQuery((PetscObject)*Y, "VecGetSubVector_Scatter", &scatter));
+  PetscCall(PetscObjectStateGet((PetscObject)X, &before));
+  X->ops->restoresubvector = NULL;
+  ierr                     = VecRestoreSubVector(X, is, Y);
+  X->ops->restoresubvector = self;
+  PetscCall(ierr);
+  PetscCall(PetscObjectStateGet((PetscObject)X, &after));
+  if (!scatter && after != before && PB_IsB200(X)) ((Vec_SeqB200 *)X->data)->mask = PB_CPU; /* the sub-vector was written: X's host array holds it */
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
 static PetscErrorCode VecGetLocalVector_B200(Vec v, Vec w) { return PB_LocalVectorBegin(v, w, PETSC_TRUE); }
 static PetscErrorCode VecRestoreLocalVector_B200(Vec v, Vec w) { return PB_LocalVectorEnd(v, w, PETSC_TRUE); }
 static PetscErrorCode VecGetLocalVectorRead_B200(Vec v, Vec w) { return PB_LocalVectorBegin(v, w, PETSC_FALSE); }
@@ -858,6 +892,8 @@ PETSC_EXTERN PetscErrorCode VecCreate_SeqB200(Vec v)
   v->ops->shift                      = VecShift_SeqB200;
   v->ops->duplicatevecs              = VecDuplicateVecs_B200;
   v->ops->destroyvecs                = VecDestroyVecs_B200;
+  v->ops->getsubvector               = VecGetSubVector_SeqB200;
+  v->ops->restoresubvector           = VecRestoreSubVector_SeqB200;
   v->ops->getlocalvector             = VecGetLocalVector_B200;
   v->ops->restorelocalvector         = VecRestoreLocalVector_B200;
   v->ops->getlocalvectorread         = VecGetLocalVectorRead_B200;
