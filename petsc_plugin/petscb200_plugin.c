@@ -954,6 +954,23 @@ typedef struct {
   b200CooPlan coo;
 } Mat_B200;
 
+/* The context of a seqaijb200 matrix.  It can be absent: MatHeaderMerge() keeps A's ops but takes the other matrix's data AND spptr
+   (gcreate.c:449-486) -- e.g. the in-place MatLUFactor() / MatPermute() of a seqaijb200 matrix end with our ops on top of a plain
+   MATSEQAIJ's data.  The context is then rebuilt on first use: the parent's entry points are the same for every MATSEQAIJ (captured
+   at the first conversion), the device mirror is simply not there yet (valid = false). */
+static Mat_B200  PB_MatParent;
+static PetscBool PB_MatParentSet = PETSC_FALSE;
+static Mat_B200 *PB_M(Mat A)
+{
+  if (!A->spptr && PB_MatParentSet) {
+    Mat_B200 *m = NULL;
+    if (PetscNew(&m) != PETSC_SUCCESS) return NULL;
+    *m       = PB_MatParent;
+    A->spptr = m;
+  }
+  return (Mat_B200 *)A->spptr;
+}
+
 static PetscErrorCode PB_MatFreeDevice(Mat_B200 *m)
 {
   PetscFunctionBegin;
@@ -1005,7 +1022,7 @@ static PetscErrorCode PB_MatSync(Mat A)
 }
 static PetscErrorCode PB_MatSyncEx(Mat A, PetscBool need_assembled)
 {
-  Mat_B200        *m = (Mat_B200 *)A->spptr;
+  Mat_B200        *m = PB_M(A);
   Mat_SeqAIJ      *a = (Mat_SeqAIJ *)A->data;
   PetscObjectState st;
   const PetscInt   nr = A->rmap->n;
@@ -1050,7 +1067,7 @@ static PetscErrorCode PB_MatSyncEx(Mat A, PetscBool need_assembled)
    master copy): adopt the arrays instead of uploading the same data again */
 static PetscErrorCode PB_MatAdoptDevice(Mat A, int *d_i, int *d_j, double *d_a)
 {
-  Mat_B200        *m = (Mat_B200 *)A->spptr;
+  Mat_B200        *m = PB_M(A);
   Mat_SeqAIJ      *a = (Mat_SeqAIJ *)A->data;
   PetscObjectState st;
   PetscFunctionBegin;
@@ -1078,7 +1095,7 @@ static PetscErrorCode PB_MatAdoptDevice(Mat A, int *d_i, int *d_j, double *d_a)
 
 static PetscErrorCode MatMult_SeqAIJB200(Mat A, Vec x, Vec y)
 {
-  Mat_B200     *m = (Mat_B200 *)A->spptr;
+  Mat_B200     *m = PB_M(A);
   Mat_SeqAIJ   *a = (Mat_SeqAIJ *)A->data;
   const double *dx;
   double       *dy;
@@ -1095,7 +1112,7 @@ static PetscErrorCode MatMult_SeqAIJB200(Mat A, Vec x, Vec y)
 }
 static PetscErrorCode MatMultAdd_SeqAIJB200(Mat A, Vec x, Vec y, Vec z)
 {
-  Mat_B200     *m = (Mat_B200 *)A->spptr;
+  Mat_B200     *m = PB_M(A);
   Mat_SeqAIJ   *a = (Mat_SeqAIJ *)A->data;
   const double *dx, *dy;
   double       *dz;
@@ -1125,7 +1142,7 @@ static PetscErrorCode MatMultAdd_SeqAIJB200(Mat A, Vec x, Vec y, Vec z)
 }
 static PetscErrorCode MatGetDiagonal_SeqAIJB200(Mat A, Vec v)
 {
-  Mat_B200 *m = (Mat_B200 *)A->spptr;
+  Mat_B200 *m = PB_M(A);
   double   *dv;
   PetscFunctionBegin;
   if (PB_BoundToCPU(A) || !PB_IsB200(v)) { /* host vector: the parent's loop over a->diag */
@@ -1146,7 +1163,7 @@ static PetscErrorCode MatGetDiagonal_SeqAIJB200(Mat A, Vec v)
 /* MatMultTranspose[Add]_SeqAIJ (aij.c:1383-1440) on the explicit transposed pattern: bit-identical accumulation order */
 static PetscErrorCode PB_MatSyncTranspose(Mat A)
 {
-  Mat_B200 *m = (Mat_B200 *)A->spptr;
+  Mat_B200 *m = PB_M(A);
   PetscFunctionBegin;
   PetscCall(PB_MatSync(A)); /* may drop m->T when the pattern changed */
   if (!m->T) {
@@ -1166,7 +1183,7 @@ static PetscErrorCode PB_MatSyncTranspose(Mat A)
 }
 static PetscErrorCode MatMultTranspose_SeqAIJB200(Mat A, Vec x, Vec y)
 {
-  Mat_B200     *m = (Mat_B200 *)A->spptr;
+  Mat_B200     *m = PB_M(A);
   const double *dx;
   double       *dy;
   PetscFunctionBegin;
@@ -1186,7 +1203,7 @@ static PetscErrorCode MatMultTranspose_SeqAIJB200(Mat A, Vec x, Vec y)
 }
 static PetscErrorCode MatMultTransposeAdd_SeqAIJB200(Mat A, Vec x, Vec z, Vec y)
 {
-  Mat_B200     *m = (Mat_B200 *)A->spptr;
+  Mat_B200     *m = PB_M(A);
   const double *dx, *dz;
   double       *dy;
   PetscFunctionBegin;
@@ -1229,7 +1246,7 @@ static PetscErrorCode MatGetCurrentMemType_SeqAIJB200(Mat A, PetscMemType *mtype
    device-resident v[] are bit-identical to the reference's, then mirrored into the host array. */
 static PetscErrorCode MatSetPreallocationCOO_SeqAIJB200(Mat A, PetscCount n, PetscInt coo_i[], PetscInt coo_j[])
 {
-  Mat_B200            *m = (Mat_B200 *)A->spptr;
+  Mat_B200            *m = PB_M(A);
   int                  dev_i = 0, dev_j = 0;
   PetscInt            *hi = coo_i, *hj = coo_j;
   PetscContainer       container;
@@ -1259,7 +1276,7 @@ static PetscErrorCode MatSetPreallocationCOO_SeqAIJB200(Mat A, PetscCount n, Pet
 }
 static PetscErrorCode MatSetValuesCOO_SeqAIJB200(Mat A, const PetscScalar v[], InsertMode imode)
 {
-  Mat_B200        *m = (Mat_B200 *)A->spptr;
+  Mat_B200        *m = PB_M(A);
   Mat_SeqAIJ      *a = (Mat_SeqAIJ *)A->data;
   int              dev = 0;
   PetscObjectState st;
@@ -1305,7 +1322,7 @@ static PetscErrorCode MatProductSetFromOptions_SeqDense_SeqAIJB200(Mat C)
 
 static PetscErrorCode MatDestroy_SeqAIJB200(Mat A)
 {
-  Mat_B200 *m = (Mat_B200 *)A->spptr;
+  Mat_B200 *m = PB_M(A);
   PetscErrorCode (*destroy)(Mat) = m->destroy_seqaij;
   PetscFunctionBegin;
   PetscCall(PB_MatFreeDevice(m));
@@ -1321,7 +1338,7 @@ static PetscErrorCode MatDestroy_SeqAIJB200(Mat A)
 PETSC_EXTERN PetscErrorCode MatConvert_SeqAIJ_SeqAIJB200(Mat A, MatType type, MatReuse reuse, Mat *newmat);
 static PetscErrorCode       MatDuplicate_SeqAIJB200(Mat A, MatDuplicateOption op, Mat *B)
 {
-  Mat_B200 *m = (Mat_B200 *)A->spptr;
+  Mat_B200 *m = PB_M(A);
   PetscFunctionBegin;
   PetscCall((*m->duplicate_seqaij)(A, op, B));
   PetscCall(MatConvert_SeqAIJ_SeqAIJB200(*B, MATSEQAIJB200, MAT_INPLACE_MATRIX, B));
@@ -1351,6 +1368,10 @@ PETSC_EXTERN PetscErrorCode MatConvert_SeqAIJ_SeqAIJB200(Mat A, MatType type, Ma
   m->multtransposeadd_seqaij = B->ops->multtransposeadd;
   PetscCall(PetscObjectQueryFunction((PetscObject)B, "MatSetPreallocationCOO_C", &m->coo_prealloc_seqaij));
   PetscCall(PetscObjectQueryFunction((PetscObject)B, "MatSetValuesCOO_C", &m->coo_setvalues_seqaij));
+  if (!PB_MatParentSet) {
+    PB_MatParent    = *m; /* entry points only: the device fields are still zero */
+    PB_MatParentSet = PETSC_TRUE;
+  }
   B->spptr            = m;
   B->ops->mult        = MatMult_SeqAIJB200;
   B->ops->multadd     = MatMultAdd_SeqAIJB200;
@@ -1462,7 +1483,7 @@ static PetscErrorCode MatLUFactorNumeric_FactorB200(Mat F, Mat A, const MatFacto
   PetscFunctionBegin;
   if (A->ops->mult == MatMult_SeqAIJB200) {
     PetscCall(PB_MatSync(A));
-    d_a = ((Mat_B200 *)A->spptr)->d_a;
+    d_a = (PB_M(A))->d_a;
   } else {
     Mat_SeqAIJ *a = (Mat_SeqAIJ *)A->data;
     if (!f->d_aval_tmp) PetscCallB200(b200Malloc(PB_h, (void **)&f->d_aval_tmp, sizeof(double) * ((size_t)a->nz + 1)));
@@ -1538,7 +1559,7 @@ static PetscErrorCode MatCholeskyFactorNumeric_FactorB200(Mat F, Mat A, const Ma
   PetscFunctionBegin;
   if (A->ops->mult == MatMult_SeqAIJB200) {
     PetscCall(PB_MatSync(A));
-    d_a = ((Mat_B200 *)A->spptr)->d_a;
+    d_a = (PB_M(A))->d_a;
   } else {
     Mat_SeqAIJ *a = (Mat_SeqAIJ *)A->data;
     if (!f->d_aval_tmp) PetscCallB200(b200Malloc(PB_h, (void **)&f->d_aval_tmp, sizeof(double) * ((size_t)a->nz + 1)));
@@ -1902,6 +1923,7 @@ typedef struct {
   Mat              mat;
   PetscBool        fuse, usable;
   PetscErrorCode (*apply_parent)(PC, Vec, Vec);
+  PetscErrorCode (*getdiagonal_parent)(PC, Vec, Vec);
 } PC_JacobiB200;
 
 static PetscErrorCode PB_JacobiCtx(PC pc, PC_JacobiB200 **jac)
@@ -1976,7 +1998,7 @@ static PetscErrorCode PCApplyBA_JacobiB200(PC pc, PCSide side, Vec x, Vec y, Vec
   PetscCall(PB_JacobiCtx(pc, &jac));
   if (side == PC_LEFT) PetscCall(PB_JacobiRefresh(pc, jac));
   if (side == PC_LEFT && jac->usable && PB_IsB200(x) && PB_IsB200(y) && A->ops->mult == MatMult_SeqAIJB200 && !PB_BoundToCPU(A)) {
-    Mat_B200     *m = (Mat_B200 *)A->spptr;
+    Mat_B200     *m = PB_M(A);
     Mat_SeqAIJ   *a = (Mat_SeqAIJ *)A->data;
     const double *dx, *dd;
     double       *dy;
@@ -1992,7 +2014,7 @@ static PetscErrorCode PCApplyBA_JacobiB200(PC pc, PCSide side, Vec x, Vec y, Vec
     /* mpiaij.c:1047-1061 + jacobi.c:354 fused: diagonal block writes w = dinv.*(A_d x) while the halo travels; the rows
        that own off-diagonal entries are then redone with both blocks in the reference's order */
     Mat_MPIAIJB200 *mp = (Mat_MPIAIJB200 *)A->data;
-    Mat_B200       *mA = (Mat_B200 *)mp->A->spptr, *mB = (Mat_B200 *)mp->B->spptr;
+    Mat_B200       *mA = PB_M(mp->A), *mB = PB_M(mp->B);
     Mat_SeqAIJ     *sA = (Mat_SeqAIJ *)mp->A->data, *sB = (Mat_SeqAIJ *)mp->B->data;
     const double   *dx, *dd, *dlr;
     double         *dy, *dl;
@@ -2031,6 +2053,24 @@ static PetscErrorCode PCApplyBA_JacobiB200(PC pc, PCSide side, Vec x, Vec y, Vec
   }
   PetscFunctionReturn(PETSC_SUCCESS);
 }
+/* PCJacobiGetDiagonal(): the parent copies out the (inverted) diagonal its own apply created lazily (jacobi.c:144-157: "Use PCApply
+   to force creation"); when the sub-class applied the preconditioner from its device copy the parent never made one */
+static PetscErrorCode PCJacobiGetDiagonal_JacobiB200(PC pc, Vec diag, Vec diagsqrt)
+{
+  PC_JacobiB200 *jac;
+  PetscFunctionBegin;
+  PetscCall(PB_JacobiCtx(pc, &jac));
+  if (diag && !diagsqrt && jac->usable && jac->dinv) {
+    PetscCall(PB_JacobiRefresh(pc, jac));
+    if (jac->usable) {
+      PetscCall(VecCopy(jac->dinv, diag));
+      PetscFunctionReturn(PETSC_SUCCESS);
+    }
+  }
+  PetscCheck(jac->getdiagonal_parent, PetscObjectComm((PetscObject)pc), PETSC_ERR_SUP, "PCJacobiGetDiagonal is not available");
+  PetscCall((*jac->getdiagonal_parent)(pc, diag, diagsqrt));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
 PETSC_EXTERN PetscErrorCode PCCreate_JacobiB200(PC pc)
 {
   PC_JacobiB200 *jac;
@@ -2045,6 +2085,8 @@ PETSC_EXTERN PetscErrorCode PCCreate_JacobiB200(PC pc)
   PetscCall(PetscContainerSetCtxDestroy(c, PB_JacobiCtxDestroy));
   PetscCall(PetscObjectCompose((PetscObject)pc, "PCJacobiB200_ctx", (PetscObject)c));
   PetscCall(PetscContainerDestroy(&c));
+  PetscCall(PetscObjectQueryFunction((PetscObject)pc, "PCJacobiGetDiagonal_C", &jac->getdiagonal_parent));
+  PetscCall(PetscObjectComposeFunction((PetscObject)pc, "PCJacobiGetDiagonal_C", PCJacobiGetDiagonal_JacobiB200));
   jac->apply_parent       = pc->ops->apply;
   pc->ops->apply          = PCApply_JacobiB200;
   pc->ops->applytranspose = PCApply_JacobiB200;

@@ -1,5 +1,5 @@
 """The PETSc plugin's HOST LOGIC on the CPU: the reference's own device-variant test programs and KSP tutorials
-(tools/ref_conformance.py, 82 cases) run inside real PETSc with the plugin loaded and the b200 types selected, while the plugin's
+(tools/ref_conformance.py, 85 cases) run inside real PETSc with the plugin loaded and the b200 types selected, while the plugin's
 C-ABI calls are bound (LD_PRELOAD) to tests/mock/libb200mock.so, a host test double of libpetscb200.so with malloc'ed "device"
 memory and sequential kernels.  What is exercised is everything the plugin does around the kernels: offload masks, object states and
 PETSc's norm cache, lazy host arrays, mirror invalidation after MatSetValues / MatZeroEntries / COO, sub-classing of PCJACOBI and

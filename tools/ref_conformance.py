@@ -65,6 +65,11 @@ GENERIC = {
     "snes/tutorials/ex19.c": [("ilu", "-da_refine 2 -snes_monitor_short -pc_type ilu", "D"),
                                 ("fieldsplit", "-da_refine 2 -snes_monitor_short -pc_type fieldsplit -pc_fieldsplit_block_size 4 -pc_fieldsplit_type additive", "D")],
     "ts/tutorials/ex3.c": [("1", "-ts_monitor -ts_max_steps 5 -nox", "T")],
+    # found by sweeping the reference's tests on the mock device: in-place LU / MatPermute end in MatHeaderMerge (our ops, the other
+    # matrix's data and a NULL spptr); PCJacobiGetDiagonal after the sub-class applied the PC
+    "mat/tests/ex15.c": [("1", "", "T")],
+    "mat/tests/ex68.c": [("1", "", "T")],
+    "ksp/ksp/tests/ex4.c": [("1", "-ksp_monitor -m 5 -pc_type jacobi -ksp_gmres_cgs_refinement_type refine_always", "T")],
     "ksp/ksp/tutorials/ex50.c": [("tut_1", "-da_grid_x 4 -da_grid_y 4 -mat_view", "D"), ("1", "-pc_type mg -pc_mg_type full -ksp_type cg -ksp_monitor -da_refine 3 -mg_coarse_pc_type svd -ksp_view", "D")],
 }
 TYPE_OPTS = {("T", False): "-mat_type aij -vec_type standard", ("T", True): "-mat_type aijb200 -vec_type b200",
