@@ -27,6 +27,8 @@ make -s -C "$ROOT/petsc_plugin" PETSC_INC="$INC" PETSC_LIBDIR="$OUT/lib"
 /usr/bin/gcc -O2 -o "$OUT/bin/plugin_driver" "$ROOT/petsc_plugin/plugin_driver.c" $INC -I"$ROOT/include" $LNK -L"$ROOT/petsc_b200/lib" -lpetscb200 -Wl,-rpath,\$ORIGIN/../../../../petsc_b200/lib
 # VecScatter / PetscSF on device vectors against the host types (tests/test_petsc_plugin_{cpu,gpu}.py)
 /usr/bin/gcc -O2 -std=gnu11 -Wall -o "$OUT/bin/sf_driver" "$ROOT/petsc_plugin/sf_driver.c" $INC -I"$ROOT/include" $LNK -L"$ROOT/petsc_b200/lib" -lpetscb200 -Wl,-rpath,\$ORIGIN/../../../../petsc_b200/lib
+# one check per host/device coherence rule of the plugin (found with the reference's own programs)
+/usr/bin/gcc -O2 -std=gnu11 -Wall -o "$OUT/bin/coherence_driver" "$ROOT/petsc_plugin/coherence_driver.c" $INC $LNK
 # the PETSc program that runs the BASELINE workloads on the b200 types (bench.py, tools/, GPU tests): executable + shared object
 DRV_LNK="-L$ROOT/petsc_plugin -lpetscb200plugin -L$ROOT/petsc_b200/lib -lpetscb200 -L$OUT/lib -lpetsc -Wl,-rpath,\$ORIGIN -Wl,-rpath,\$ORIGIN/../petsc_b200/lib -Wl,-rpath,\$ORIGIN/../baseline/_ref/petsc/lib -Wl,-rpath,$BLASDIR -Wl,-rpath-link,$BLASDIR -Wl,--allow-shlib-undefined -lm"
 /usr/bin/gcc -O2 -g -std=gnu11 -Wall -Wno-unused-parameter -Wno-format-truncation -o "$ROOT/petsc_plugin/b200_driver" "$ROOT/petsc_plugin/b200_driver.c" $INC -I"$ROOT/include" $DRV_LNK

@@ -138,6 +138,7 @@ typedef struct {
   double *d_sumsq; /* fused MAXPY+norm */
   double *h_sumsq; /* non-NULL: d_sumsq is the device alias of this mapped pinned host scalar (one rank: no all-reduce on it) */
   PetscObjectState sumsq_state;
+  int              host_writers; /* VecGetArray / VecGetArrayWrite handed the host array out for writing and it is not restored yet */
   struct PB_Slab  *slab;       /* VecDuplicateVecs: d points into one shared device allocation (bvec2.c:670-691) */
   double          *lv_saved_d; /* VecGetLocalVector*: this vector's own device array while it aliases another's */
   int              lv_saved_mask, lv_active;
@@ -245,6 +246,7 @@ static PetscErrorCode VecGetArray_SeqB200(Vec v, PetscScalar **a)
   PetscFunctionBegin;
   PetscCall(PB_VecToHost(v));
   b->mask = PB_CPU;
+  b->host_writers++;
   *a      = b->seq.array;
   PetscFunctionReturn(PETSC_SUCCESS);
 }
@@ -263,13 +265,20 @@ static PetscErrorCode VecGetArrayWrite_SeqB200(Vec v, PetscScalar **a)
   PetscFunctionBegin;
   PetscCall(PB_VecHostAlloc(v));
   b->mask = PB_CPU;
+  b->host_writers++;
   *a      = b->seq.array;
   PetscFunctionReturn(PETSC_SUCCESS);
 }
+/* the end of a host WRITE access: the host array is the valid copy from here on, whatever happened in between (the reference's
+   device vectors set PETSC_OFFLOAD_CPU in their restore as well).  Programs do call Vec operations on a vector whose array they
+   hold -- ts/tutorials/ex10.c: DMDAVecGetArray(F); VecZeroEntries(F); fill; Restore -- which on VECSEQ act on the very memory the
+   caller is filling; VecSet therefore works on the host array while it is handed out (VecSet_SeqB200). */
 static PetscErrorCode VecRestoreArray_SeqB200(Vec v, PetscScalar **a)
 {
+  Vec_SeqB200 *b = (Vec_SeqB200 *)v->data;
   PetscFunctionBegin;
-  (void)v;
+  if (b->host_writers > 0) b->host_writers--;
+  b->mask = PB_CPU;
   if (a) *a = NULL;
   PetscFunctionReturn(PETSC_SUCCESS);
 }
@@ -325,6 +334,10 @@ static PetscErrorCode VecSet_SeqB200(Vec x, PetscScalar a)
   double *d;
   PetscFunctionBegin;
   if (!x->map->n) PetscFunctionReturn(PETSC_SUCCESS);
+  if (((Vec_SeqB200 *)x->data)->host_writers > 0) { /* somebody holds the host array for writing: set THAT memory, as VECSEQ would */
+    PetscCall((*PB_VecSeqOps.set)(x, a));
+    PetscFunctionReturn(PETSC_SUCCESS);
+  }
   PetscCall(PB_VecWrite(x, &d));
   PetscCallB200(b200VecSet(PB_h, N_(x), a, d));
   PetscFunctionReturn(PETSC_SUCCESS);

@@ -56,7 +56,9 @@ def test_reference_programs_on_b200_types_through_the_mock_device():
 
 
 def test_plugin_drivers_on_the_mock_device():
-    """petsc_plugin/sf_driver.c (VecScatter / PetscSF on b200 vectors: the device branch of the PetscSF sub-class, staging of mixed
+    """petsc_plugin/coherence_driver.c (one check per host/device coherence rule the reference's programs exposed: norm cache vs
+    device writes, Vec operations on a handed-out host array, sub-vectors written on the device, MatHeaderMerge, PCJacobiGetDiagonal,
+    value updates between solves), petsc_plugin/sf_driver.c (VecScatter / PetscSF on b200 vectors: the device branch of the PetscSF sub-class, staging of mixed
     and in-place scatters) and petsc_plugin/plugin_driver.c (COO from device-resident arrays, transposed products, MatBindToCPU) with
     the b200 types on the mock device: every check equals the host types bit for bit."""
     import subprocess
@@ -64,7 +66,11 @@ def test_plugin_drivers_on_the_mock_device():
     env = dict(os.environ, LD_LIBRARY_PATH=rc.BLASDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""), LD_PRELOAD=rc.MOCK)
     for exe, extra, must in (("sf_driver", [], ["vec type seqb200", "general scatter: 6 operations on the device, 0 staged through the host", "ok mixed_scatters_were_staged",
                                                   "ok sf_operations_ran_where_expected", "ok sf_new_graph_replans", "all ok"]),
-                             ("plugin_driver", ["-mat_b200_spmv_ordered"], ["ok coo_device_insert_equals_reference", "ok matmulttransposeadd_inplace_bit_exact", "ok matmult_bound_to_cpu", "all ok"])):
+                             ("plugin_driver", ["-mat_b200_spmv_ordered"], ["ok coo_device_insert_equals_reference", "ok matmulttransposeadd_inplace_bit_exact", "ok matmult_bound_to_cpu", "all ok"]),
+                             ("coherence_driver", [], ["mat type seqaijb200 vec type seqb200", "ok norm_after_matmult_is_not_the_cached_one", "ok vecset_zero_after_device_write",
+                                                       "ok vecset_while_host_array_is_handed_out", "ok subvector_written_on_device_then_parent_read",
+                                                       "ok second_solve_after_value_update_bcgs_jacobi", "ok pcjacobigetdiagonal_after_solve", "ok inplace_lu_solve",
+                                                       "ok destroy_after_headermerge", "all ok"])):
         path = os.path.join(ROOT, "baseline", "_ref", "petsc", "bin", exe)
         if not os.path.exists(path):
             pytest.skip(exe + " not built")
