@@ -70,6 +70,7 @@ typedef struct b200Event_s *b200Event;
 int b200EventCreate(b200Event *ev);
 int b200EventDestroy(b200Event ev);
 int b200EventRecord(b200Handle h, b200Event ev);
+int b200EventSynchronize(b200Event ev);               /* host waits for the work recorded BEFORE ev only (later kernels keep running) */
 int b200EventElapsedMs(b200Event start, b200Event stop, double *ms); /* synchronises on stop */
 
 /* ---- memory (replaces cudaMalloc/cudaMemcpy in aijcusparse.cu:1477-1590, veccupmimpl.h:391-440) ---- */

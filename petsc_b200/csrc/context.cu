@@ -226,6 +226,12 @@ extern "C" int b200EventRecord(b200Handle h, b200Event ev)
   B200_CUDA(cudaEventRecord(ev->ev, h->stream));
   return 0;
 }
+extern "C" int b200EventSynchronize(b200Event ev)
+{
+  B200_CHECK(ev, B200_ERR_ARG_NULL, "null event");
+  B200_CUDA(cudaEventSynchronize(ev->ev));
+  return 0;
+}
 extern "C" int b200EventElapsedMs(b200Event a, b200Event b, double *ms)
 {
   B200_CHECK(a && b && ms, B200_ERR_ARG_NULL, "null argument");

@@ -12,6 +12,7 @@
  *   PCRegister             "jacobib200" and (unless -b200_keep_pcjacobi) "jacobi": the reference's PCJACOBI sub-classed with a
  *                          fused ops->applyBA (src/ksp/pc/interface/pcregis.c, precon.c:810-865)
  *   KSPRegister            "pipecgb200": single-reduction CG, one reduction kernel + one recurrence kernel per iteration
+ *                          "pgmresb200": pipelined GMRES, the one reduction of an iteration is read one iteration after its launch
  *   VecRegister            "mpib200";  MatRegister "mpiaijb200": the row-partitioned types over NCCL ranks (one process per GPU)
  *   PetscSFRegister        "b200" and (unless -b200_keep_sfbasic) "basic": PETSCSFBASIC sub-classed so that VecScatter / PetscSF
  *                          broadcasts and reductions on device data run as device kernels (src/vec/is/sf/interface/sfregi.c:78)
@@ -47,6 +48,7 @@
 #define MATSOLVERB200 "b200"
 #define PCJACOBIB200  "jacobib200"
 #define KSPPIPECGB200 "pipecgb200"
+#define KSPPGMRESB200 "pgmresb200"
 
 #define VECMPIB200    "mpib200"
 #define MATMPIAIJB200 "mpiaijb200"
@@ -2247,6 +2249,303 @@ PETSC_EXTERN PetscErrorCode KSPCreate_PipeCGB200(KSP ksp)
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
+/* ================================================================== KSP "pgmresb200": pipelined GMRES, one reduction per iteration,
+   read one iteration after it was launched (the GMRES half).  The method is Ghysels, Ashby, Meerbergen & Vanroose's
+   p(1)-GMRES, the one behind the reference's KSPPGMRES (src/ksp/ksp/impls/gmres/pgmres/pgmres.c): the iterates and the residual
+   history are those of -ksp_type pgmres (reference-run fixtures, 1e-12 * r0).  The reference overlaps an MPI reduction with the
+   next matrix product through VecMDotBegin/End; on one GPU its split phase computes the local part synchronously, so nothing
+   overlaps.  Here the reduction of iteration j -- ONE VecMDot kernel writing into mapped pinned memory, the norm fused into the
+   VecMAXPY before it -- is launched, an event recorded, and the host reads the results in iteration j+1 AFTER it has queued that
+   iteration's fused B*A product: the host waits for the event only, the device keeps working on the product.  One host wait per
+   iteration where KSPGMRES needs two (after VecMDot, after VecNorm).  Host vectors / several ranks: the same algorithm through the
+   public Vec interface (every reduction then synchronises where it is issued).
+   Left preconditioning, preconditioned residual norm, restart = -ksp_gmres_restart (30). */
+typedef struct {
+  PetscInt     max_k;
+  Vec         *vv; /* max_k + 3 basis vectors; work[0], work[1] = temp, tmat */
+  PetscScalar *hh, *hes, *grs, *cc, *ss, *nrs, *work;
+  double      *h_red, *d_red; /* mapped pinned: results of the pending VecMDot (max_k + 3 doubles) */
+  b200Event    ev;
+  PetscBool    async;
+  /* what is pending from the previous iteration */
+  PetscInt     pend_mdot; /* number of dot products in flight (0 = none); they are column pend_col of H */
+  PetscInt     pend_col;
+  Vec          pend_norm_vec; /* the vector whose fused |.|^2 is in flight (NULL = none) */
+  PetscReal    pend_norm;     /* generic path: the value itself */
+} KSP_PGMRESB200;
+#define PG_HH(a, b)  (pg->hh + (size_t)(b) * (pg->max_k + 2) + (a))
+#define PG_HES(a, b) (pg->hes + (size_t)(b) * (pg->max_k + 2) + (a))
+
+static PetscErrorCode KSPSetUp_PGMRESB200(KSP ksp)
+{
+  KSP_PGMRESB200 *pg = (KSP_PGMRESB200 *)ksp->data;
+  const size_t    hs = (size_t)(pg->max_k + 2) * (pg->max_k + 2);
+  PetscFunctionBegin;
+  if (pg->vv) PetscFunctionReturn(PETSC_SUCCESS);
+  PetscCall(KSPSetWorkVecs(ksp, 2));
+  PetscCall(KSPCreateVecs(ksp, pg->max_k + 3, &pg->vv, 0, NULL));
+  PetscCall(PetscCalloc7(hs, &pg->hh, hs, &pg->hes, pg->max_k + 3, &pg->grs, pg->max_k + 3, &pg->cc, pg->max_k + 3, &pg->ss, pg->max_k + 3, &pg->nrs, pg->max_k + 3, &pg->work));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode KSPReset_PGMRESB200(KSP ksp)
+{
+  KSP_PGMRESB200 *pg = (KSP_PGMRESB200 *)ksp->data;
+  PetscFunctionBegin;
+  if (pg->vv) PetscCall(VecDestroyVecs(pg->max_k + 3, &pg->vv));
+  PetscCall(PetscFree7(pg->hh, pg->hes, pg->grs, pg->cc, pg->ss, pg->nrs, pg->work));
+  if (pg->h_red) PetscCallB200(b200FreeHost(pg->h_red));
+  pg->h_red = pg->d_red = NULL;
+  if (pg->ev) PetscCallB200(b200EventDestroy(pg->ev));
+  pg->ev = NULL;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode KSPDestroy_PGMRESB200(KSP ksp)
+{
+  PetscFunctionBegin;
+  PetscCall(KSPReset_PGMRESB200(ksp));
+  PetscCall(KSPDestroyDefault(ksp));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode KSPSetFromOptions_PGMRESB200(KSP ksp, PetscOptionItems PetscOptionsObject)
+{
+  KSP_PGMRESB200 *pg = (KSP_PGMRESB200 *)ksp->data;
+  PetscInt        restart = pg->max_k;
+  PetscBool       flg;
+  PetscFunctionBegin;
+  PetscOptionsHeadBegin(PetscOptionsObject, "KSP pgmresb200 options");
+  PetscCall(PetscOptionsInt("-ksp_gmres_restart", "Number of Krylov search directions", "KSPGMRESSetRestart", restart, &restart, &flg));
+  if (flg) {
+    PetscCheck(restart >= 1, PetscObjectComm((PetscObject)ksp), PETSC_ERR_ARG_OUTOFRANGE, "restart must be positive");
+    if (restart != pg->max_k) {
+      PetscCall(KSPReset_PGMRESB200(ksp));
+      pg->max_k        = restart;
+      ksp->setupstage  = KSP_SETUP_NEW;
+    }
+  }
+  PetscCall(PetscOptionsBool("-ksp_pgmresb200_async", "Launch the reduction and read it one iteration later (device vectors, one rank)", "", pg->async, &pg->async, NULL));
+  PetscOptionsHeadEnd();
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+/* "VecMDotBegin(z, nv, VV, H(:,col))" */
+static PetscErrorCode PG_MDotBegin(KSP_PGMRESB200 *pg, PetscBool dev, Vec z, PetscInt nv, PetscInt col)
+{
+  PetscFunctionBegin;
+  if (dev) {
+    const double  *dz;
+    const double **yp;
+    PetscCall(PB_VecRead(z, &dz));
+    PetscCall(PetscMalloc1(nv, &yp));
+    for (PetscInt j = 0; j < nv; j++) PetscCall(PB_VecRead(pg->vv[j], &yp[j]));
+    PetscCallB200(b200VecMDotAsync(PB_h, N_(z), (int)nv, dz, yp, pg->d_red));
+    PetscCallB200(b200EventRecord(PB_h, pg->ev)); /* everything the next iteration has to wait for is before this point */
+    PetscCall(PetscFree(yp));
+    PetscCall(PetscLogFlops(2.0 * nv * z->map->n));
+    pg->pend_mdot = nv;
+    pg->pend_col  = col;
+  } else {
+    PetscCall(VecMDot(z, nv, pg->vv, PG_HH(0, col)));
+    pg->pend_mdot = 0;
+  }
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+/* "VecNormBegin(v)" right after the VecMAXPY that produced v: on the device the squared norm is already in flight (fused) */
+static PetscErrorCode PG_NormBegin(KSP_PGMRESB200 *pg, PetscBool dev, Vec v)
+{
+  PetscFunctionBegin;
+  pg->pend_norm_vec = NULL;
+  if (dev) {
+    Vec_SeqB200     *b = (Vec_SeqB200 *)v->data;
+    PetscObjectState st;
+    PetscCall(PetscObjectStateGet((PetscObject)v, &st));
+    if (b->h_sumsq && b->sumsq_state == st) {
+      pg->pend_norm_vec = v;
+      PetscFunctionReturn(PETSC_SUCCESS);
+    }
+  }
+  PetscCall(VecNorm(v, NORM_2, &pg->pend_norm));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+/* the End of both: one wait for the event recorded after the VecMDot launch */
+static PetscErrorCode PG_ReductionsEnd(KSP_PGMRESB200 *pg)
+{
+  PetscFunctionBegin;
+  if (pg->pend_mdot || pg->pend_norm_vec) PetscCallB200(b200EventSynchronize(pg->ev));
+  if (pg->pend_mdot) {
+    for (PetscInt j = 0; j < pg->pend_mdot; j++) *PG_HH(j, pg->pend_col) = ((volatile double *)pg->h_red)[j];
+    pg->pend_mdot = 0;
+  }
+  if (pg->pend_norm_vec) {
+    pg->pend_norm     = PetscSqrtReal(*(volatile double *)((Vec_SeqB200 *)pg->pend_norm_vec->data)->h_sumsq);
+    pg->pend_norm_vec = NULL;
+  }
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode PG_Log(KSP ksp, PetscReal rnorm)
+{
+  PetscFunctionBegin;
+  PetscCall(KSPLogResidualHistory(ksp, rnorm));
+  PetscCall(KSPMonitor(ksp, ksp->its, rnorm));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode KSPSolve_PGMRESB200(KSP ksp)
+{
+  KSP_PGMRESB200 *pg = (KSP_PGMRESB200 *)ksp->data;
+  const PetscInt  max_k = pg->max_k;
+  Vec             x = ksp->vec_sol, b = ksp->vec_rhs, temp = ksp->work[0], tmat = ksp->work[1], *vv = pg->vv;
+  Mat             A, P;
+  PetscBool       dev = pg->async, guess_zero = ksp->guess_zero;
+  PetscInt        itcount = 0;
+  PetscReal       rnorm = -1.0;
+
+  PetscFunctionBegin;
+  PetscCall(PCGetOperators(ksp->pc, &A, &P));
+  if (PB_size > 1) dev = PETSC_FALSE; /* several ranks: the reductions are all-reduced where they are issued */
+  for (PetscInt j = 0; j < max_k + 3 && dev; j++) dev = PB_IsB200(vv[j]) ? PETSC_TRUE : PETSC_FALSE;
+  if (dev && !pg->h_red) {
+    PetscCall(PB_Init());
+    PetscCallB200(b200MallocMapped((void **)&pg->h_red, (void **)&pg->d_red, sizeof(double) * (size_t)(max_k + 3)));
+    PetscCallB200(b200EventCreate(&pg->ev));
+  }
+  ksp->its    = 0;
+  ksp->reason = KSP_CONVERGED_ITERATING;
+  while (!ksp->reason) {
+    PetscInt  it     = 0;
+    PetscBool hapend = PETSC_FALSE;
+    PetscReal resn;
+    /* KSPInitialResidual, left preconditioning (itres.c) */
+    if (!guess_zero) {
+      PetscCall(KSP_MatMult(ksp, A, x, temp));
+      PetscCall(VecCopy(b, tmat));
+      PetscCall(VecAXPY(tmat, -1.0, temp));
+      PetscCall(KSP_PCApply(ksp, tmat, vv[0]));
+    } else PetscCall(KSP_PCApply(ksp, b, vv[0]));
+    /* ---- one cycle (pgmres.c:17-174) ---- */
+    pg->pend_mdot     = 0;
+    pg->pend_norm_vec = NULL;
+    PetscCall(VecNorm(vv[0], NORM_2, &resn));
+    KSPCheckNorm(ksp, resn);
+    if (resn != 0.0) PetscCall(VecScale(vv[0], 1.0 / resn));
+    pg->grs[0] = resn;
+    rnorm      = resn;
+    ksp->rnorm = rnorm;
+    PetscCall(PG_Log(ksp, rnorm));
+    if (!resn) {
+      ksp->reason = KSP_CONVERGED_ATOL;
+      break;
+    }
+    PetscCall((*ksp->converged)(ksp, ksp->its, rnorm, &ksp->reason, ksp->cnvP));
+    for (; !ksp->reason; it++) {
+      Vec Zcur = vv[it], Znext = vv[it + 1];
+      if (it < max_k + 1 && ksp->its + 1 < PetscMax(2, ksp->max_it)) PetscCall(KSP_PCApplyBAorAB(ksp, Zcur, Znext, tmat)); /* Znext <- B A Zcur, queued BEFORE the wait */
+      PetscCall(PG_ReductionsEnd(pg));
+      if (it > 1) *PG_HH(it - 1, it - 2) = pg->pend_norm;
+      if (it > 1) {
+        PetscCall(VecScale(vv[it - 1], 1.0 / *PG_HH(it - 1, it - 2)));
+        { /* Hessenberg update of column it-2: copy, apply the previous rotations, new rotation (pgmres.c:226-301) */
+          const PetscInt c = it - 2;
+          PetscScalar   *h = PG_HH(0, c);
+          PetscReal      hapbnd;
+          for (PetscInt j = 0; j <= c + 1; j++) *PG_HES(j, c) = h[j];
+          hapbnd = PetscAbsScalar(h[c + 1] / pg->grs[c]);
+          if (hapbnd > 1.0e-30) hapbnd = 1.0e-30; /* ksp->haptol-like bound of the reference (gmres haptol default) */
+          if (PetscAbsScalar(h[c + 1]) < hapbnd) hapend = PETSC_TRUE;
+          for (PetscInt j = 0; j < c; j++) {
+            const PetscScalar hhj = h[j];
+            h[j]     = pg->cc[j] * hhj + pg->ss[j] * h[j + 1];
+            h[j + 1] = -pg->ss[j] * hhj + pg->cc[j] * h[j + 1];
+          }
+          if (!hapend) {
+            const PetscReal delta = PetscSqrtReal(h[c] * h[c] + h[c + 1] * h[c + 1]);
+            if (delta == 0.0) {
+              ksp->reason = KSP_DIVERGED_NULL;
+              break;
+            }
+            pg->cc[c]      = h[c] / delta;
+            pg->ss[c]      = h[c + 1] / delta;
+            h[c]           = pg->cc[c] * h[c] + pg->ss[c] * h[c + 1];
+            pg->grs[c + 1] = -pg->ss[c] * pg->grs[c];
+            pg->grs[c]     = pg->cc[c] * pg->grs[c];
+            resn           = PetscAbsScalar(pg->grs[c + 1]);
+          } else resn = 0.0;
+        }
+        ksp->its++;
+        rnorm      = resn;
+        ksp->rnorm = rnorm;
+        PetscCall((*ksp->converged)(ksp, ksp->its, rnorm, &ksp->reason, ksp->cnvP));
+        if (ksp->reason) break;
+        if (it < max_k + 1) PetscCall(PG_Log(ksp, rnorm));
+        if (hapend) {
+          ksp->reason = KSP_DIVERGED_BREAKDOWN;
+          break;
+        }
+        if (!(it < max_k + 1 && ksp->its < ksp->max_it)) break;
+        {
+          const PetscScalar sc = *PG_HH(it - 1, it - 2);
+          PetscCall(VecScale(Zcur, 1.0 / sc));
+          PetscCall(VecScale(Znext, 1.0 / sc));
+          for (PetscInt k = 0; k < it; k++) *PG_HH(k, it - 1) /= sc;
+          *PG_HH(it - 1, it - 1) /= sc;
+        }
+      }
+      if (it > 0) {
+        for (PetscInt k = 0; k < it + 1; k++) {
+          pg->work[k] = 0;
+          for (PetscInt j = PetscMax(k - 1, 0); j < it - 1; j++) pg->work[k] -= *PG_HES(k, j) * *PG_HH(j, it - 1);
+        }
+        PetscCall(VecMAXPY(Znext, it + 1, pg->work, vv));
+        PetscCall(VecAXPY(Znext, -*PG_HH(it - 1, it - 1), Zcur));
+        for (PetscInt k = 0; k < it; k++) pg->work[k] = -*PG_HH(k, it - 1);
+        PetscCall(VecMAXPY(Zcur, it, pg->work, vv));
+        PetscCall(PG_NormBegin(pg, dev, vv[it]));
+      }
+      PetscCall(PG_MDotBegin(pg, dev, Znext, it + 1, it));
+    }
+    PetscCall(PG_ReductionsEnd(pg)); /* nothing may stay in flight across a restart */
+    itcount += PetscMax(it - 1, 0);
+    { /* the correction: back substitution on the rotated Hessenberg, x += VV * y (pgmres.c:176-206) */
+      const PetscInt k = it - 2;
+      if (k >= 0) {
+        pg->nrs[k] = (*PG_HH(k, k) != 0.0) ? pg->grs[k] / *PG_HH(k, k) : 0.0;
+        for (PetscInt kk = k - 1; kk >= 0; kk--) {
+          PetscScalar tt = pg->grs[kk];
+          for (PetscInt j = kk + 1; j <= k; j++) tt -= *PG_HH(kk, j) * pg->nrs[j];
+          pg->nrs[kk] = tt / *PG_HH(kk, kk);
+        }
+        PetscCall(VecSet(temp, 0.0));
+        PetscCall(VecMAXPY(temp, k + 1, pg->nrs, vv));
+        PetscCall(VecAXPY(x, 1.0, temp));
+      }
+    }
+    if (!ksp->reason && ksp->its == ksp->max_it) ksp->reason = KSP_DIVERGED_ITS;
+    if (ksp->reason) PetscCall(PG_Log(ksp, rnorm));
+    if (itcount >= ksp->max_it) {
+      if (!ksp->reason) ksp->reason = KSP_DIVERGED_ITS;
+      break;
+    }
+    guess_zero = PETSC_FALSE;
+  }
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+PETSC_EXTERN PetscErrorCode KSPCreate_PGMRESB200(KSP ksp)
+{
+  KSP_PGMRESB200 *pg;
+  PetscFunctionBegin;
+  PetscCall(PetscNew(&pg));
+  pg->max_k = 30; /* GMRES_DEFAULT_MAXK (gmresimpl.h) */
+  pg->async = PETSC_TRUE;
+  ksp->data = (void *)pg;
+  PetscCall(KSPSetSupportedNorm(ksp, KSP_NORM_PRECONDITIONED, PC_LEFT, 3));
+  ksp->ops->setup          = KSPSetUp_PGMRESB200;
+  ksp->ops->solve          = KSPSolve_PGMRESB200;
+  ksp->ops->reset          = KSPReset_PGMRESB200;
+  ksp->ops->destroy        = KSPDestroy_PGMRESB200;
+  ksp->ops->view           = NULL;
+  ksp->ops->setfromoptions = KSPSetFromOptions_PGMRESB200;
+  ksp->ops->buildsolution  = KSPBuildSolutionDefault;
+  ksp->ops->buildresidual  = KSPBuildResidualDefault;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
 /* ================================================================== PetscSF "b200": PETSCSFBASIC sub-classed for device data
    (SURVEY 8f.4).  VecScatterBegin hands the SF whatever VecGetArray[Read]AndMemType returns (vscat.c:50-51,70-73): for b200 vectors
    that is a device pointer tagged PETSC_MEMTYPE_CUDA.  A PETSc configured with a device back end runs its d_ScatterAnd<Op> kernels
@@ -2543,6 +2842,7 @@ PETSC_EXTERN PetscErrorCode PetscDLLibraryRegister_petscb200plugin(void)
   PetscCall(MatSolverTypeRegister(MATSOLVERB200, MATSEQAIJ, MAT_FACTOR_ICC, MatGetFactor_seqaijb200_b200));
   PetscCall(PCRegister(PCJACOBIB200, PCCreate_JacobiB200));
   PetscCall(KSPRegister(KSPPIPECGB200, KSPCreate_PipeCGB200));
+  PetscCall(KSPRegister(KSPPGMRESB200, KSPCreate_PGMRESB200));
   /* -pc_type jacobi is the fused sub-class unless -b200_keep_pcjacobi (PCRegister replaces an existing name; PCRegister
      itself runs PCRegisterAll first, so the stock entry is already there to be replaced) */
   PetscCall(PetscOptionsGetBool(NULL, NULL, "-b200_keep_pcjacobi", &keep, NULL));

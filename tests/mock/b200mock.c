@@ -273,7 +273,7 @@ int b200VecMDot(b200Handle h, int64_t n, int nv, const double *x, const double *
   for (int j = 0; j < nv; j++) { DEVPTR(y[j]); double s = 0; LOOP s += x[i] * y[j][i]; r[j] = s; }
   return 0;
 }
-int b200VecMDotAsync(b200Handle h, int64_t n, int nv, const double *x, const double *const *y, double *dr) { DEVPTR(dr); return b200VecMDot(h, n, nv, x, y, dr); }
+int b200VecMDotAsync(b200Handle h, int64_t n, int nv, const double *x, const double *const *y, double *dr) { return b200VecMDot(h, n, nv, x, y, dr); } /* dr: device or mapped pinned memory */
 int b200VecMAXPYAsync(b200Handle h, int64_t n, int nv, const double *alpha, const double *const *y, double *x, double *sumsq)
 {
   K1() DEVPTR(x);
@@ -502,6 +502,7 @@ struct b200Event_s {
 int b200EventCreate(b200Event *ev) { *ev = calloc(1, sizeof(**ev)); return 0; }
 int b200EventDestroy(b200Event ev) { free(ev); return 0; }
 int b200EventRecord(b200Handle h, b200Event ev) { (void)h; (void)ev; return 0; }
+int b200EventSynchronize(b200Event ev) { (void)ev; return 0; }
 int b200EventElapsedMs(b200Event a, b200Event b, double *ms) { (void)a; (void)b; *ms = 1.0; return 0; }
 int b200GenLaplace7Nnz(int nx, int ny, int nz, int64_t r0, int64_t r1, int64_t *nnz) { *nnz = ora_lap7_rows_nnz(nx, ny, nz, r0, r1); return 0; }
 int b200GenLaplace7(b200Handle h, int nx, int ny, int nz, int64_t r0, int64_t r1, int *rowptr, int *colidx, double *val)

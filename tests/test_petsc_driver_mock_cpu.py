@@ -62,3 +62,10 @@ def test_e2e_host_buffers_and_ex2_config1():
                                      "ksp_lap5_30_pipecg_jacobi", "ksp_lap27_10_pipecg_icc"])
 def test_real_petsc_ksp_history_vs_reference_fixture(oracle, fixture):
     G.test_real_petsc_ksp_history_vs_reference_fixture(oracle, fixture)
+
+
+@pytest.mark.parametrize("fixture", ["ksp_lap5_30_pgmres_jacobi", "ksp_lap7_12_pgmres_ilu", "ksp_lap5_30_pgmres5_none"])
+def test_pgmresb200_history_vs_reference_pgmres_fixture(oracle, fixture):
+    """The pipelined GMRES registered by the plugin (reductions launched asynchronously into mapped memory, read after an event one
+    iteration later) against the reference's KSPPGMRES fixtures: 1e-12 * r0, same iteration count and reason."""
+    G.test_real_petsc_ksp_history_vs_reference_fixture(oracle, fixture)

@@ -45,6 +45,16 @@ def test_plugin_leaves_cpu_types_untouched():
     a = ex2(base + ["-pc_type", "jacobi", "-ksp_type", "pipecgb200", "-dll_append", PLUGIN])
     b = ex2(base + ["-pc_type", "jacobi", "-ksp_type", "pipecg"])
     assert a.returncode == 0 and last(a) == last(b), a.stdout + a.stderr
+    # the registered pipelined GMRES on host vectors (public Vec interface): the reference's KSPPGMRES history, restarts included
+    for extra in ([], ["-ksp_gmres_restart", "7"]):
+        a = ex2(["-m", "30", "-n", "30", "-pc_type", "jacobi", "-ksp_rtol", "1e-8", "-ksp_monitor", "-ksp_type", "pgmresb200", "-dll_append", PLUGIN] + extra)
+        b = ex2(["-m", "30", "-n", "30", "-pc_type", "jacobi", "-ksp_rtol", "1e-8", "-ksp_monitor", "-ksp_type", "pgmres"] + extra)
+        ha = [float(m) for m in re.findall(r"KSP Residual norm ([0-9.eE+-]+)", a.stdout)]
+        hb = [float(m) for m in re.findall(r"KSP Residual norm ([0-9.eE+-]+)", b.stdout)]
+        assert a.returncode == 0 and len(ha) == len(hb) and len(ha) > 20, a.stdout[-500:] + a.stderr[-500:]
+        assert max(abs(x - y) for x, y in zip(ha, hb)) <= 1e-10 * hb[0]
+        ea, eb = [re.search(r"Norm of error ([0-9.eE+-]+) iterations (\d+)", last(o)).groups() for o in (a, b)]
+        assert ea[1] == eb[1] and abs(float(ea[0]) - float(eb[0])) <= 1e-3 * float(eb[0])
     view = ex2(base + ["-pc_type", "jacobi", "-ksp_view", "-dll_append", PLUGIN]).stdout
     assert re.search(r"type: jacobi", view) and "seqaij" in view and "b200" not in view
 
