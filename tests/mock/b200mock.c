@@ -11,7 +11,7 @@
  * It is NOT a fallback: it is never installed next to the product, never linked by it, carries a different file name, and the
  * product library still fails loudly without a GPU (tests/test_abi_cpu.py::test_no_cpu_fallback_without_gpu).  Functions that are
  * pure host code in the real library (b200MpiaijSplitHost, b200MpiaijBuildGarray, b200IndexedGroupHost, b200HostFree) are not
- * defined here and resolve to the real library.  Multi-rank entry points (Comm / Halo) return PETSC_ERR_SUP.
+ * defined here and resolve to the real library.  Several ranks = several processes whose collectives go through files in /dev/shm (an all-gather of byte strings).
  * ILU(0) / ICC(0) use the oracle's restatements (oracle/liboracle.so), whose layout is the reference's.
  */
 #include <math.h>
@@ -522,23 +522,178 @@ int b200GenLaplace27(b200Handle h, int n, int *rowptr, int *colidx, double *val)
   g_launches++;
   return 0;
 }
-int b200CommBarrier(b200Handle h) { (void)h; return 0; }
 
-/* ---- multi-rank entry points: not in the mock */
-#define NOSUP(name) return fail(B200_ERR_SUP, #name ": the mock library is single-rank")
-int b200CommInitRank(b200Handle h, int n, int r, const void *id) { (void)h; (void)n; (void)r; (void)id; NOSUP(b200CommInitRank); }
-int b200CommAllreduceSum(b200Handle h, double *b, int c) { (void)h; (void)b; (void)c; return 0; }
-int b200CommAllreduceMax(b200Handle h, double *b, int c) { (void)h; (void)b; (void)c; return 0; }
-int b200HaloCreateFromGarray(b200Handle h, int m, int ec, const int *g, int64_t *ranges, b200Halo *halo)
+/* ---- several ranks = several processes: collectives through files in /dev/shm (an all-gather of byte strings; every collective
+   below is built on it).  Correctness only; the order of additions is by rank / plan order like the real library's. */
+#include <sys/stat.h>
+#include <unistd.h>
+static int  g_rank = 0, g_nranks = 1;
+static long g_seq  = 0;
+static char g_dir[256];
+static int allgather_bytes(const void *mine, size_t bytes, char ***all, size_t **sizes)
 {
-  (void)h; (void)g;
-  CHECK(ec == 0, B200_ERR_SUP, "b200HaloCreateFromGarray: the mock library is single-rank (no off-process columns)");
-  ranges[0] = 0; ranges[1] = m;
-  *halo = NULL;
+  char path[512], tmp[512];
+  snprintf(tmp, sizeof tmp, "%s/%ld_%d.tmp", g_dir, g_seq, g_rank);
+  snprintf(path, sizeof path, "%s/%ld_%d", g_dir, g_seq, g_rank);
+  FILE *f = fopen(tmp, "wb");
+  CHECK(f, B200_ERR_LIB, "mock collective: cannot write %s", tmp);
+  if (bytes) fwrite(mine, 1, bytes, f);
+  fclose(f);
+  rename(tmp, path);
+  *all   = calloc((size_t)g_nranks, sizeof(char *));
+  *sizes = calloc((size_t)g_nranks, sizeof(size_t));
+  for (int p = 0; p < g_nranks; p++) {
+    struct stat st;
+    int         spins = 0;
+    snprintf(path, sizeof path, "%s/%ld_%d", g_dir, g_seq, p);
+    while (stat(path, &st) != 0) {
+      usleep(100);
+      CHECK(++spins < 600000, B200_ERR_LIB, "mock collective %ld: rank %d never arrived", g_seq, p); /* 60 s */
+    }
+    (*sizes)[p] = (size_t)st.st_size;
+    (*all)[p]   = malloc((size_t)st.st_size + 1);
+    f           = fopen(path, "rb");
+    if (st.st_size) { size_t got = fread((*all)[p], 1, (size_t)st.st_size, f); (void)got; }
+    fclose(f);
+  }
+  if (g_seq >= 2) { /* everybody has finished collective seq-2 once all files of seq-1 exist, which this rank has seen */
+    snprintf(path, sizeof path, "%s/%ld_%d", g_dir, g_seq - 2, g_rank);
+    unlink(path);
+  }
+  g_seq++;
   return 0;
 }
-int b200HaloDestroy(b200Halo halo) { (void)halo; return 0; }
-int b200HaloBegin(b200Handle h, b200Halo halo, const double *x, double *l) { (void)h; (void)halo; (void)x; (void)l; return 0; }
-int b200HaloEnd(b200Handle h, b200Halo halo) { (void)h; (void)halo; return 0; }
-int b200HaloReduceBegin(b200Handle h, b200Halo halo, const double *l) { (void)h; (void)halo; (void)l; return 0; }
-int b200HaloReduceEnd(b200Handle h, b200Halo halo, double *y) { (void)h; (void)halo; (void)y; return 0; }
+static void free_all(char **all, size_t *sizes)
+{
+  for (int p = 0; p < g_nranks; p++) free(all[p]);
+  free(all);
+  free(sizes);
+}
+int b200CommGetUniqueId(void *id128)
+{
+  unsigned char *b = id128;
+  FILE          *f = fopen("/dev/urandom", "rb");
+  if (f) { size_t got = fread(b, 1, 128, f); (void)got; fclose(f); }
+  return 0;
+}
+int b200CommInitRank(b200Handle h, int n, int r, const void *id)
+{
+  (void)h;
+  const unsigned char *b = id;
+  g_nranks = n; g_rank = r; g_seq = 0;
+  snprintf(g_dir, sizeof g_dir, "/dev/shm/b200mock_%02x%02x%02x%02x%02x%02x%02x%02x", b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
+  mkdir(g_dir, 0700);
+  return 0;
+}
+int b200CommDestroy(b200Handle h) { (void)h; return 0; }
+int b200CommRank(b200Handle h, int *r, int *n) { (void)h; *r = g_rank; *n = g_nranks; return 0; }
+int b200CommBarrier(b200Handle h)
+{
+  (void)h;
+  if (g_nranks == 1) return 0;
+  char **all; size_t *sz;
+  int    rc = allgather_bytes("", 0, &all, &sz);
+  if (!rc) free_all(all, sz);
+  return rc;
+}
+static int allreduce(double *buf, int count, int max)
+{
+  if (g_nranks == 1) return 0;
+  char **all; size_t *sz;
+  int    rc = allgather_bytes(buf, sizeof(double) * (size_t)count, &all, &sz);
+  if (rc) return rc;
+  for (int k = 0; k < count; k++) {
+    double v = ((double *)all[0])[k];
+    for (int p = 1; p < g_nranks; p++) {
+      const double w = ((double *)all[p])[k];
+      v = max ? (w > v ? w : v) : v + w;
+    }
+    buf[k] = v;
+  }
+  free_all(all, sz);
+  return 0;
+}
+int b200CommAllreduceSum(b200Handle h, double *b, int c) { (void)h; return allreduce(b, c, 0); }
+int b200CommAllreduceMax(b200Handle h, double *b, int c) { (void)h; return allreduce(b, c, 1); }
+struct b200Halo_s {
+  int      m, ec, *garray; /* mine */
+  int64_t *ranges;         /* [nranks + 1] */
+  int    **pg, *pec;       /* every rank's garray */
+  char   **red; size_t *redsz; /* lvecs in flight of a reverse scatter */
+};
+int b200HaloCreateFromGarray(b200Handle h, int m, int ec, const int *g, int64_t *ranges, b200Halo *halo)
+{
+  (void)h;
+  if (g_nranks == 1) {
+    CHECK(ec == 0, B200_ERR_ARG_OUTOFRANGE, "garray holds columns that are locally owned or outside the global range");
+    ranges[0] = 0; ranges[1] = m;
+    *halo = NULL;
+    return 0;
+  }
+  b200Halo H = calloc(1, sizeof(*H));
+  char **all; size_t *sz;
+  int    rc = allgather_bytes(&m, sizeof(int), &all, &sz);
+  if (rc) return rc;
+  ranges[0] = 0;
+  for (int p = 0; p < g_nranks; p++) ranges[p + 1] = ranges[p] + *(int *)all[p];
+  free_all(all, sz);
+  H->m = m; H->ec = ec;
+  H->garray = malloc(sizeof(int) * ((size_t)ec + 1)); memcpy(H->garray, g, sizeof(int) * (size_t)ec);
+  H->ranges = malloc(sizeof(int64_t) * ((size_t)g_nranks + 1)); memcpy(H->ranges, ranges, sizeof(int64_t) * ((size_t)g_nranks + 1));
+  rc = allgather_bytes(g, sizeof(int) * (size_t)ec, &all, &sz);
+  if (rc) return rc;
+  H->pg = calloc((size_t)g_nranks, sizeof(int *)); H->pec = calloc((size_t)g_nranks, sizeof(int));
+  for (int p = 0; p < g_nranks; p++) {
+    H->pec[p] = (int)(sz[p] / sizeof(int));
+    H->pg[p]  = malloc(sz[p] + 4); memcpy(H->pg[p], all[p], sz[p]);
+  }
+  free_all(all, sz);
+  for (int q = 0; q < ec; q++) CHECK(g[q] < ranges[g_rank] || g[q] >= ranges[g_rank + 1], B200_ERR_ARG_OUTOFRANGE, "garray holds a locally owned column");
+  *halo = H;
+  return 0;
+}
+int b200HaloDestroy(b200Halo H)
+{
+  if (!H) return 0;
+  for (int p = 0; p < g_nranks; p++) free(H->pg[p]);
+  free(H->pg); free(H->pec); free(H->garray); free(H->ranges); free(H);
+  return 0;
+}
+int b200HaloBegin(b200Handle h, b200Halo H, const double *x, double *lvec)
+{
+  (void)h;
+  if (!H) return 0;
+  char **all; size_t *sz;
+  int    rc = allgather_bytes(x, sizeof(double) * (size_t)H->m, &all, &sz);
+  if (rc) return rc;
+  for (int q = 0, p = 0; q < H->ec; q++) {
+    while (H->garray[q] >= H->ranges[p + 1]) p++;
+    lvec[q] = ((double *)all[p])[H->garray[q] - H->ranges[p]];
+  }
+  free_all(all, sz);
+  g_launches++;
+  return 0;
+}
+int b200HaloEnd(b200Handle h, b200Halo H) { (void)h; (void)H; return 0; }
+int b200HaloReduceBegin(b200Handle h, b200Halo H, const double *lvec)
+{
+  (void)h;
+  if (!H) return 0;
+  return allgather_bytes(lvec, sizeof(double) * (size_t)H->ec, &H->red, &H->redsz);
+}
+int b200HaloReduceEnd(b200Handle h, b200Halo H, double *y)
+{
+  (void)h;
+  if (!H) return 0;
+  for (int p = 0; p < g_nranks; p++) { /* peer after peer in plan order, a peer's entries in its garray order */
+    if (p == g_rank) continue;
+    for (int q = 0; q < H->pec[p]; q++) {
+      const int c = H->pg[p][q];
+      if (c >= H->ranges[g_rank] && c < H->ranges[g_rank + 1]) y[c - H->ranges[g_rank]] += ((double *)H->red[p])[q];
+    }
+  }
+  free_all(H->red, H->redsz);
+  H->red = NULL;
+  g_launches++;
+  return 0;
+}
