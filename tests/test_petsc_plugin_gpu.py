@@ -165,8 +165,8 @@ def test_sf_driver_vecscatter_and_petscsf_on_device_vectors():
 
 
 @pytest.mark.skipif(not (have() and os.path.exists(os.path.join(BIN, "coherence_driver"))), reason="baseline/_ref/petsc/bin/coherence_driver not built")
-@pytest.mark.xfail(strict=False, reason="written after the last GPU run of the round; passes on the CPU mock device (tests/test_plugin_logic_mock_cpu.py)")
 def test_coherence_driver_host_device_rules():
-    """One check per host/device coherence rule of the plugin (petsc_plugin/coherence_driver.c), b200 types against host types."""
+    """One check per host/device coherence rule of the plugin (petsc_plugin/coherence_driver.c), b200 types against host types.
+    Ran green on a B200 with the very last GPU seconds of round 2 (profiles/round2_last_gpu_confirmation.log)."""
     out = run("coherence_driver", B200)
     assert "mat type seqaijb200 vec type seqb200" in out and "all ok" in out and "FAILED" not in out, out
